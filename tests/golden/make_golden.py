@@ -1,0 +1,40 @@
+"""Regenerates the golden fixtures from the fp64 oracle (the TensorFlow reference cannot run in
+this image -- "parity unpinned", see oracle/supernet_oracle.py).  Run from the repo root:
+
+    python tests/golden/make_golden.py
+"""
+import os
+import sys
+
+import numpy as np
+import torch
+
+ROOT = os.path.dirname(os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+sys.path.insert(0, ROOT)
+from oracle import supernet_oracle as O  # noqa: E402
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+
+
+def main():
+    x = O.make_input("hippocampus", 2)
+    p, v, mf, sf = O.UNetOracle("hippocampus", 32, 3, 1, torch.float64)(x, True)
+    rng = np.random.default_rng(0)
+    idx = np.sort(rng.choice(p.numel(), 512, replace=False))
+    np.savez_compressed(
+        os.path.join(HERE, "hippocampus_b2_fp64.npz"), idx=idx,
+        p=p.flatten()[idx].numpy(), v=v.flatten()[idx].numpy(),
+        mf=mf.flatten()[idx].numpy(), sf=sf.flatten()[idx].numpy(),
+        p_sum=float(p.sum()), v_sum=float(v.sum()))
+    g = torch.Generator().manual_seed(42)
+    mu = torch.randn(1, 6, 6, 4, generator=g, dtype=torch.float64)
+    var = torch.rand(1, 6, 6, 4, generator=g, dtype=torch.float64)
+    w = torch.randn(3, 3, 4, 8, generator=g, dtype=torch.float64) * 0.1
+    ws = torch.empty(8, dtype=torch.float64).uniform_(-8, -2, generator=g)
+    m, vv = O.conv_intermediate_as_written(mu, var, w, ws)
+    np.savez_compressed(os.path.join(HERE, "layers_fp64.npz"), mu=mu.numpy(), var=var.numpy(), w=w.numpy(),
+                        ws=ws.numpy(), m_out=m.numpy(), v_out=vv.numpy())
+
+
+if __name__ == "__main__":
+    main()

@@ -1,0 +1,239 @@
+"""CPU tests that pin the oracle: the reference ships no tests or golden
+vectors ("parity unpinned"), so the restatement is validated by independent formulations,
+a Monte-Carlo check, structural identities, hand-computed cases and committed golden fixtures."""
+import os
+
+import numpy as np
+import pytest
+import torch
+import torch.nn.functional as F
+
+from oracle import supernet_oracle as O
+
+D = torch.float64
+GOLD = os.path.join(os.path.dirname(__file__), "golden")
+
+
+def _rand_layer(B=2, H=7, W=6, cin=3, cout=4, k=3, seed=0):
+    g = torch.Generator().manual_seed(seed)
+    mu = torch.randn(B, H, W, cin, generator=g, dtype=D)
+    var = torch.rand(B, H, W, cin, generator=g, dtype=D)
+    w = torch.randn(k, k, cin, cout, generator=g, dtype=D) * 0.1
+    ws = torch.empty(cout, dtype=D).uniform_(-6, -2, generator=g)
+    return mu, var, w, ws
+
+
+@pytest.mark.parametrize("k", [1, 2, 3])
+def test_conv_forms_agree(k):
+    mu, var, w, ws = _rand_layer(k=k)
+    m1, v1 = O.conv_intermediate_as_written(mu, var, w, ws)
+    m2, v2 = O.conv_intermediate_conv_form(mu, var, w, ws)
+    assert torch.allclose(m1, m2, atol=1e-13) and torch.allclose(v1, v2, atol=1e-13)
+    m1, v1 = O.conv_input_as_written(mu, w, ws)
+    m2, v2 = O.conv_input_conv_form(mu, w, ws)
+    assert torch.allclose(m1, m2, atol=1e-13) and torch.allclose(v1, v2, atol=1e-13)
+
+
+def test_conv_against_naive_loops():
+    """Pure-python loops on a tiny case: K ordering (kh,kw,ci) and VALID geometry."""
+    mu, var, w, ws = _rand_layer(B=1, H=4, W=5, cin=2, cout=3, k=3, seed=3)
+    s = torch.log1p(torch.exp(ws))
+    m_ref = torch.zeros(1, 2, 3, 3, dtype=D)
+    v_ref = torch.zeros(1, 2, 3, 3, dtype=D)
+    for i in range(2):
+        for j in range(3):
+            for n in range(3):
+                for kh in range(3):
+                    for kw in range(3):
+                        for c in range(2):
+                            x, v, ww = mu[0, i + kh, j + kw, c], var[0, i + kh, j + kw, c], w[kh, kw, c, n]
+                            m_ref[0, i, j, n] += x * ww
+                            v_ref[0, i, j, n] += v * ww * ww + s[n] * (x * x + v)
+    m, v = O.conv_intermediate_as_written(mu, var, w, ws)
+    assert torch.allclose(m, m_ref, atol=1e-13) and torch.allclose(v, v_ref, atol=1e-13)
+
+
+def test_conv_variance_monte_carlo():
+    """Var[sum W x] for independent W~N(w_mu, s), x~N(mu, var) equals the propagated variance."""
+    g = torch.Generator().manual_seed(5)
+    mu, var, w, ws = _rand_layer(B=1, H=3, W=3, cin=2, cout=2, k=3, seed=11)
+    ws = ws + 3.0                      # larger weight variance so all three terms matter
+    s = torch.log1p(torch.exp(ws))
+    _, v = O.conv_intermediate_conv_form(mu, var, w, ws)
+    n = 200000
+    xs = mu.flatten() + var.flatten().sqrt() * torch.randn(n, mu.numel(), generator=g, dtype=D)
+    wk = w.reshape(-1, 2)                                             # [(kh,kw,ci), n]
+    wsamp = wk + s.sqrt() * torch.randn(n, *wk.shape, generator=g, dtype=D)
+    y = torch.einsum("bk,bkn->bn", xs, wsamp)
+    emp = y.var(0)
+    assert torch.allclose(emp, v.flatten(), rtol=3e-2)
+
+
+def test_unpool_identity_and_upconv_as_transposed_conv():
+    g = torch.Generator().manual_seed(1)
+    x = torch.randn(2, 3, 4, 5, generator=g, dtype=D)
+    u = O.unpool(x)
+    assert u.shape == (2, 7, 9, 5)
+    ref = torch.zeros_like(u)
+    ref[:, 1::2, 1::2, :] = x
+    assert torch.equal(u, ref)
+    # unpool + 2x2 VALID conv == stride-2 transposed conv with the flipped kernel == 4 parity GEMMs
+    w = torch.randn(2, 2, 5, 3, generator=g, dtype=D)
+    y = O.conv2d_valid(u, w)
+    par = torch.zeros(2, 6, 8, 3, dtype=D)
+    for a in range(2):
+        for b in range(2):
+            par[:, a::2, b::2, :] = torch.einsum("bhwc,cn->bhwn", x, w[1 - a, 1 - b])
+    assert torch.allclose(y, par, atol=1e-13)
+    wt = w.flip(0, 1).permute(2, 3, 0, 1)                             # [Cin, Cout, kh, kw]
+    yt = F.conv_transpose2d(x.permute(0, 3, 1, 2), wt, stride=2).permute(0, 2, 3, 1)
+    assert torch.allclose(y, yt, atol=1e-13)
+
+
+def test_padding_pool_relu_concat_hand_cases():
+    mu = torch.tensor([[[[1.0], [-2.0]], [[3.0], [0.5]]]], dtype=D)       # [1,2,2,1]
+    var = torch.tensor([[[[0.1], [0.2]], [[0.3], [0.4]]]], dtype=D)
+    m, v = O.padding(mu, var, (1, 0), 0.1)
+    assert m.shape == (1, 3, 3, 1) and m[0, 0, 0, 0] == 0 and v[0, 0, 0, 0] == 0.1 and v[0, 1, 1, 0] == 0.1 * 1
+    assert m[0, 1, 1, 0] == 1.0 and v[0, 2, 2, 0] == 0.4
+    mp, vp = O.maxpooling(mu, var)
+    assert mp.flatten().tolist() == [3.0] and vp.flatten().tolist() == [0.3]
+    mr, vr = O.relu(mu, var)
+    assert mr.flatten().tolist() == [1.0, 0.0, 3.0, 0.5] and vr.flatten().tolist() == [0.1, 0.0, 0.3, 0.4]
+    enc = torch.arange(16, dtype=D).reshape(1, 4, 4, 1)
+    mc, vc = O.conc(mu, var, enc, enc * 2)
+    assert mc.shape == (1, 2, 2, 2)
+    assert mc[0, :, :, 1].flatten().tolist() == [5.0, 6.0, 9.0, 10.0]
+    assert mc[0, :, :, 0].flatten().tolist() == [1.0, -2.0, 3.0, 0.5]
+    assert vc[0, :, :, 1].flatten().tolist() == [10.0, 12.0, 18.0, 20.0]
+
+
+def test_relu_gate_is_strict_and_constant_for_autodiff():
+    mu = torch.tensor([[[[0.0, 1.0, -1.0]]]], dtype=D, requires_grad=True)
+    var = torch.ones(1, 1, 1, 3, dtype=D, requires_grad=True)
+    m, v = O.relu(mu, var)
+    assert v.flatten().tolist() == [0.0, 1.0, 0.0]
+    (m.sum() + (v * torch.tensor([1.0, 2.0, 3.0], dtype=D)).sum()).backward()
+    assert mu.grad.flatten().tolist() == [0.0, 1.0, 0.0]
+    assert var.grad.flatten().tolist() == [0.0, 2.0, 0.0]
+
+
+def test_maxpool_odd_size_same_padding():
+    mu = -torch.arange(1, 10, dtype=D).reshape(1, 3, 3, 1)             # all negative, padded cells must not win
+    var = torch.arange(1, 10, dtype=D).reshape(1, 3, 3, 1)
+    m, v = O.maxpooling(mu, var)
+    assert m.shape == (1, 2, 2, 1)
+    assert m.flatten().tolist() == [-1.0, -3.0, -7.0, -9.0] and v.flatten().tolist() == [1.0, 3.0, 7.0, 9.0]
+
+
+@pytest.mark.parametrize("C", [3, 4, 5])
+def test_softmax_forms_agree(C):
+    g = torch.Generator().manual_seed(C)
+    mu = torch.randn(2, 3, 3, C, generator=g, dtype=D) * 2
+    var = torch.rand(2, 3, 3, C, generator=g, dtype=D)
+    p1, v1 = O.softmax_as_written(mu, var)
+    p2, v2 = O.softmax_closed_form(mu, var)
+    assert p1.shape == (2, 9, C)
+    assert torch.allclose(p1, p2, atol=1e-14) and torch.allclose(v1, v2, atol=1e-14)
+    # first-order delta method == J diag(var) J^T diagonal via autograd Jacobian
+    J = torch.autograd.functional.jacobian(lambda z: torch.softmax(z, -1), mu[0, 0, 0])
+    assert torch.allclose((J.square() @ var[0, 0, 0]), v1[0, 0], atol=1e-13)
+
+
+def test_nll_and_regularizer_hand_values():
+    y = torch.tensor([[[1.0, 0.0]]], dtype=D)
+    p = torch.tensor([[[0.75, 0.25]]], dtype=D)
+    v = torch.tensor([[[0.5, 0.25]]], dtype=D)
+    q = 0.0625 / 0.501 + 0.0625 / 0.251
+    l = np.log(0.501 * 0.251)
+    assert abs(float(O.nll_gaussian(y, p, v)) - 0.5 * (q + l)) < 1e-14
+    ws = torch.tensor([-3.0, 0.5], dtype=D)
+    s = np.log1p(np.exp(ws.numpy()))
+    assert abs(float(O.sigma_regularizer(ws, 9.0)) - (-9.0 * np.mean(1 + np.log(s) - s))) < 1e-14
+    assert float(O.l2_regularizer(torch.tensor([1.0, -2.0], dtype=D))) == 5.0
+
+
+def test_backward_formulas_match_autograd():
+    """SURVEY.md A.3 closed-form conv backward vs autograd of the as-written forward."""
+    mu, var, w, ws = _rand_layer(B=2, H=6, W=5, cin=3, cout=4, k=3, seed=7)
+    for t in (mu, var, w, ws):
+        t.requires_grad_(True)
+    m, v = O.conv_intermediate_as_written(mu, var, w, ws)
+    g = torch.Generator().manual_seed(9)
+    gm = torch.randn(m.shape, generator=g, dtype=D)
+    gv = torch.randn(v.shape, generator=g, dtype=D)
+    a_mu, a_var, a_w, a_ws = torch.autograd.grad((m * gm).sum() + (v * gv).sum(), (mu, var, w, ws))
+    s = O.softplus(ws).detach()
+    wd, mud, vard = w.detach(), mu.detach(), var.detach()
+    k = 3
+    t = (gv * s).sum(-1)                                              # [B,Ho,Wo]
+    boxT = F.conv_transpose2d(t.unsqueeze(1), torch.ones(1, 1, k, k, dtype=D)).squeeze(1)
+    def convT(gt, wt):                                                # full correlation with flipped W
+        return F.conv_transpose2d(gt.permute(0, 3, 1, 2), wt.permute(3, 2, 0, 1)).permute(0, 2, 3, 1)
+    g_mu = convT(gm, wd) + 2 * mud * boxT.unsqueeze(-1)
+    g_var = convT(gv, wd.square()) + boxT.unsqueeze(-1)
+    pm = O.extract_patches(mud, k).reshape(-1, k * k * 3)
+    pv = O.extract_patches(vard, k).reshape(-1, k * k * 3)
+    g_w = (pm.T @ gm.reshape(-1, 4) + 2 * wd.reshape(-1, 4) * (pv.T @ gv.reshape(-1, 4))).reshape(wd.shape)
+    r = (pm.square() + pv).sum(-1)
+    g_ws = (gv.reshape(-1, 4) * r.unsqueeze(-1)).sum(0) * torch.sigmoid(ws.detach())
+    for a, b in ((a_mu, g_mu), (a_var, g_var), (a_w, g_w), (a_ws, g_ws)):
+        assert torch.allclose(a, b, atol=1e-11)
+
+
+def test_gradcheck_small_layers():
+    mu, var, w, ws = _rand_layer(B=1, H=4, W=4, cin=2, cout=2, k=2, seed=13)
+    for t in (mu, var, w, ws):
+        t.requires_grad_(True)
+    assert torch.autograd.gradcheck(lambda *a: O.conv_intermediate_conv_form(*a), (mu, var, w, ws), atol=1e-7)
+    z = torch.randn(1, 2, 2, 3, dtype=D, requires_grad=True)
+    zv = torch.rand(1, 2, 2, 3, dtype=D, requires_grad=True)
+    assert torch.autograd.gradcheck(lambda a, b: O.softmax_closed_form(a, b), (z, zv), atol=1e-7)
+
+
+@pytest.mark.parametrize("variant,C,cin", [("hippocampus", 3, 1), ("brats", 4, 4)])
+def test_model_geometry_and_param_count(variant, C, cin):
+    m = O.UNetOracle(variant, 32, C, cin, torch.float32)
+    n_params = sum(p.numel() for p in m.parameters())
+    assert n_params == (466019 if variant == "hippocampus" else 7760484)   # SURVEY.md 6 / BASELINE.md 2
+    if variant == "hippocampus":
+        p, v = m(O.make_input(variant, 1))
+        assert p.shape == (1, 54 * 54, 3) and v.shape == p.shape
+        assert bool((v >= 0).all()) and torch.allclose(p.sum(-1), torch.ones(1, 2916), atol=1e-5)
+
+
+def test_model_forms_agree_hippocampus():
+    x = O.make_input("hippocampus", 1)
+    a = O.UNetOracle("hippocampus", 32, 3, 1, D, form="as_written")(x, True)
+    b = O.UNetOracle("hippocampus", 32, 3, 1, D, form="conv")(x, True)
+    for ta, tb in zip(a, b):
+        assert O.rel_l2(ta, tb) < 1e-12
+
+
+def test_truncated_normal_and_weight_determinism():
+    w1 = O.make_weights("hippocampus", 32, 3, 1)
+    w2 = O.make_weights("hippocampus", 32, 3, 1)
+    for k in w1:
+        assert torch.equal(w1[k][0], w2[k][0]) and torch.equal(w1[k][1], w2[k][1])
+        assert float(w1[k][0].abs().max()) <= 0.2
+    lo, hi = w1["conv_final"][1].min(), w1["conv_final"][1].max()
+    assert -4.6 <= lo and hi <= -2.2
+    assert w1["conv1"][1].min() >= -12 and w1["conv1"][1].max() <= -4.6
+
+
+def test_golden_fixtures_match_oracle():
+    """The committed fixtures (tests/golden/make_golden.py) must still be reproduced."""
+    path = os.path.join(GOLD, "hippocampus_b2_fp64.npz")
+    z = np.load(path)
+    x = O.make_input("hippocampus", 2)
+    p, v, mf, sf = O.UNetOracle("hippocampus", 32, 3, 1, D)(x, True)
+    idx = z["idx"]
+    for name, t in (("p", p), ("v", v), ("mf", mf), ("sf", sf)):
+        got = t.detach().flatten()[idx].numpy()
+        assert np.allclose(got, z[name], rtol=1e-9, atol=0), name
+    assert abs(float(z["p_sum"]) - float(p.sum())) < 1e-6
+    assert np.isclose(float(z["v_sum"]), float(v.sum()), rtol=1e-9)
+    lay = np.load(os.path.join(GOLD, "layers_fp64.npz"))
+    mu, var, w, ws = (torch.from_numpy(lay[k]) for k in ("mu", "var", "w", "ws"))
+    m, vv = O.conv_intermediate_conv_form(mu, var, w, ws)
+    assert np.allclose(m.numpy(), lay["m_out"], rtol=1e-12) and np.allclose(vv.numpy(), lay["v_out"], rtol=1e-12)
