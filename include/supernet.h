@@ -1,0 +1,146 @@
+/* supernet.h -- C ABI of libsupernet_b200.so: the SUPER-Net moment-propagation hot path on B200 (sm_100a).
+ *
+ * The reference (/root/reference, TensorFlow/Keras) has no plugin/FFI boundary: the path sits behind
+ * Keras Layer.__call__ with a (mean, sigma) -> (mean, sigma) surface, "sigma" being the VARIANCE
+ * (SURVEY.md 0.3, 8b).  This header is the boundary a binding for those layers would call; each entry
+ * point cites the reference interface it replaces (file:line into /root/reference).
+ *
+ * Conventions
+ *   - plain C: POD structs, raw device pointers, sizes; no C++/torch types; nothing throws.
+ *   - every function returns SN_OK (0) or a negative sn_status; sn_last_error() gives the thread-local text.
+ *   - all work is enqueued on the caller's stream (sn_stream_t == cudaStream_t), asynchronously; no
+ *     host synchronisation, no device allocation (the caller owns every buffer, workspace included),
+ *     so a sequence of calls is CUDA-graph capturable.  No pointer is retained after return.
+ *   - there is NO CPU fallback and no alternate backend: unsupported configurations are errors.
+ *   - "f32" tensors: NHWC contiguous float (the reference's layout); weights HWIO
+ *     [k,k,Cin,Cout] float (Brats.py:55,108), w_sigma is the RAW pre-softplus [Cout] vector (Brats.py:59-63).
+ *   - "packed" tensors (FAST mode): three bf16 planes [3][B][H][W][C]: plane 0 = mean_hi, plane 1 = mean_lo
+ *     (mean = hi + lo, ~16 mantissa bits), plane 2 = variance.  Written by the producing kernel's epilogue,
+ *     consumed directly by TMA -> tcgen05 (DESIGN.md "data layout").
+ */
+#ifndef SUPERNET_B200_H_
+#define SUPERNET_B200_H_
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define SN_ABI_VERSION 1
+
+typedef void* sn_stream_t; /* cudaStream_t */
+
+typedef enum sn_status {
+  SN_OK = 0,
+  SN_ERR_BAD_ARG = -1,      /* null pointer, non-positive size, inconsistent geometry          */
+  SN_ERR_UNSUPPORTED = -2,  /* valid but not implemented (e.g. stride != 1, k > 3 on the TC path) */
+  SN_ERR_MISALIGNED = -3,   /* pointer / channel count violates a 16-byte TMA/vector requirement */
+  SN_ERR_ARCH = -4,         /* device is not sm_100                                             */
+  SN_ERR_LAUNCH = -5,       /* CUDA launch/runtime error                                        */
+  SN_ERR_DRIVER = -6        /* tensor-map encode (driver entry point) failed                    */
+} sn_status;
+
+enum { SN_CONV_RELU = 1 };  /* fuse the ReLU moment gate (Brats.py:233-238) into the conv epilogue */
+
+int sn_version(void);
+const char* sn_last_error(void);
+/* SN_OK when the current device can run the kernels (compute capability 10.x). */
+int sn_device_check(void);
+
+/* ------------------------------------------------------------------------------------------------
+ * FP32 mode (CUDA-core implicit GEMM, fp32 operands and accumulation; parity bar 1e-5).
+ * ------------------------------------------------------------------------------------------------ */
+
+/* Geometry of one stride-1 VALID moment convolution (the only mode the reference uses, Brats.py:37,89). */
+typedef struct sn_conv_desc {
+  int32_t batch, in_h, in_w, cin, cout, ksize;
+  int32_t flags; /* SN_CONV_* */
+  int32_t reserved;
+} sn_conv_desc;
+
+/* myConv_input.call (Brats.py:65-76) when var_in == NULL, myConv_intermediate.call (Brats.py:118-137)
+ * otherwise:  mu_out = mu_in (*) W ;  var_out = var_in (*) W^2 + softplus(w_sigma)[n] * box_k(sum_c mu_in^2 + var_in).
+ * rsum_out (optional, [B,Ho,Wo]) receives box_k(sum_c mu^2+var), which bwd_weight needs.
+ * With SN_CONV_RELU the outputs are post-ReLU (Brats.py:233-238) and relu_mask-free: the gate is mu_out > 0. */
+int sn_conv_moments_fwd(const sn_conv_desc* d, const float* mu_in, const float* var_in, const float* w_mu,
+                        const float* w_sigma, float* mu_out, float* var_out, float* rsum_out, sn_stream_t st);
+
+/* Data gradient of the above (what tf.GradientTape derives at Brats.py:578,593):
+ *   g_mu_in = g_mu_out (*)^T W + 2 mu_in . box^T(t),  g_var_in = g_var_out (*)^T W^2 + box^T(t),  t = sum_n g_var_out s_n.
+ * g_var_in may be NULL (first layer: the input is deterministic).  flags must not contain SN_CONV_RELU. */
+int sn_conv_moments_bwd_data(const sn_conv_desc* d, const float* g_mu_out, const float* g_var_out,
+                             const float* mu_in, const float* w_mu, const float* w_sigma, float* g_mu_in,
+                             float* g_var_in, sn_stream_t st);
+
+/* Weight gradient:  g_w_mu = corr(mu_in, g_mu_out) + 2 W . corr(var_in, g_var_out);
+ *   g_w_sigma[n] = sigmoid(w_sigma[n]) * sum_p g_var_out[p,n] * rsum[p].   Outputs are overwritten.
+ * var_in may be NULL (first layer). */
+int sn_conv_moments_bwd_weight(const sn_conv_desc* d, const float* mu_in, const float* var_in,
+                               const float* g_mu_out, const float* g_var_out, const float* rsum,
+                               const float* w_mu, const float* w_sigma, float* g_w_mu, float* g_w_sigma,
+                               sn_stream_t st);
+
+/* myReLU.call + grad_ReLU (Brats.py:220-238): mu_out = max(mu,0), var_out = var * 1[mu > 0]. In-place allowed. */
+int sn_relu_moments_fwd(size_t n, const float* mu, const float* var, float* mu_out, float* var_out, sn_stream_t st);
+/* g_* _in = g_* _out * 1[mu_in > 0] (the gate is a constant for autodiff). */
+int sn_relu_moments_bwd(size_t n, const float* mu_in, const float* g_mu_out, const float* g_var_out,
+                        float* g_mu_in, float* g_var_in, sn_stream_t st);
+
+/* mymaxpooling.call + get_pooled (Brats.py:171-174,206-216): 2x2/2 SAME max-pool of the mean, variance taken at
+ * the arg-max.  Output is [B,ceil(H/2),ceil(W/2),C].  argmax_out (optional) stores the 2-bit window position
+ * (dy*2+dx) per output element instead of TF's flat int64 index. */
+int sn_maxpool2_moments_fwd(int32_t batch, int32_t h, int32_t w, int32_t c, const float* mu, const float* var,
+                            float* mu_out, float* var_out, uint8_t* argmax_out, sn_stream_t st);
+/* Routes both gradients to the stored arg-max position; g_*_in ([B,H,W,C]) are fully overwritten. */
+int sn_maxpool2_moments_bwd(int32_t batch, int32_t h, int32_t w, int32_t c, const uint8_t* argmax,
+                            const float* g_mu_out, const float* g_var_out, float* g_mu_in, float* g_var_in,
+                            sn_stream_t st);
+
+/* Strided window copy:
+ *   dst[b, dst_y0 + dst_step*y, dst_x0 + dst_step*x, dst_c0 + ch] = src[b, src_y0 + src_step*y, src_x0 + src_step*x, src_c0 + ch]
+ * for y < h, x < w, ch < c.  One primitive behind unpool (Brats.py:178-203: dst_step 2, dst offset 1), mypadding
+ * (Brats.py:159-163, after sn_fill), crop_tensor + concat (Brats_functions.py:518-526, Brats.py:257-260) and all
+ * of their adjoints (the adjoint of unpool reads with src_step 2). */
+typedef struct sn_window {
+  int32_t batch, h, w, c;                                  /* window extent */
+  int32_t src_h, src_w, src_c, src_y0, src_x0, src_c0;      /* full source dims and window origin */
+  int32_t dst_h, dst_w, dst_c, dst_y0, dst_x0, dst_c0;      /* full destination dims and window origin */
+  int32_t dst_step;                                        /* 1, or 2 for zero-stuffing */
+  int32_t src_step;                                        /* 1 (0 is read as 1), or 2 for the adjoint of zero-stuffing */
+} sn_window;
+int sn_window_copy(const sn_window* win, const float* src, float* dst, sn_stream_t st);
+int sn_fill(float* dst, size_t n, float value, sn_stream_t st);
+
+/* mysoftmax.call (Brats.py:269-283) on [rows, C] (rows = B*H*W, C <= 8):
+ *   p = softmax(mu);  var_out_i = sum_j (p_i (delta_ij - p_j))^2 var_j. */
+int sn_softmax_moments_fwd(size_t rows, int32_t c, const float* mu, const float* var, float* p_out,
+                           float* var_out, sn_stream_t st);
+/* VJP of both outputs w.r.t. both inputs. */
+int sn_softmax_moments_bwd(size_t rows, int32_t c, const float* p, const float* var_in, const float* g_p,
+                           const float* g_var_out, float* g_mu, float* g_var_in, sn_stream_t st);
+
+/* nll_gaussian (Brats.py:293-311) applied to clip(var, clip_lo, clip_hi) (Brats.py:573-574: [1e-12,1e3];
+ * Brats.py:588-589: [-1e4,1e3]).  acc: 2 doubles of caller workspace (zeroed by the call); loss_out: 1 float:
+ *   0.5 * ( finite_or_0( mean_rows sum_c (p-y)^2/(v+1e-3) ) + mean_rows log prod_c (v+1e-3) ). */
+int sn_nll_gaussian_fwd(size_t rows, int32_t c, const float* y, const float* p, const float* var, float clip_lo,
+                        float clip_hi, double* acc, float* loss_out, sn_stream_t st);
+/* Gradients w.r.t. p and the UNclipped var (zero outside [clip_lo, clip_hi]); g_loss is a device scalar;
+ * acc is the workspace filled by the forward (needed for the NaN/Inf -> 0 rule). */
+int sn_nll_gaussian_bwd(size_t rows, int32_t c, const float* y, const float* p, const float* var, float clip_lo,
+                        float clip_hi, const double* acc, const float* g_loss, float* g_p, float* g_var,
+                        sn_stream_t st);
+
+/* One conv's contribution to add_n(model.losses) (Brats.py:575): l2(1.)(w_mu) (Brats.py:56,109) plus
+ * sigma_regularizer(k*k)(w_sigma) (Brats.py:314-320).  Accumulates into *acc (double, caller-zeroed). */
+int sn_kl_regularizer_fwd(const float* w_mu, size_t n_w, const float* w_sigma, int32_t cout, int32_t ksize,
+                          double* acc, sn_stream_t st);
+/* g_w_mu += scale * 2 w_mu ;  g_w_sigma[n] += scale * (-k^2/cout) (1/s_n - 1) sigmoid(w_sigma[n]). */
+int sn_kl_regularizer_bwd(const float* w_mu, size_t n_w, const float* w_sigma, int32_t cout, int32_t ksize,
+                          float scale, float* g_w_mu, float* g_w_sigma, sn_stream_t st);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* SUPERNET_B200_H_ */
