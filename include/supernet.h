@@ -14,9 +14,9 @@
  *   - there is NO CPU fallback and no alternate backend: unsupported configurations are errors.
  *   - "f32" tensors: NHWC contiguous float (the reference's layout); weights HWIO
  *     [k,k,Cin,Cout] float (Brats.py:55,108), w_sigma is the RAW pre-softplus [Cout] vector (Brats.py:59-63).
- *   - "packed" tensors (FAST mode): three bf16 planes [3][B][H][W][C]: plane 0 = mean_hi, plane 1 = mean_lo
- *     (mean = hi + lo, ~16 mantissa bits), plane 2 = variance.  Written by the producing kernel's epilogue,
- *     consumed directly by TMA -> tcgen05 (DESIGN.md "data layout").
+ *   - "packed" tensors (FAST mode): bf16 [B][H][W][3][C]: per pixel the planes mean_hi, mean_lo (mean = hi + lo,
+ *     ~16 mantissa bits) and variance.  Written by the producing kernel's epilogue, consumed directly by
+ *     TMA -> tcgen05 (DESIGN.md "data layout").
  */
 #ifndef SUPERNET_B200_H_
 #define SUPERNET_B200_H_
@@ -139,6 +139,75 @@ int sn_kl_regularizer_fwd(const float* w_mu, size_t n_w, const float* w_sigma, i
 /* g_w_mu += scale * 2 w_mu ;  g_w_sigma[n] += scale * (-k^2/cout) (1/s_n - 1) sigmoid(w_sigma[n]). */
 int sn_kl_regularizer_bwd(const float* w_mu, size_t n_w, const float* w_sigma, int32_t cout, int32_t ksize,
                           float scale, float* g_w_mu, float* g_w_sigma, sn_stream_t st);
+
+/* ------------------------------------------------------------------------------------------------
+ * FAST mode (inference): tcgen05 / TMEM implicit GEMM fed by TMA im2col tiles; the mean is carried as a
+ * bf16 hi/lo pair (3 UMMAs: hi*Whi + lo*Whi + hi*Wlo, ~2^-16 relative), the variance as one bf16
+ * (1 UMMA against bf16(W^2)), fp32 accumulation in TMEM, variance clamped >= 0 in the epilogue.
+ *
+ * "packed" moment tensor: [n][h][w][3][c] bf16 -- per pixel the three planes mean_hi, mean_lo, variance,
+ * each c channels (c % 32 == 0 for tensors the tensor-core conv reads).  A sn_packed_view addresses a
+ * window of such a buffer, which is how mypadding (Brats.py:159-163), crop_tensor + concat
+ * (Brats_functions.py:518-526, Brats.py:257-260) and unpool's scatter (Brats.py:178-203) are fused away:
+ * producers write straight into the interior / channel slice / strided positions of the consumer's buffer.
+ * ------------------------------------------------------------------------------------------------ */
+typedef struct sn_packed_view {
+  void* base;           /* plane 0, element (0,0,0,0) of the FULL buffer; 16-byte aligned          */
+  int32_t n, h, w, c;   /* FULL buffer dims                                                        */
+  int32_t y0, x0, c0;   /* window origin inside the buffer (crop / pad interior / concat slice)    */
+  int32_t reserved;
+} sn_packed_view;
+
+size_t sn_packed_bytes(int32_t n, int32_t h, int32_t w, int32_t c);
+
+/* fp32 [pixels][c] mean/variance <-> packed [pixels][3][c] (var == NULL packs a zero variance). */
+int sn_pack_moments(size_t pixels, int32_t c, const float* mu, const float* var, void* packed, sn_stream_t st);
+int sn_unpack_moments(size_t pixels, int32_t c, const void* packed, float* mu, float* var, sn_stream_t st);
+/* Fill a whole packed buffer with (mean 0, variance var_fill): the mypadding border (Brats.py:159-163,370-372). */
+int sn_packed_fill(void* packed, size_t pixels, int32_t c, float var_fill, sn_stream_t st);
+
+/* Once per weight update: HWIO fp32 w_mu -> tensor-core operands [3][taps][cout][cin] bf16 (plane 0 = W_hi,
+ * 1 = W_lo, 2 = bf16(W^2)) and s_out[n] = softplus(w_sigma[n]) (Brats.py:67,120).  upconv != 0 (requires
+ * ksize == 2): the four "taps" are the output parities (a,b) of the stride-2 transposed convolution that unpool
+ * (Brats.py:178-203) followed by the 2x2 VALID conv (Brats.py:349,414-415) amounts to: tap 2a+b holds W[1-a,1-b]. */
+size_t sn_prepared_weight_bytes(int32_t ksize, int32_t cin, int32_t cout);
+int sn_prepare_weights(const float* w_mu, const float* w_sigma, int32_t ksize, int32_t cin, int32_t cout,
+                       int32_t upconv, void* w_packed, float* s_out, sn_stream_t st);
+
+enum { SN_TC_RELU = 1, SN_TC_UPCONV = 2, SN_TC_DST_F32 = 4 };
+
+/* One fused moment convolution on the tensor cores: myConv_intermediate.call (Brats.py:118-137), optionally
+ * with the ReLU gate of Brats.py:233-238 (SN_TC_RELU), reading the channel-concat of up to two packed windows
+ * (src[0] = decoder first, src[1] = cropped encoder: myConc, Brats.py:247-261) and writing a packed window.
+ *   - ksize in {1,2,3}, stride 1, VALID over the in_h x in_w window; src_c[i] % 32 == 0, cout % 32 == 0;
+ *   - SN_TC_UPCONV (ksize must be 2, weights prepared with upconv = 1): myupsampling + the 2x2 conv
+ *     (Brats.py:414-415) as four parity GEMMs; output pixel (2y+a, 2x+b) of a 2*in_h x 2*in_w window;
+ *   - SN_TC_DST_F32: write fp32 NHWC mean/variance (dst_mu, dst_var: contiguous [batch,out_h,out_w,cout])
+ *     instead of the packed window dst. */
+typedef struct sn_tc_conv_desc {
+  sn_packed_view src[2];
+  int32_t src_c[2];       /* channels taken from each source (src_c[1] == 0: single source) */
+  int32_t batch, in_h, in_w, ksize, cout, flags;
+  const void* w_packed;   /* from sn_prepare_weights */
+  const float* s;         /* softplus(w_sigma) [cout], from sn_prepare_weights */
+  sn_packed_view dst;
+  float* dst_mu;
+  float* dst_var;
+} sn_tc_conv_desc;
+int sn_conv_moments_fwd_tc(const sn_tc_conv_desc* d, sn_stream_t st);
+
+/* myConv_input.call (Brats.py:65-76) (+ ReLU with SN_TC_RELU) on fp32 NHWC x (cin <= 8), written as a packed window. */
+int sn_first_conv_fwd_packed(int32_t batch, int32_t in_h, int32_t in_w, int32_t cin, int32_t cout, int32_t ksize,
+                             const float* x, const float* w_mu, const float* w_sigma, const sn_packed_view* dst,
+                             int32_t flags, sn_stream_t st);
+/* mymaxpooling (Brats.py:171-174) on an in_h x in_w x c packed window -> packed window (2x2/2, SAME). */
+int sn_maxpool2_packed(const sn_packed_view* src, int32_t batch, int32_t in_h, int32_t in_w, int32_t c,
+                       const sn_packed_view* dst, sn_stream_t st);
+/* conv_final (k = 1, Brats.py:367,454) fused with mysoftmax (Brats.py:269-283): packed window in (cin == 32),
+ * fp32 [batch*in_h*in_w, n_labels] probabilities and variances out; presoftmax_{mu,var} optional (may be NULL). */
+int sn_final_conv_softmax_packed(const sn_packed_view* src, int32_t batch, int32_t in_h, int32_t in_w, int32_t cin,
+                                 int32_t n_labels, const float* w_mu, const float* w_sigma, float* p_out,
+                                 float* var_out, float* presoftmax_mu, float* presoftmax_var, sn_stream_t st);
 
 #ifdef __cplusplus
 }

@@ -29,7 +29,7 @@ class sn_window(C.Structure):
 
 
 class sn_packed_view(C.Structure):
-    _fields_ = [("base", C.c_void_p), ("plane_stride", C.c_int64),
+    _fields_ = [("base", C.c_void_p),
                 ("n", C.c_int32), ("h", C.c_int32), ("w", C.c_int32), ("c", C.c_int32),
                 ("y0", C.c_int32), ("x0", C.c_int32), ("c0", C.c_int32), ("reserved", C.c_int32)]
 
@@ -39,8 +39,7 @@ class sn_tc_conv_desc(C.Structure):
                 ("batch", C.c_int32), ("in_h", C.c_int32), ("in_w", C.c_int32), ("ksize", C.c_int32),
                 ("cout", C.c_int32), ("flags", C.c_int32),
                 ("w_packed", C.c_void_p), ("s", C.c_void_p),
-                ("dst", sn_packed_view), ("dst_mu", C.c_void_p), ("dst_var", C.c_void_p),
-                ("rsum_scratch", C.c_void_p)]
+                ("dst", sn_packed_view), ("dst_mu", C.c_void_p), ("dst_var", C.c_void_p)]
 
 
 SN_CONV_RELU = 1

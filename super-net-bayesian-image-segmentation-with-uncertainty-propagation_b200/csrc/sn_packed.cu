@@ -1,0 +1,452 @@
+// FAST mode bandwidth-bound kernels around the tensor-core convolution.  All of them work on the packed
+// moment layout [n][h][w][3][c] bf16 (planes mean_hi, mean_lo, variance per pixel) with 16-byte accesses:
+// pack / unpack / fill, weight preparation, the first convolution (fp32 image in, Cin <= 8), the arg-max
+// pooling and the final 1x1 convolution fused with the softmax-Jacobian variance.
+#include "sn_common.cuh"
+
+namespace sn {
+
+__device__ __forceinline__ float blo(uint32_t v) { return __uint_as_float(v << 16); }
+__device__ __forceinline__ float bhi(uint32_t v) { return __uint_as_float(v & 0xFFFF0000u); }
+__device__ __forceinline__ uint32_t pk2(float a, float b) {
+  __nv_bfloat162 t = __floats2bfloat162_rn(a, b);
+  return *reinterpret_cast<uint32_t*>(&t);
+}
+// 8 fp32 means -> hi and lo words (4 x bf16x2 each)
+__device__ __forceinline__ void split8(const float (&m)[8], uint4& hi, uint4& lo) {
+  uint32_t h[4], l[4];
+#pragma unroll
+  for (int j = 0; j < 4; ++j) {
+    const __nv_bfloat16 h0 = __float2bfloat16_rn(m[2 * j]), h1 = __float2bfloat16_rn(m[2 * j + 1]);
+    h[j] = (uint32_t)__bfloat16_as_ushort(h0) | ((uint32_t)__bfloat16_as_ushort(h1) << 16);
+    l[j] = pk2(m[2 * j] - __bfloat162float(h0), m[2 * j + 1] - __bfloat162float(h1));
+  }
+  hi = make_uint4(h[0], h[1], h[2], h[3]);
+  lo = make_uint4(l[0], l[1], l[2], l[3]);
+}
+__device__ __forceinline__ uint4 pack8(const float (&v)[8]) {
+  return make_uint4(pk2(v[0], v[1]), pk2(v[2], v[3]), pk2(v[4], v[5]), pk2(v[6], v[7]));
+}
+__device__ __forceinline__ void unpack8(const uint4& u, float (&f)[8]) {
+  f[0] = blo(u.x); f[1] = bhi(u.x); f[2] = blo(u.y); f[3] = bhi(u.y);
+  f[4] = blo(u.z); f[5] = bhi(u.z); f[6] = blo(u.w); f[7] = bhi(u.w);
+}
+
+// ---------------------------------------------------------------------------------------------------------
+// pack / unpack / fill: one thread per (pixel, 8-channel group)
+// ---------------------------------------------------------------------------------------------------------
+__global__ void pack_kernel(size_t pixels, int c, const float* __restrict__ mu, const float* __restrict__ var,
+                            __nv_bfloat16* __restrict__ out) {
+  const int g = c / 8;
+  const size_t total = pixels * g;
+  const size_t stride = (size_t)gridDim.x * blockDim.x;
+  for (size_t i = blockIdx.x * (size_t)blockDim.x + threadIdx.x; i < total; i += stride) {
+    const size_t pix = i / g;
+    const int c8 = (int)(i - pix * g) * 8;
+    float m[8], v[8];
+    const float4 a = *reinterpret_cast<const float4*>(mu + pix * c + c8);
+    const float4 b = *reinterpret_cast<const float4*>(mu + pix * c + c8 + 4);
+    m[0] = a.x; m[1] = a.y; m[2] = a.z; m[3] = a.w; m[4] = b.x; m[5] = b.y; m[6] = b.z; m[7] = b.w;
+    if (var) {
+      const float4 e = *reinterpret_cast<const float4*>(var + pix * c + c8);
+      const float4 f = *reinterpret_cast<const float4*>(var + pix * c + c8 + 4);
+      v[0] = e.x; v[1] = e.y; v[2] = e.z; v[3] = e.w; v[4] = f.x; v[5] = f.y; v[6] = f.z; v[7] = f.w;
+    } else {
+#pragma unroll
+      for (int j = 0; j < 8; ++j) v[j] = 0.f;
+    }
+    uint4 hi, lo;
+    split8(m, hi, lo);
+    __nv_bfloat16* o = out + pix * 3 * c + c8;
+    *reinterpret_cast<uint4*>(o) = hi;
+    *reinterpret_cast<uint4*>(o + c) = lo;
+    *reinterpret_cast<uint4*>(o + 2 * c) = pack8(v);
+  }
+}
+
+__global__ void unpack_kernel(size_t pixels, int c, const __nv_bfloat16* __restrict__ in, float* __restrict__ mu,
+                              float* __restrict__ var) {
+  const int g = c / 8;
+  const size_t total = pixels * g;
+  const size_t stride = (size_t)gridDim.x * blockDim.x;
+  for (size_t i = blockIdx.x * (size_t)blockDim.x + threadIdx.x; i < total; i += stride) {
+    const size_t pix = i / g;
+    const int c8 = (int)(i - pix * g) * 8;
+    const __nv_bfloat16* s = in + pix * 3 * c + c8;
+    float h[8], l[8], v[8];
+    unpack8(*reinterpret_cast<const uint4*>(s), h);
+    unpack8(*reinterpret_cast<const uint4*>(s + c), l);
+    unpack8(*reinterpret_cast<const uint4*>(s + 2 * c), v);
+    float* pm = mu + pix * c + c8;
+    *reinterpret_cast<float4*>(pm) = make_float4(h[0] + l[0], h[1] + l[1], h[2] + l[2], h[3] + l[3]);
+    *reinterpret_cast<float4*>(pm + 4) = make_float4(h[4] + l[4], h[5] + l[5], h[6] + l[6], h[7] + l[7]);
+    if (var) {
+      float* pv = var + pix * c + c8;
+      *reinterpret_cast<float4*>(pv) = make_float4(v[0], v[1], v[2], v[3]);
+      *reinterpret_cast<float4*>(pv + 4) = make_float4(v[4], v[5], v[6], v[7]);
+    }
+  }
+}
+
+__global__ void packed_fill_kernel(size_t pixels, int c, float var_fill, __nv_bfloat16* __restrict__ out) {
+  const int g = c / 8;
+  const size_t total = pixels * g;
+  const size_t stride = (size_t)gridDim.x * blockDim.x;
+  const uint32_t vv = pk2(var_fill, var_fill);
+  const uint4 vfill = make_uint4(vv, vv, vv, vv), zero = make_uint4(0, 0, 0, 0);
+  for (size_t i = blockIdx.x * (size_t)blockDim.x + threadIdx.x; i < total; i += stride) {
+    const size_t pix = i / g;
+    const int c8 = (int)(i - pix * g) * 8;
+    __nv_bfloat16* o = out + pix * 3 * c + c8;
+    *reinterpret_cast<uint4*>(o) = zero;
+    *reinterpret_cast<uint4*>(o + c) = zero;
+    *reinterpret_cast<uint4*>(o + 2 * c) = vfill;
+  }
+}
+
+// ---------------------------------------------------------------------------------------------------------
+// weight preparation: HWIO fp32 -> [3][taps][cout][cin] bf16 (W_hi, W_lo, W^2), s = softplus(w_sigma)
+// ---------------------------------------------------------------------------------------------------------
+__global__ void prepare_weights_kernel(const float* __restrict__ w, const float* __restrict__ ws, int k, int cin,
+                                       int cout, int upconv, __nv_bfloat16* __restrict__ out,
+                                       float* __restrict__ s_out) {
+  const int taps = k * k;
+  const size_t plane = (size_t)taps * cout * cin;
+  const size_t stride = (size_t)gridDim.x * blockDim.x;
+  const size_t t0 = blockIdx.x * (size_t)blockDim.x + threadIdx.x;
+  for (size_t i = t0; i < plane; i += stride) {
+    const int ci = (int)(i % cin);
+    size_t t = i / cin;
+    const int n = (int)(t % cout);
+    const int tap = (int)(t / cout);
+    int kh = tap / k, kw = tap - kh * k;
+    if (upconv) { kh = 1 - kh; kw = 1 - kw; }     // parity (a,b) <- W[1-a, 1-b]
+    const float v = w[(((size_t)kh * k + kw) * cin + ci) * cout + n];
+    __nv_bfloat16 hi, lo;
+    split_bf16(v, hi, lo);
+    out[i] = hi;
+    out[plane + i] = lo;
+    out[2 * plane + i] = __float2bfloat16_rn(v * v);   // squared in fp32, rounded once
+  }
+  for (size_t i = t0; i < (size_t)cout; i += stride) s_out[i] = softplus_f(ws[i]);
+}
+
+// ---------------------------------------------------------------------------------------------------------
+// first convolution (Brats.py:65-76): fp32 image, Cin <= 8, k <= 3; thread = (pixel, 8 output channels)
+// ---------------------------------------------------------------------------------------------------------
+
+__global__ void __launch_bounds__(256) first_conv_packed_kernel(int B, int H, int W, int cin, int cout, int k,
+                                                                const float* __restrict__ x,
+                                                                const float* __restrict__ w,
+                                                                const float* __restrict__ ws, sn_packed_view dst,
+                                                                int relu) {
+  extern __shared__ float sm[];            // weights [K][cout], then s[cout]
+  const int K = k * k * cin;
+  float* sw = sm;
+  float* ss = sm + K * cout;
+  for (int i = threadIdx.x; i < K * cout; i += blockDim.x) sw[i] = w[i];
+  for (int i = threadIdx.x; i < cout; i += blockDim.x) ss[i] = softplus_f(ws[i]);
+  __syncthreads();
+  const int Ho = H - k + 1, Wo = W - k + 1;
+  const int g = cout / 8;
+  const size_t total = (size_t)B * Ho * Wo * g;
+  const size_t stride = (size_t)gridDim.x * blockDim.x;
+  __nv_bfloat16* out = reinterpret_cast<__nv_bfloat16*>(dst.base);
+  for (size_t i = blockIdx.x * (size_t)blockDim.x + threadIdx.x; i < total; i += stride) {
+    const int n8 = (int)(i % g) * 8;
+    size_t t = i / g;
+    const int xo = (int)(t % Wo);
+    t /= Wo;
+    const int yo = (int)(t % Ho);
+    const int b = (int)(t / Ho);
+    float acc[8];
+#pragma unroll
+    for (int j = 0; j < 8; ++j) acc[j] = 0.f;
+    float r = 0.f;
+    int kk = 0;
+    for (int kh = 0; kh < k; ++kh)
+      for (int kw = 0; kw < k; ++kw) {
+        const float* px = x + (((size_t)b * H + yo + kh) * W + xo + kw) * cin;
+        for (int ci = 0; ci < cin; ++ci, ++kk) {
+          const float xv = __ldg(px + ci);
+          r = fmaf(xv, xv, r);
+          const float4 w0 = *reinterpret_cast<const float4*>(sw + kk * cout + n8);
+          const float4 w1 = *reinterpret_cast<const float4*>(sw + kk * cout + n8 + 4);
+          acc[0] = fmaf(xv, w0.x, acc[0]); acc[1] = fmaf(xv, w0.y, acc[1]);
+          acc[2] = fmaf(xv, w0.z, acc[2]); acc[3] = fmaf(xv, w0.w, acc[3]);
+          acc[4] = fmaf(xv, w1.x, acc[4]); acc[5] = fmaf(xv, w1.y, acc[5]);
+          acc[6] = fmaf(xv, w1.z, acc[6]); acc[7] = fmaf(xv, w1.w, acc[7]);
+        }
+      }
+    float var[8];
+#pragma unroll
+    for (int j = 0; j < 8; ++j) {
+      var[j] = ss[n8 + j] * r;
+      if (relu) {
+        var[j] = acc[j] > 0.f ? var[j] : 0.f;
+        acc[j] = fmaxf(acc[j], 0.f);
+      }
+    }
+    uint4 hi, lo;
+    split8(acc, hi, lo);
+    __nv_bfloat16* o = out + ((((size_t)b * dst.h + yo + dst.y0) * dst.w + xo + dst.x0) * 3) * dst.c + dst.c0 + n8;
+    *reinterpret_cast<uint4*>(o) = hi;
+    *reinterpret_cast<uint4*>(o + dst.c) = lo;
+    *reinterpret_cast<uint4*>(o + 2 * dst.c) = pack8(var);
+  }
+}
+
+// ---------------------------------------------------------------------------------------------------------
+// arg-max pooling on packed windows (Brats.py:171-174,206-216); thread = (output pixel, 8 channels)
+// ---------------------------------------------------------------------------------------------------------
+__global__ void maxpool_packed_kernel(sn_packed_view src, int B, int H, int W, int c, sn_packed_view dst) {
+  const int Ho = (H + 1) / 2, Wo = (W + 1) / 2;
+  const int g = c / 8;
+  const size_t total = (size_t)B * Ho * Wo * g;
+  const size_t stride = (size_t)gridDim.x * blockDim.x;
+  const __nv_bfloat16* in = reinterpret_cast<const __nv_bfloat16*>(src.base);
+  __nv_bfloat16* out = reinterpret_cast<__nv_bfloat16*>(dst.base);
+  for (size_t i = blockIdx.x * (size_t)blockDim.x + threadIdx.x; i < total; i += stride) {
+    const int c8 = (int)(i % g) * 8;
+    size_t t = i / g;
+    const int xo = (int)(t % Wo);
+    t /= Wo;
+    const int yo = (int)(t % Ho);
+    const int b = (int)(t / Ho);
+    float best[8];
+    uint32_t bh[8], bl[8], bv[8];      // winning (hi, lo, var) as raw bf16 bits
+#pragma unroll
+    for (int j = 0; j < 8; ++j) { best[j] = -INFINITY; bh[j] = bl[j] = bv[j] = 0; }
+#pragma unroll
+    for (int d = 0; d < 4; ++d) {
+      const int y = 2 * yo + (d >> 1), xx = 2 * xo + (d & 1);
+      if (y < H && xx < W) {
+        const __nv_bfloat16* s =
+            in + ((((size_t)b * src.h + y + src.y0) * src.w + xx + src.x0) * 3) * src.c + src.c0 + c8;
+        const uint4 h = *reinterpret_cast<const uint4*>(s);
+        const uint4 l = *reinterpret_cast<const uint4*>(s + src.c);
+        const uint4 v = *reinterpret_cast<const uint4*>(s + 2 * src.c);
+        const uint32_t hw[4] = {h.x, h.y, h.z, h.w}, lw[4] = {l.x, l.y, l.z, l.w}, vw[4] = {v.x, v.y, v.z, v.w};
+#pragma unroll
+        for (int e = 0; e < 4; ++e) {
+          const float m0 = blo(hw[e]) + blo(lw[e]), m1 = bhi(hw[e]) + bhi(lw[e]);
+          if (m0 > best[2 * e]) {
+            best[2 * e] = m0; bh[2 * e] = hw[e] & 0xFFFFu; bl[2 * e] = lw[e] & 0xFFFFu; bv[2 * e] = vw[e] & 0xFFFFu;
+          }
+          if (m1 > best[2 * e + 1]) {
+            best[2 * e + 1] = m1; bh[2 * e + 1] = hw[e] >> 16; bl[2 * e + 1] = lw[e] >> 16; bv[2 * e + 1] = vw[e] >> 16;
+          }
+        }
+      }
+    }
+    __nv_bfloat16* o =
+        out + ((((size_t)b * dst.h + yo + dst.y0) * dst.w + xo + dst.x0) * 3) * dst.c + dst.c0 + c8;
+    *reinterpret_cast<uint4*>(o) = make_uint4(bh[0] | (bh[1] << 16), bh[2] | (bh[3] << 16), bh[4] | (bh[5] << 16),
+                                              bh[6] | (bh[7] << 16));
+    *reinterpret_cast<uint4*>(o + dst.c) = make_uint4(bl[0] | (bl[1] << 16), bl[2] | (bl[3] << 16),
+                                                      bl[4] | (bl[5] << 16), bl[6] | (bl[7] << 16));
+    *reinterpret_cast<uint4*>(o + 2 * dst.c) = make_uint4(bv[0] | (bv[1] << 16), bv[2] | (bv[3] << 16),
+                                                          bv[4] | (bv[5] << 16), bv[6] | (bv[7] << 16));
+  }
+}
+
+// ---------------------------------------------------------------------------------------------------------
+// final 1x1 convolution + softmax with Jacobian variance (Brats.py:367,454,269-283); thread = pixel
+// ---------------------------------------------------------------------------------------------------------
+template <int C>
+__global__ void __launch_bounds__(128) final_conv_softmax_kernel(sn_packed_view src, int B, int H, int W, int cin,
+                                                                 const float* __restrict__ w,
+                                                                 const float* __restrict__ ws,
+                                                                 float* __restrict__ p_out,
+                                                                 float* __restrict__ v_out,
+                                                                 float* __restrict__ pre_mu,
+                                                                 float* __restrict__ pre_var) {
+  extern __shared__ float sm[];            // W [cin][C], W^2 [cin][C], s [C]
+  float* sw = sm;
+  float* sw2 = sm + cin * C;
+  float* ss = sm + 2 * cin * C;
+  for (int i = threadIdx.x; i < cin * C; i += blockDim.x) {
+    const float v = w[i];
+    sw[i] = v;
+    sw2[i] = v * v;
+  }
+  for (int i = threadIdx.x; i < C; i += blockDim.x) ss[i] = softplus_f(ws[i]);
+  __syncthreads();
+  const size_t total = (size_t)B * H * W;
+  const size_t stride = (size_t)gridDim.x * blockDim.x;
+  const __nv_bfloat16* in = reinterpret_cast<const __nv_bfloat16*>(src.base);
+  for (size_t i = blockIdx.x * (size_t)blockDim.x + threadIdx.x; i < total; i += stride) {
+    const int xx = (int)(i % W);
+    size_t t = i / W;
+    const int y = (int)(t % H);
+    const int b = (int)(t / H);
+    const __nv_bfloat16* s = in + ((((size_t)b * src.h + y + src.y0) * src.w + xx + src.x0) * 3) * src.c + src.c0;
+    float m[C], v[C];
+#pragma unroll
+    for (int j = 0; j < C; ++j) m[j] = v[j] = 0.f;
+    float r = 0.f;
+    for (int c8 = 0; c8 < cin; c8 += 8) {
+      float h[8], l[8], vv[8];
+      unpack8(*reinterpret_cast<const uint4*>(s + c8), h);
+      unpack8(*reinterpret_cast<const uint4*>(s + src.c + c8), l);
+      unpack8(*reinterpret_cast<const uint4*>(s + 2 * src.c + c8), vv);
+#pragma unroll
+      for (int e = 0; e < 8; ++e) {
+        const float mu = h[e] + l[e];
+        r += fmaf(mu, mu, vv[e]);
+#pragma unroll
+        for (int j = 0; j < C; ++j) {
+          m[j] = fmaf(mu, sw[(c8 + e) * C + j], m[j]);
+          v[j] = fmaf(vv[e], sw2[(c8 + e) * C + j], v[j]);
+        }
+      }
+    }
+    float mx = -INFINITY;
+#pragma unroll
+    for (int j = 0; j < C; ++j) {
+      v[j] = fmaxf(fmaf(ss[j], r, v[j]), 0.f);
+      mx = fmaxf(mx, m[j]);
+    }
+    float p[C], sum = 0.f;
+#pragma unroll
+    for (int j = 0; j < C; ++j) { p[j] = expf(m[j] - mx); sum += p[j]; }
+    const float inv = 1.f / sum;
+#pragma unroll
+    for (int j = 0; j < C; ++j) p[j] *= inv;
+#pragma unroll
+    for (int a = 0; a < C; ++a) {
+      float acc = 0.f;   // sum_j (p_a (delta_aj - p_j))^2 v_j : non-negative terms only
+#pragma unroll
+      for (int j = 0; j < C; ++j) {
+        const float J = p[a] * ((a == j ? 1.f : 0.f) - p[j]);
+        acc = fmaf(J * J, v[j], acc);
+      }
+      p_out[i * C + a] = p[a];
+      v_out[i * C + a] = acc;
+    }
+    if (pre_mu) {
+#pragma unroll
+      for (int j = 0; j < C; ++j) { pre_mu[i * C + j] = m[j]; pre_var[i * C + j] = v[j]; }
+    }
+  }
+}
+
+static int check_pview(const sn_packed_view* v, int batch, int h, int w, int c, const char* who) {
+  SN_REQUIRE(v && v->base && aligned16(v->base), SN_ERR_BAD_ARG, "%s: null/misaligned packed view", who);
+  SN_REQUIRE(v->n >= batch && v->c % 8 == 0 && v->c0 % 8 == 0 && c % 8 == 0, SN_ERR_MISALIGNED,
+             "%s: channel counts/offsets must be multiples of 8", who);
+  SN_REQUIRE(v->y0 >= 0 && v->x0 >= 0 && v->c0 >= 0 && v->y0 + h <= v->h && v->x0 + w <= v->w && v->c0 + c <= v->c,
+             SN_ERR_BAD_ARG, "%s: window outside the buffer", who);
+  return SN_OK;
+}
+
+}  // namespace sn
+
+using namespace sn;
+
+extern "C" {
+
+size_t sn_packed_bytes(int32_t n, int32_t h, int32_t w, int32_t c) {
+  return (size_t)n * h * w * 3 * c * sizeof(__nv_bfloat16);
+}
+
+int sn_pack_moments(size_t pixels, int32_t c, const float* mu, const float* var, void* packed, sn_stream_t st) {
+  SN_REQUIRE(mu && packed, SN_ERR_BAD_ARG, "pack: null pointer");
+  SN_REQUIRE(c > 0 && c % 8 == 0, SN_ERR_MISALIGNED, "pack: channels %d must be a multiple of 8", c);
+  SN_REQUIRE(aligned16(mu) && (!var || aligned16(var)) && aligned16(packed), SN_ERR_MISALIGNED, "pack: misaligned");
+  if (pixels == 0) return SN_OK;
+  pack_kernel<<<ew_grid(pixels * (c / 8), 256), 256, 0, as_stream(st)>>>(pixels, c, mu, var,
+                                                                         reinterpret_cast<__nv_bfloat16*>(packed));
+  return check_launch("pack");
+}
+
+int sn_unpack_moments(size_t pixels, int32_t c, const void* packed, float* mu, float* var, sn_stream_t st) {
+  SN_REQUIRE(mu && packed, SN_ERR_BAD_ARG, "unpack: null pointer");
+  SN_REQUIRE(c > 0 && c % 8 == 0, SN_ERR_MISALIGNED, "unpack: channels %d must be a multiple of 8", c);
+  SN_REQUIRE(aligned16(mu) && (!var || aligned16(var)) && aligned16(packed), SN_ERR_MISALIGNED, "unpack: misaligned");
+  if (pixels == 0) return SN_OK;
+  unpack_kernel<<<ew_grid(pixels * (c / 8), 256), 256, 0, as_stream(st)>>>(
+      pixels, c, reinterpret_cast<const __nv_bfloat16*>(packed), mu, var);
+  return check_launch("unpack");
+}
+
+int sn_packed_fill(void* packed, size_t pixels, int32_t c, float var_fill, sn_stream_t st) {
+  SN_REQUIRE(packed && aligned16(packed), SN_ERR_BAD_ARG, "packed_fill: null/misaligned pointer");
+  SN_REQUIRE(c > 0 && c % 8 == 0, SN_ERR_MISALIGNED, "packed_fill: channels %d must be a multiple of 8", c);
+  if (pixels == 0) return SN_OK;
+  packed_fill_kernel<<<ew_grid(pixels * (c / 8), 256), 256, 0, as_stream(st)>>>(
+      pixels, c, var_fill, reinterpret_cast<__nv_bfloat16*>(packed));
+  return check_launch("packed_fill");
+}
+
+size_t sn_prepared_weight_bytes(int32_t ksize, int32_t cin, int32_t cout) {
+  return (size_t)3 * ksize * ksize * cin * cout * sizeof(__nv_bfloat16);
+}
+
+int sn_prepare_weights(const float* w_mu, const float* w_sigma, int32_t ksize, int32_t cin, int32_t cout,
+                       int32_t upconv, void* w_packed, float* s_out, sn_stream_t st) {
+  SN_REQUIRE(w_mu && w_sigma && w_packed && s_out, SN_ERR_BAD_ARG, "prepare_weights: null pointer");
+  SN_REQUIRE(ksize >= 1 && ksize <= 3 && cin > 0 && cout > 0, SN_ERR_BAD_ARG, "prepare_weights: bad sizes");
+  SN_REQUIRE(!upconv || ksize == 2, SN_ERR_BAD_ARG, "prepare_weights: upconv needs ksize == 2");
+  size_t n = (size_t)ksize * ksize * cin * cout;
+  prepare_weights_kernel<<<ew_grid(n, 256), 256, 0, as_stream(st)>>>(
+      w_mu, w_sigma, ksize, cin, cout, upconv, reinterpret_cast<__nv_bfloat16*>(w_packed), s_out);
+  return check_launch("prepare_weights");
+}
+
+int sn_first_conv_fwd_packed(int32_t batch, int32_t in_h, int32_t in_w, int32_t cin, int32_t cout, int32_t ksize,
+                             const float* x, const float* w_mu, const float* w_sigma, const sn_packed_view* dst,
+                             int32_t flags, sn_stream_t st) {
+  SN_REQUIRE(x && w_mu && w_sigma && dst, SN_ERR_BAD_ARG, "first_conv: null pointer");
+  SN_REQUIRE(batch > 0 && cin >= 1 && cin <= 8 && ksize >= 1 && ksize <= 3 && in_h >= ksize && in_w >= ksize,
+             SN_ERR_UNSUPPORTED, "first_conv: needs cin <= 8 and k <= 3 (got cin %d, k %d)", cin, ksize);
+  SN_REQUIRE(cout % 8 == 0 && cout <= 256, SN_ERR_UNSUPPORTED, "first_conv: cout %d", cout);
+  const int Ho = in_h - ksize + 1, Wo = in_w - ksize + 1;
+  int rc = check_pview(dst, batch, Ho, Wo, cout, "first_conv dst");
+  if (rc) return rc;
+  const size_t smem = ((size_t)ksize * ksize * cin * cout + cout) * sizeof(float);
+  const size_t total = (size_t)batch * Ho * Wo * (cout / 8);
+  first_conv_packed_kernel<<<ew_grid(total, 256, 4), 256, smem, as_stream(st)>>>(
+      batch, in_h, in_w, cin, cout, ksize, x, w_mu, w_sigma, *dst, (flags & SN_TC_RELU) ? 1 : 0);
+  return check_launch("first_conv_packed");
+}
+
+int sn_maxpool2_packed(const sn_packed_view* src, int32_t batch, int32_t in_h, int32_t in_w, int32_t c,
+                       const sn_packed_view* dst, sn_stream_t st) {
+  SN_REQUIRE(batch > 0 && in_h > 0 && in_w > 0 && c > 0, SN_ERR_BAD_ARG, "maxpool_packed: bad shape");
+  int rc = check_pview(src, batch, in_h, in_w, c, "maxpool_packed src");
+  if (rc) return rc;
+  const int Ho = (in_h + 1) / 2, Wo = (in_w + 1) / 2;
+  if ((rc = check_pview(dst, batch, Ho, Wo, c, "maxpool_packed dst"))) return rc;
+  const size_t total = (size_t)batch * Ho * Wo * (c / 8);
+  maxpool_packed_kernel<<<ew_grid(total, 256), 256, 0, as_stream(st)>>>(*src, batch, in_h, in_w, c, *dst);
+  return check_launch("maxpool_packed");
+}
+
+int sn_final_conv_softmax_packed(const sn_packed_view* src, int32_t batch, int32_t in_h, int32_t in_w, int32_t cin,
+                                 int32_t n_labels, const float* w_mu, const float* w_sigma, float* p_out,
+                                 float* var_out, float* presoftmax_mu, float* presoftmax_var, sn_stream_t st) {
+  SN_REQUIRE(w_mu && w_sigma && p_out && var_out, SN_ERR_BAD_ARG, "final_conv: null pointer");
+  SN_REQUIRE((presoftmax_mu == nullptr) == (presoftmax_var == nullptr), SN_ERR_BAD_ARG,
+             "final_conv: pass both pre-softmax outputs or neither");
+  SN_REQUIRE(n_labels >= 1 && n_labels <= 8, SN_ERR_UNSUPPORTED, "final_conv: %d classes (max 8)", n_labels);
+  SN_REQUIRE(cin > 0 && cin % 8 == 0 && cin <= 256, SN_ERR_UNSUPPORTED, "final_conv: cin %d", cin);
+  int rc = check_pview(src, batch, in_h, in_w, cin, "final_conv src");
+  if (rc) return rc;
+  const size_t total = (size_t)batch * in_h * in_w;
+  const size_t smem = ((size_t)2 * cin * n_labels + n_labels) * sizeof(float);
+  const int grid = ew_grid(total, 128, 8);
+#define SN_FINAL(CC)                                                                                           \
+  case CC:                                                                                                     \
+    final_conv_softmax_kernel<CC><<<grid, 128, smem, as_stream(st)>>>(*src, batch, in_h, in_w, cin, w_mu, w_sigma, \
+                                                                       p_out, var_out, presoftmax_mu,          \
+                                                                       presoftmax_var);                        \
+    break;
+  switch (n_labels) {
+    SN_FINAL(1) SN_FINAL(2) SN_FINAL(3) SN_FINAL(4) SN_FINAL(5) SN_FINAL(6) SN_FINAL(7) SN_FINAL(8)
+  }
+#undef SN_FINAL
+  return check_launch("final_conv_softmax");
+}
+
+}  // extern "C"

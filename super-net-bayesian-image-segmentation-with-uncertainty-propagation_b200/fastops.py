@@ -1,0 +1,112 @@
+"""FAST-mode (tcgen05) entry points of the C-ABI as thin Python functions over torch tensors.
+
+A packed moment tensor is a torch.bfloat16 tensor of shape [n, h, w, 3, c] (planes mean_hi, mean_lo, variance
+per pixel; include/supernet.h).  `PackedView` names a window of one.  Inference only: no autograd.
+"""
+from __future__ import annotations
+
+import ctypes as C
+from dataclasses import dataclass
+from typing import Optional, Tuple
+
+import torch
+
+from . import _lib
+from ._lib import SN_TC_DST_F32, SN_TC_RELU, SN_TC_UPCONV, check, ptr, sn_packed_view, sn_tc_conv_desc, stream_ptr
+
+Tensor = torch.Tensor
+
+
+@dataclass
+class PackedView:
+    buf: Tensor                 # [n, h, w, 3, c] bfloat16, contiguous
+    y0: int = 0
+    x0: int = 0
+    c0: int = 0
+
+    def c_view(self) -> sn_packed_view:
+        n, h, w, three, c = self.buf.shape
+        assert three == 3 and self.buf.dtype == torch.bfloat16 and self.buf.is_contiguous()
+        return sn_packed_view(self.buf.data_ptr(), n, h, w, c, self.y0, self.x0, self.c0, 0)
+
+
+def packed_empty(n: int, h: int, w: int, c: int, device) -> Tensor:
+    return torch.empty((n, h, w, 3, c), device=device, dtype=torch.bfloat16)
+
+
+def packed_fill(buf: Tensor, var_fill: float) -> None:
+    n, h, w, _, c = buf.shape
+    check(_lib.load().sn_packed_fill(ptr(buf), C.c_size_t(n * h * w), c, C.c_float(var_fill), stream_ptr()),
+          "packed_fill")
+
+
+def pack_moments(mu: Tensor, var: Optional[Tensor]) -> Tensor:
+    """fp32 NHWC (mu, var) -> packed [n,h,w,3,c]."""
+    n, h, w, c = mu.shape
+    out = packed_empty(n, h, w, c, mu.device)
+    check(_lib.load().sn_pack_moments(C.c_size_t(n * h * w), c, ptr(mu.contiguous()),
+                                      ptr(var.contiguous() if var is not None else None), ptr(out), stream_ptr()),
+          "pack_moments")
+    return out
+
+
+def unpack_moments(buf: Tensor) -> Tuple[Tensor, Tensor]:
+    n, h, w, _, c = buf.shape
+    mu = torch.empty((n, h, w, c), device=buf.device, dtype=torch.float32)
+    var = torch.empty_like(mu)
+    check(_lib.load().sn_unpack_moments(C.c_size_t(n * h * w), c, ptr(buf), ptr(mu), ptr(var), stream_ptr()),
+          "unpack_moments")
+    return mu, var
+
+
+def prepare_weights(w_mu: Tensor, w_sigma: Tensor, upconv: bool = False) -> Tuple[Tensor, Tensor]:
+    """HWIO fp32 -> ([3, taps, cout, cin] bf16 operands, softplus(w_sigma) [cout])."""
+    k, _, cin, cout = w_mu.shape
+    wp = torch.empty((3, k * k, cout, cin), device=w_mu.device, dtype=torch.bfloat16)
+    s = torch.empty(cout, device=w_mu.device, dtype=torch.float32)
+    check(_lib.load().sn_prepare_weights(ptr(w_mu.detach().contiguous()), ptr(w_sigma.detach().contiguous()), k, cin,
+                                         cout, 1 if upconv else 0, ptr(wp), ptr(s), stream_ptr()), "prepare_weights")
+    return wp, s
+
+
+def conv_moments_tc(src0: PackedView, c0: int, batch: int, in_h: int, in_w: int, ksize: int, cout: int,
+                    w_packed: Tensor, s: Tensor, dst: Optional[PackedView] = None, relu: bool = False,
+                    upconv: bool = False, src1: Optional[PackedView] = None, c1: int = 0,
+                    dst_f32: Optional[Tuple[Tensor, Tensor]] = None) -> None:
+    d = sn_tc_conv_desc()
+    d.src[0] = src0.c_view()
+    d.src[1] = (src1 if src1 is not None else src0).c_view()
+    d.src_c[0], d.src_c[1] = c0, c1
+    d.batch, d.in_h, d.in_w, d.ksize, d.cout = batch, in_h, in_w, ksize, cout
+    d.flags = (SN_TC_RELU if relu else 0) | (SN_TC_UPCONV if upconv else 0) | (SN_TC_DST_F32 if dst_f32 else 0)
+    d.w_packed = w_packed.data_ptr()
+    d.s = s.data_ptr()
+    if dst_f32 is not None:
+        d.dst_mu, d.dst_var = dst_f32[0].data_ptr(), dst_f32[1].data_ptr()
+    else:
+        d.dst = dst.c_view()
+    check(_lib.load().sn_conv_moments_fwd_tc(C.byref(d), stream_ptr()), "conv_moments_fwd_tc")
+
+
+def first_conv_packed(x: Tensor, w_mu: Tensor, w_sigma: Tensor, dst: PackedView, relu: bool = True) -> None:
+    B, H, W, cin = x.shape
+    k, _, _, cout = w_mu.shape
+    v = dst.c_view()
+    check(_lib.load().sn_first_conv_fwd_packed(B, H, W, cin, cout, k, ptr(x), ptr(w_mu), ptr(w_sigma), C.byref(v),
+                                               SN_TC_RELU if relu else 0, stream_ptr()), "first_conv_fwd_packed")
+
+
+def maxpool2_packed(src: PackedView, batch: int, in_h: int, in_w: int, c: int, dst: PackedView) -> None:
+    a, b = src.c_view(), dst.c_view()
+    check(_lib.load().sn_maxpool2_packed(C.byref(a), batch, in_h, in_w, c, C.byref(b), stream_ptr()),
+          "maxpool2_packed")
+
+
+def final_conv_softmax_packed(src: PackedView, batch: int, in_h: int, in_w: int, cin: int, w_mu: Tensor,
+                              w_sigma: Tensor, p_out: Tensor, var_out: Tensor, pre_mu: Optional[Tensor] = None,
+                              pre_var: Optional[Tensor] = None) -> None:
+    v = src.c_view()
+    n_labels = w_mu.shape[-1]
+    check(_lib.load().sn_final_conv_softmax_packed(C.byref(v), batch, in_h, in_w, cin, n_labels, ptr(w_mu),
+                                                   ptr(w_sigma), ptr(p_out), ptr(var_out), ptr(pre_mu), ptr(pre_var),
+                                                   stream_ptr()), "final_conv_softmax_packed")

@@ -1,0 +1,179 @@
+"""GPU parity tests of the FAST-mode (tcgen05) kernels against the CPU oracle, layer by layer.
+
+Tolerances (BASELINE.json north_star): mean maps 1e-3 relative L2, variance maps 1e-2, both against the fp64
+oracle on identical inputs.  Per layer the kernels do much better (bf16x3 mean ~1e-5, bf16 variance ~3e-3),
+so the per-layer bars here are tighter: mean 1e-4, variance 5e-3.
+"""
+import pytest
+import torch
+
+from oracle import supernet_oracle as O
+
+pytestmark = pytest.mark.gpu
+
+MEAN_TOL, VAR_TOL = 1e-4, 5e-3
+
+
+@pytest.fixture(scope="module")
+def S():
+    import supernet_b200 as S_
+    lib = S_._lib.load()
+    assert lib.sn_device_check() == 0
+    from supernet_b200 import fastops  # noqa: F401
+    return S_
+
+
+def dev(t):
+    return t.to(torch.float32).cuda().contiguous()
+
+
+def rel(a, b):
+    return O.rel_l2(a.detach().cpu(), b.detach().cpu())
+
+
+def rand_layer(B, H, W, cin, cout, k, seed=0):
+    g = torch.Generator().manual_seed(seed)
+    mu = torch.randn(B, H, W, cin, generator=g, dtype=torch.float64)
+    var = torch.rand(B, H, W, cin, generator=g, dtype=torch.float64)
+    w = torch.randn(k, k, cin, cout, generator=g, dtype=torch.float64) * 0.1
+    ws = torch.empty(cout, dtype=torch.float64).uniform_(-6, -2, generator=g)
+    return [t.float().double() for t in (mu, var, w, ws)]
+
+
+def test_pack_roundtrip(S):
+    F = S.fastops
+    g = torch.Generator().manual_seed(1)
+    mu = torch.randn(2, 5, 7, 32, generator=g) * 100
+    var = torch.rand(2, 5, 7, 32, generator=g)
+    buf = F.pack_moments(dev(mu), dev(var))
+    assert buf.shape == (2, 5, 7, 3, 32)
+    m2, v2 = F.unpack_moments(buf)
+    assert rel(m2, mu) < 2e-5 and rel(v2, var) < 4e-3
+    # plane semantics: hi = bf16(mu), lo = bf16(mu - hi), var = bf16(var)
+    hi = mu.bfloat16()
+    assert torch.equal(buf[..., 0, :].cpu(), hi)
+    assert torch.equal(buf[..., 1, :].cpu(), (mu - hi.float()).bfloat16())
+    assert torch.equal(buf[..., 2, :].cpu(), var.bfloat16())
+
+
+TC_CASES = [
+    # B, H, W, cin, cout, k
+    (2, 10, 9, 32, 32, 3),     # M = 112 < one tile, single K block per tap
+    (3, 12, 14, 64, 64, 3),    # M = 360: tiles straddle rows and images
+    (1, 20, 20, 128, 128, 3),  # NT = 128
+    (2, 9, 9, 256, 256, 3),    # two N tiles of 128
+    (2, 11, 13, 32, 64, 1),    # 1x1
+    (2, 7, 8, 64, 32, 2),      # plain k = 2
+    (1, 34, 33, 32, 96, 3),    # cout multiple of 32 only -> NT = 32, three N tiles
+]
+
+
+@pytest.mark.parametrize("case", TC_CASES)
+@pytest.mark.parametrize("relu", [False, True])
+def test_conv_tc_f32_dst(S, case, relu):
+    F = S.fastops
+    B, H, W, cin, cout, k = case
+    mu, var, w, ws = rand_layer(B, H, W, cin, cout, k, seed=sum(case))
+    m_ref, v_ref = O.conv_intermediate_conv_form(mu, var, w, ws)
+    if relu:
+        m_ref, v_ref = O.relu(m_ref, v_ref)
+    src = F.PackedView(F.pack_moments(dev(mu), dev(var)))
+    wp, s = F.prepare_weights(dev(w), dev(ws))
+    Ho, Wo = H - k + 1, W - k + 1
+    m = torch.full((B, Ho, Wo, cout), float("nan"), device="cuda")
+    v = torch.full((B, Ho, Wo, cout), float("nan"), device="cuda")
+    F.conv_moments_tc(src, cin, B, H, W, k, cout, wp, s, relu=relu, dst_f32=(m, v))
+    torch.cuda.synchronize()
+    assert bool(torch.isfinite(m).all()) and bool(torch.isfinite(v).all())
+    assert rel(m, m_ref) < MEAN_TOL, rel(m, m_ref)
+    assert rel(v, v_ref) < VAR_TOL, rel(v, v_ref)
+    assert float(v.min()) >= 0.0
+
+
+def test_conv_tc_packed_window_concat(S):
+    """Two sources (decoder window + cropped encoder window), output into the interior of a padded buffer."""
+    F = S.fastops
+    B, H, W, k, cout = 2, 10, 10, 3, 64
+    mu_d, var_d, _, _ = rand_layer(B, H, W, 64, cout, k, seed=5)
+    mu_e, var_e, _, _ = rand_layer(B, H + 4, W + 4, 32, cout, k, seed=6)
+    _, _, w, ws = rand_layer(B, H, W, 96, cout, k, seed=7)
+    m_in, v_in = O.conc(mu_d, var_d, mu_e, var_e)
+    m_ref, v_ref = O.relu(*O.conv_intermediate_conv_form(m_in, v_in, w, ws))
+    m_ref, v_ref = O.padding(m_ref, v_ref, (2, 2), 0.1)
+    # decoder source lives at offset (1,2) of a bigger buffer; encoder source is cropped by its window origin
+    dbuf = F.packed_empty(B, H + 3, W + 5, 64, "cuda")
+    F.packed_fill(dbuf, 7.0)
+    dbuf[:, 1:1 + H, 2:2 + W] = F.pack_moments(dev(mu_d), dev(var_d))
+    ebuf = F.pack_moments(dev(mu_e), dev(var_e))
+    out = F.packed_empty(B, H - 2 + 4, W - 2 + 4, cout, "cuda")
+    F.packed_fill(out, 0.1)
+    wp, s = F.prepare_weights(dev(w), dev(ws))
+    F.conv_moments_tc(F.PackedView(dbuf, 1, 2, 0), 64, B, H, W, k, cout, wp, s,
+                      dst=F.PackedView(out, 2, 2, 0), relu=True, src1=F.PackedView(ebuf, 2, 2, 0), c1=32)
+    m, v = F.unpack_moments(out)
+    assert rel(m, m_ref) < MEAN_TOL and rel(v, v_ref) < VAR_TOL
+    assert torch.equal(v[:, 0].cpu(), torch.full_like(v[:, 0].cpu(), float(torch.tensor(0.1).bfloat16())))
+
+
+@pytest.mark.parametrize("case", [(2, 6, 6, 64, 32), (1, 9, 7, 128, 64), (2, 5, 5, 256, 128)])
+def test_upconv_tc(S, case):
+    """unpool + 2x2 VALID conv (Brats.py:414-415) == four parity GEMMs, scattered into a padded window."""
+    F = S.fastops
+    B, H, W, cin, cout = case
+    mu, var, w, ws = rand_layer(B, H, W, cin, cout, 2, seed=sum(case))
+    um, uv = O.upsampling(mu, var)
+    m_ref, v_ref = O.conv_intermediate_conv_form(um, uv, w, ws)
+    assert m_ref.shape[1] == 2 * H
+    m_ref, v_ref = O.padding(m_ref, v_ref, (3, 3), 0.1)
+    src = F.PackedView(F.pack_moments(dev(mu), dev(var)))
+    wp, s = F.prepare_weights(dev(w), dev(ws), upconv=True)
+    out = F.packed_empty(B, 2 * H + 6, 2 * W + 6, cout, "cuda")
+    F.packed_fill(out, 0.1)
+    F.conv_moments_tc(src, cin, B, H, W, 2, cout, wp, s, dst=F.PackedView(out, 3, 3, 0), upconv=True)
+    m, v = F.unpack_moments(out)
+    assert rel(m, m_ref) < MEAN_TOL and rel(v, v_ref) < VAR_TOL
+
+
+def test_first_conv_pool_final(S):
+    F = S.fastops
+    g = torch.Generator().manual_seed(3)
+    x = torch.rand(2, 12, 14, 4, generator=g, dtype=torch.float64).float().double()
+    _, _, w, ws = rand_layer(2, 12, 14, 4, 32, 3, seed=9)
+    m_ref, v_ref = O.relu(*O.conv_input_conv_form(x, w, ws))
+    buf = F.packed_empty(2, 10, 12, 32, "cuda")
+    F.first_conv_packed(dev(x), dev(w), dev(ws), F.PackedView(buf), relu=True)
+    m, v = F.unpack_moments(buf)
+    assert rel(m, m_ref) < 2e-5 and rel(v, v_ref) < VAR_TOL
+    # pooling on the packed tensor == oracle pooling of the unpacked (bf16-rounded) values, exactly
+    pm_ref, pv_ref = O.maxpooling(m.cpu(), v.cpu())
+    pbuf = F.packed_empty(2, 6, 7, 32, "cuda")            # written at offset (1,1) like mypad1's interior
+    F.packed_fill(pbuf, 0.1)
+    F.maxpool2_packed(F.PackedView(buf), 2, 10, 12, 32, F.PackedView(pbuf, 1, 1, 0))
+    pm, pv = F.unpack_moments(pbuf)
+    assert torch.equal(pm[:, 1:, 1:].cpu(), pm_ref) and torch.equal(pv[:, 1:, 1:].cpu(), pv_ref)
+    # final 1x1 conv + softmax
+    for C in (3, 4, 5):
+        _, _, wf, wsf = rand_layer(2, 10, 12, 32, C, 1, seed=20 + C)
+        mf_ref, sf_ref = O.conv_intermediate_conv_form(m.cpu().double(), v.cpu().double(), wf, wsf)
+        p_ref, vo_ref = O.softmax_as_written(mf_ref, sf_ref)
+        p = torch.empty(2, 120, C, device="cuda")
+        vo = torch.empty_like(p)
+        pre_m = torch.empty_like(p)
+        pre_v = torch.empty_like(p)
+        F.final_conv_softmax_packed(F.PackedView(buf), 2, 10, 12, 32, dev(wf), dev(wsf), p, vo, pre_m, pre_v)
+        assert rel(pre_m, mf_ref.reshape(2, 120, C)) < 1e-5 and rel(pre_v, sf_ref.reshape(2, 120, C)) < 1e-5
+        assert rel(p, p_ref) < 1e-5 and rel(vo, vo_ref) < 1e-5
+
+
+def test_tc_rejects_bad_arguments(S):
+    F = S.fastops
+    buf = F.packed_empty(1, 8, 8, 32, "cuda")
+    wp = torch.zeros(3, 9, 32, 32, device="cuda", dtype=torch.bfloat16)
+    s = torch.zeros(32, device="cuda")
+    out = F.packed_empty(1, 6, 6, 32, "cuda")
+    with pytest.raises(RuntimeError):       # channels not a multiple of 32
+        F.conv_moments_tc(F.PackedView(buf), 16, 1, 8, 8, 3, 32, wp, s, dst=F.PackedView(out))
+    with pytest.raises(RuntimeError):       # destination window too small
+        F.conv_moments_tc(F.PackedView(buf), 32, 1, 8, 8, 3, 32, wp, s, dst=F.PackedView(out, 1, 0, 0))
+    with pytest.raises(RuntimeError):       # kernel size 4
+        F.conv_moments_tc(F.PackedView(buf), 32, 1, 8, 8, 4, 32, wp, s, dst=F.PackedView(out))
