@@ -1,0 +1,176 @@
+"""FAST-mode inference engine: the whole Density_prop_with_pad_UNET forward (Brats.py:377-457 /
+Hippocampus.py:373-421) as a fixed sequence of C-ABI calls over preallocated packed buffers.
+
+What the reference does with separate ops is address arithmetic here:
+  * myReLU (Brats.py:233-238)             -> conv epilogue flag
+  * mypadding (Brats.py:159-163)          -> the producer writes into the interior of a buffer whose border
+                                            was filled once (mean 0, variance sigma_fill)
+  * myConc + crop_tensor (Brats.py:247-261) -> the conv reads two source windows (decoder, cropped encoder)
+  * myupsampling + 2x2 conv (Brats.py:414-415) -> four parity GEMMs scattered to (2y+a, 2x+b)
+  * conv_final + mysoftmax (Brats.py:454-455) -> one kernel
+Nothing is allocated and nothing synchronises inside run(), so the sequence is CUDA-graph capturable; the
+engine captures it on first use (graph=True) to remove ~40 launches of host latency per forward.
+"""
+from __future__ import annotations
+
+from typing import Callable, List, Optional, Tuple
+
+import torch
+
+from . import fastops as F
+from .fastops import PackedView
+
+Tensor = torch.Tensor
+
+
+class InferenceEngine:
+    def __init__(self, model, batch: int, in_h: int, in_w: int, in_c: int, device, graph: bool = True):
+        self.model = model
+        self.shape = (batch, in_h, in_w, in_c)
+        self.device = torch.device(device)
+        self.use_graph = graph
+        self._graph: Optional[torch.cuda.CUDAGraph] = None
+        self._steps: List[Callable[[], None]] = []
+        self._weights_version = None
+        self._build()
+
+    def matches(self, x: Tensor) -> bool:
+        return tuple(x.shape) == self.shape and x.device == self.device
+
+    # ------------------------------------------------------------------------------------------------
+    def _prepare_weights(self) -> None:
+        """softplus / W^2 / bf16 operand split, once per weight update (sn_prepare_weights)."""
+        m = self.model
+        self.prepared = {}
+        for name in m.conv_names:
+            if name in ("conv_input", "conv_final"):
+                continue
+            w, ws = getattr(m, name).weights()
+            self.prepared[name] = F.prepare_weights(w, ws, upconv=name.endswith("conv2x2"))
+
+    def refresh_weights(self) -> None:
+        self._prepare_weights()
+        self._graph = None         # prepared-weight buffers were reallocated
+
+    def _build(self) -> None:
+        m = self.model
+        B, H, W, Cin = self.shape
+        dev = self.device
+        n = m.n_kernels
+        L = m.levels
+        fill = m.sigma_fill
+        if not all(c.built for c in m.convs()):
+            m.build_with_input(Cin, dev)
+        self._prepare_weights()
+        steps = self._steps
+        self.x_in = torch.empty(self.shape, device=dev, dtype=torch.float32)
+
+        def new(h, w, c, prefill=None):
+            t = F.packed_empty(B, h, w, c, dev)
+            if prefill is not None:
+                F.packed_fill(t, prefill)
+            return t
+
+        def conv(name, src: PackedView, c0, h, w, k, dst: PackedView, relu, src1=None, c1=0, upconv=False):
+            wp, s = self.prepared[name]
+            cout = getattr(m, name).kernel_num
+            steps.append(lambda: F.conv_moments_tc(src, c0, B, h, w, k, cout, wp, s, dst=dst, relu=relu,
+                                                   upconv=upconv, src1=src1, c1=c1))
+
+        # ---- encoder --------------------------------------------------------------------------------
+        h, w = H - 2, W - 2
+        a0 = new(h, w, n)
+        w_in, ws_in = m.conv_input.weights()
+        steps.append(lambda: F.first_conv_packed(self.x_in, w_in, ws_in, PackedView(a0), relu=True))
+        skip = new(h - 2, w - 2, n)
+        conv("conv1", PackedView(a0), n, h, w, 3, PackedView(skip), True)
+        h, w = h - 2, w - 2
+        skips: List[Tuple[Tensor, int, int, int]] = [(skip, h, w, n)]
+        cur, c = skip, n
+        ci = 2
+        for lvl in range(1, L + 1):
+            ph, pw = (h + 1) // 2, (w + 1) // 2
+            if m.variant == "brats" and lvl == L:
+                pooled = new(ph + 1, pw + 1, c, prefill=fill)          # mypad1 [1,0] (Brats.py:407)
+                pview = PackedView(pooled, 1, 1, 0)
+                ph, pw = ph + 1, pw + 1
+            else:
+                pooled = new(ph, pw, c)
+                pview = PackedView(pooled)
+            steps.append(lambda s=PackedView(cur), hh=h, ww=w, cc=c, d=pview: F.maxpool2_packed(s, B, hh, ww, cc, d))
+            h, w = ph, pw
+            cur = pooled
+            for j in range(2):
+                name = f"conv{ci}"
+                cout = getattr(m, name).kernel_num
+                out = new(h - 2, w - 2, cout)
+                conv(name, PackedView(cur), c, h, w, 3, PackedView(out), True)
+                cur, c, h, w = out, cout, h - 2, w - 2
+                ci += 1
+            if lvl < L:
+                skips.append((cur, h, w, c))
+        # ---- decoder --------------------------------------------------------------------------------
+        for d in range(1, L + 1):
+            enc, eh, ew, ec = skips[L - d]
+            cu = getattr(m, f"up{d}_conv2x2").kernel_num
+            uh, uw = 2 * h, 2 * w                                        # unpool (2h+1) then 2x2 VALID -> 2h
+            up = new(uh + 6, uw + 6, cu, prefill=fill)                   # mypad_up6 [3,3] (Brats.py:416)
+            conv(f"up{d}_conv2x2", PackedView(cur), c, h, w, 2, PackedView(up, 3, 3, 0), False, upconv=True)
+            h, w = uh + 6, uw + 6
+            oy, ox = (eh - h) // 2, (ew - w) // 2                        # crop_tensor (Brats_functions.py:518-526)
+            if oy < 0 or ox < 0:
+                raise RuntimeError("input too small: the skip tensor is smaller than the decoder tensor")
+            c1n = getattr(m, f"up{d}_conv1").kernel_num
+            mid = new(h - 2 + 4, w - 2 + 4, c1n, prefill=fill)           # mypad [2,2] (Brats.py:420)
+            conv(f"up{d}_conv1", PackedView(up), cu, h, w, 3, PackedView(mid, 2, 2, 0), True,
+                 src1=PackedView(enc, oy, ox, 0), c1=ec)
+            h, w = h + 2, w + 2
+            c2n = getattr(m, f"up{d}_conv2").kernel_num
+            out = new(h - 2, w - 2, c2n)
+            conv(f"up{d}_conv2", PackedView(mid), c1n, h, w, 3, PackedView(out), True)
+            cur, c, h, w = out, c2n, h - 2, w - 2
+        # ---- head -----------------------------------------------------------------------------------
+        self.out_hw = (h, w)
+        C = m.n_labels
+        self.p = torch.empty((B, h * w, C), device=dev, dtype=torch.float32)
+        self.v = torch.empty_like(self.p)
+        self.pre_m = torch.empty_like(self.p)
+        self.pre_v = torch.empty_like(self.p)
+        wf, wsf = m.conv_final.weights()
+        last, lc = cur, c
+        steps.append(lambda: F.final_conv_softmax_packed(PackedView(last), B, h, w, lc, wf, wsf, self.p, self.v,
+                                                         self.pre_m, self.pre_v))
+        self.n_launches = len(steps)
+
+    # ------------------------------------------------------------------------------------------------
+    def _launch_all(self) -> None:
+        for s in self._steps:
+            s()
+
+    def forward_resident(self) -> Tuple[Tensor, Tensor]:
+        """Run the forward on whatever is in self.x_in; returns the engine-owned output tensors."""
+        if not self.use_graph:
+            self._launch_all()
+        else:
+            if self._graph is None:
+                # warm-up on a side stream (lazy module loading, smem attribute), then capture
+                side = torch.cuda.Stream(device=self.device)
+                side.wait_stream(torch.cuda.current_stream())
+                with torch.cuda.stream(side):
+                    self._launch_all()
+                torch.cuda.current_stream().wait_stream(side)
+                g = torch.cuda.CUDAGraph()
+                with torch.cuda.graph(g):
+                    self._launch_all()
+                self._graph = g
+            self._graph.replay()
+        return self.p, self.v
+
+    def run(self, x: Tensor, return_presoftmax: bool = False):
+        if not self.matches(x):
+            raise RuntimeError(f"engine built for input {self.shape}, got {tuple(x.shape)}")
+        self.x_in.copy_(x, non_blocking=True)
+        p, v = self.forward_resident()
+        if return_presoftmax:
+            return p.clone(), v.clone(), self.pre_m.clone(), self.pre_v.clone()
+        return p.clone(), v.clone()

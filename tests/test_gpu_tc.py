@@ -177,3 +177,49 @@ def test_tc_rejects_bad_arguments(S):
         F.conv_moments_tc(F.PackedView(buf), 32, 1, 8, 8, 3, 32, wp, s, dst=F.PackedView(out, 1, 0, 0))
     with pytest.raises(RuntimeError):       # kernel size 4
         F.conv_moments_tc(F.PackedView(buf), 32, 1, 8, 8, 4, 32, wp, s, dst=F.PackedView(out))
+
+
+# ------------------------------------------------------------------------------------------------------------
+# whole-network parity of mode='fast' (north_star bars: mean maps 1e-3, variance maps 1e-2, argmax >= 99.9 %)
+# ------------------------------------------------------------------------------------------------------------
+def _fast_vs_oracle(S, variant, C, in_ch, B, alpha):
+    oracle = O.UNetOracle(variant, 32, C, in_ch, torch.float64)
+    w32 = O.make_weights(variant, 32, C, in_ch)
+    model = S.Density_prop_with_pad_UNET(32, C, variant=variant, mode="fast").load_weight_dict(w32, device="cuda")
+    x = O.make_input(variant, B, alpha=alpha)
+    p_ref, v_ref, mf_ref, sf_ref = oracle(x, True)
+    with torch.no_grad():
+        p, v, mf, sf = model(dev(x), return_presoftmax=True)
+        p2, v2 = model(dev(x))                       # second call replays the captured CUDA graph
+    torch.cuda.synchronize()
+    assert torch.equal(p, p2) and torch.equal(v, v2)
+    hw = O.output_hw(variant)
+    assert p.shape == (B, hw * hw, C) and v.shape == p.shape
+    errs = dict(pre_mu=rel(mf.reshape(mf_ref.shape), mf_ref), pre_var=rel(sf.reshape(sf_ref.shape), sf_ref),
+                p=rel(p, p_ref), v=rel(v, v_ref), argmax=O.argmax_agreement(p.cpu(), p_ref))
+    print(variant, errs)
+    assert bool(torch.isfinite(p).all()) and bool(torch.isfinite(v).all()) and float(v.min()) >= 0.0
+    assert errs["pre_mu"] < 1e-3 and errs["p"] < 1e-3, errs
+    assert errs["pre_var"] < 1e-2 and errs["v"] < 1e-2, errs
+    assert errs["argmax"] >= 0.999, errs
+
+
+def test_hippocampus_fast_mode(S):
+    _fast_vs_oracle(S, "hippocampus", 3, 1, 8, 1.0)      # BASELINE.json configs[0]: batch 8
+
+
+@pytest.mark.parametrize("C", [4, 5])
+def test_brats_fast_mode(S, C):
+    _fast_vs_oracle(S, "brats", C, 4, 2, O.BRATS_ALPHA)  # configs[1], alpha-scaled input
+
+
+def test_fast_matches_fp32_mode_at_full_scale_input(S):
+    """alpha = 1 BraTS input saturates the softmax: compare the two CUDA modes pre-softmax."""
+    w32 = O.make_weights("brats", 32, 4, 4)
+    x = dev(O.make_input("brats", 2))
+    fast = S.Density_prop_with_pad_UNET(32, 4, mode="fast").load_weight_dict(w32, device="cuda")
+    slow = S.Density_prop_with_pad_UNET(32, 4, mode="fp32").load_weight_dict(w32, device="cuda")
+    with torch.no_grad():
+        _, _, mf, sf = fast(x, return_presoftmax=True)
+        _, _, mf2, sf2 = slow(x, return_presoftmax=True)
+    assert rel(mf.reshape(mf2.shape), mf2) < 1e-3 and rel(sf.reshape(sf2.shape), sf2) < 1e-2
