@@ -1,0 +1,368 @@
+#!/usr/bin/env python
+"""bench.py -- BraTS SUPER U-Net inference throughput (mean + variance maps) on N B200s.
+
+Contract (one JSON line on rank 0):  python bench.py --gpus N --steps K --warmup W
+  step      = one forward of the moment-propagation U-Net (Brats.py:377-457) over one batch of synthetic slices
+  value     = whole-job slices/s with the batch already resident in HBM (CUDA-graph replay, CUDA events)
+  e2e       = the same through the host-facing call: pinned host batch -> H2D -> forward -> D2H of both maps
+  roofline  = the tcgen05 moment-conv kernel (all of its launches in a step): algorithmic FLOPs / measured time
+  cpu_baseline = the CPU oracle (port of the reference formulas; the TensorFlow reference cannot run here)
+--impl reference times that CPU path alone, on the same config.
+"""
+from __future__ import annotations
+
+import argparse
+import json
+import os
+import statistics
+import subprocess
+import sys
+import threading
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+import torch  # noqa: E402
+
+METRIC = "BraTS slices/sec (mean+var maps)"
+UNIT = "slices/s"
+N_KERNELS, N_LABELS, IN_CH, IN_HW, OUT_HW = 32, 4, 4, 204, 186
+
+
+def peaks():
+    path = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(path):
+        with open(path) as f:
+            d = json.load(f)
+        return dict(hbm=d["hbm_gbs"], tf_burst=d["bf16_tflops"], tf_sustained=d["bf16_tflops_sustained"],
+                    source="measured")
+    return dict(hbm=6650.0, tf_burst=1590.0, tf_sustained=1400.0, source="fallback")
+
+
+def conv_table(variant="brats", n=N_KERNELS, C=N_LABELS, in_ch=IN_CH, H=IN_HW):
+    """Per-layer geometry and ALGORITHMIC work per slice: two GEMMs per moment conv
+    (mean, W^2 variance), one for the first conv, four parity GEMMs (K = Cin) x 2 for an up-conv; the rank-1
+    term, ReLU, pooling and softmax count zero FLOPs.  bytes = packed in (6 B / element) + packed out."""
+    from oracle.supernet_oracle import unet_conv_specs
+    specs = {s.name: s for s in unet_conv_specs(variant, n, C, in_ch)}
+    rows = []
+    levels = 4 if variant == "brats" else 2
+    h = H
+
+    def add(name, hin, up=False, concat_from=None):
+        s = specs[name]
+        if up:
+            hout = 2 * hin
+            flops = 2 * (2.0 * hin * hin * s.cin * s.cout * 4)
+            k_in_bytes = hin * hin * s.cin * 6
+        else:
+            hout = hin - s.k + 1
+            gemms = 1 if name == "conv_input" else 2
+            flops = gemms * 2.0 * hout * hout * s.k * s.k * s.cin * s.cout
+            k_in_bytes = hin * hin * s.cin * (4 if name == "conv_input" else 6)
+        out_bytes = hout * hout * s.cout * (8 if name == "conv_final" else 6)
+        rows.append(dict(name=name, hin=hin, hout=hout, cin=s.cin, cout=s.cout, k=s.k, flops=flops,
+                         bytes=k_in_bytes + out_bytes))
+        return hout
+
+    h = add("conv_input", h)
+    h = add("conv1", h)
+    skip = [h]
+    ci = 2
+    for lvl in range(1, levels + 1):
+        h = (h + 1) // 2
+        if variant == "brats" and lvl == levels:
+            h += 1
+        for _ in range(2):
+            h = add(f"conv{ci}", h)
+            ci += 1
+        if lvl < levels:
+            skip.append(h)
+    for d in range(1, levels + 1):
+        h = add(f"up{d}_conv2x2", h, up=True) + 6
+        h = add(f"up{d}_conv1", h) + 4
+        h = add(f"up{d}_conv2", h)
+    add("conv_final", h)
+    return rows
+
+
+class ClockSampler:
+    """nvidia-smi clocks / throttle reasons sampled DURING the timed region (B200_PROFILING.md recipe)."""
+    Q = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,clocks_event_reasons.hw_slowdown,"
+         "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,"
+         "clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, gpu_index: int):
+        self.idx = gpu_index
+        self.rows = []
+        self.proc = None
+
+    def start(self):
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits",
+                                          "-lms", "100", "-i", str(self.idx)], stdout=subprocess.PIPE,
+                                         stderr=subprocess.DEVNULL, text=True)
+            self.th = threading.Thread(target=self._read, daemon=True)
+            self.th.start()
+        except Exception:
+            self.proc = None
+
+    def _read(self):
+        for line in self.proc.stdout:
+            self.rows.append([c.strip() for c in line.split(",")])
+
+    def stop(self):
+        if self.proc is None:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        time.sleep(0.15)
+        self.proc.terminate()
+        try:
+            self.proc.wait(timeout=2)
+        except Exception:
+            self.proc.kill()
+        sm, mx, reasons, power = [], [], set(), []
+        for r in self.rows:
+            try:
+                sm.append(float(r[1])); mx.append(float(r[2])); power.append(float(r[3]))
+            except Exception:
+                continue
+            for name, col in (("hw_slowdown", 5), ("hw_thermal_slowdown", 6), ("sw_thermal_slowdown", 7),
+                              ("sw_power_cap", 8)):
+                if len(r) > col and r[col].lower().startswith("active"):
+                    reasons.add(name)
+        return {"sm_mhz": statistics.median(sm) if sm else None, "sm_max_mhz": max(mx) if mx else None,
+                "power_w_max": max(power) if power else None, "samples": len(sm), "reasons": sorted(reasons)}
+
+
+def cpu_baseline(seconds_budget: float = 15.0, form: str = "as_written"):
+    """The reference's CPU path restated (oracle, fp32, torch-CPU, all host threads) on a bounded sample of the
+    BraTS workload."""
+    from oracle import supernet_oracle as O
+    cores = os.cpu_count() or 1
+    torch.set_num_threads(cores)
+    oracle = O.UNetOracle("brats", N_KERNELS, N_LABELS, IN_CH, torch.float32, form=form)
+    x = O.make_input("brats", 1, alpha=O.BRATS_ALPHA)
+    with torch.no_grad():
+        oracle(x)                                  # warm-up
+        t0 = time.perf_counter()
+        oracle(x)
+        one = time.perf_counter() - t0
+        n = max(2, min(64, int(seconds_budget / max(one, 1e-3))))
+        t0 = time.perf_counter()
+        for _ in range(n):
+            oracle(x)
+        dt = time.perf_counter() - t0
+    return {"value": n / dt, "unit": UNIT, "cores": torch.get_num_threads(), "kind": "port",
+            "sample": f"{n} BraTS slices, batch 1, fp32 torch-CPU oracle ({form} form: the reference's op sequence "
+                      f"conv2d + extract_patches + 3 matmuls per layer)"}
+
+
+def run_reference(args):
+    """--impl reference: the CPU restatement of the reference path (TensorFlow itself is not installable in this
+    image), one slice per step, all host threads."""
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    from oracle import supernet_oracle as O
+    cores = os.cpu_count() or 1
+    torch.set_num_threads(cores)
+    oracle = O.UNetOracle("brats", N_KERNELS, N_LABELS, IN_CH, torch.float32, form="as_written")
+    x = O.make_input("brats", 1, alpha=O.BRATS_ALPHA)
+    with torch.no_grad():
+        for _ in range(max(1, min(args.warmup, 3))):
+            oracle(x)
+        steps = min(args.steps, 40)
+        t0 = time.perf_counter()
+        for _ in range(steps):
+            oracle(x)
+        dt = time.perf_counter() - t0
+    v = steps / dt
+    sample = "1 BraTS slice per step (bounded sample of the batch), as-written op sequence, fp32 torch-CPU"
+    print(json.dumps({
+        "impl": "reference", "metric": METRIC, "value": v, "unit": UNIT, "n_gpus": args.gpus, "steps": steps,
+        "warmup": args.warmup, "ms_per_step": 1e3 * dt / steps, "higher_is_better": True, "scaling": "weak",
+        "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+        "config": {"workload": f"BraTS SUPER U-Net inference 204x204x4 -> 186x186x{N_LABELS} mean+variance maps, "
+                               f"n_kernels {N_KERNELS}, random-init weights", "sample": sample},
+        "cpu_baseline": {"value": v, "unit": UNIT, "cores": torch.get_num_threads(), "kind": "port",
+                         "sample": sample},
+        "e2e": {"value": v, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+        "gpu_launches": 0,
+    }))
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=30)
+    ap.add_argument("--warmup", type=int, default=5)
+    ap.add_argument("--batch", type=int, default=64, help="slices per GPU per step")
+    ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
+    ap.add_argument("--mode", default="fast", choices=["fast", "fp32"])
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    args = ap.parse_args()
+    args.warmup = max(args.warmup, 3)
+
+    if args.impl == "reference":
+        run_reference(args)
+        return
+
+    import torch.distributed as dist
+    import supernet_b200 as S
+    from oracle import supernet_oracle as O   # weight/input generators only (shared with the parity tests)
+
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    rank = int(os.environ.get("RANK", "0"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py needs a CUDA device (the product path has no CPU fallback)")
+    torch.cuda.set_device(local)
+    dev = torch.device("cuda", local)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=dev)
+    S._lib.check(S._lib.load().sn_device_check(), "device_check")
+
+    B = args.batch
+    weights = O.make_weights("brats", N_KERNELS, N_LABELS, IN_CH)
+    model = S.Density_prop_with_pad_UNET(N_KERNELS, N_LABELS, variant="brats", mode=args.mode)
+    model.load_weight_dict(weights, device=dev)
+    # every rank draws its own shard of the global batch (slices are independent: no collective on the data path)
+    x_host = O.make_input("brats", B, seed=2025 + rank, alpha=O.BRATS_ALPHA).pin_memory()
+
+    def barrier():
+        torch.cuda.synchronize()
+        if world > 1:
+            dist.barrier()
+            torch.cuda.synchronize()
+
+    table = conv_table()
+    flops_slice = sum(r["flops"] for r in table)
+    pk = peaks()
+
+    if args.mode == "fast":
+        from supernet_b200.engine import InferenceEngine
+        eng = InferenceEngine(model, B, IN_HW, IN_HW, IN_CH, dev, graph=True)
+        eng.x_in.copy_(x_host, non_blocking=True)
+        step = eng.forward_resident
+        launches_per_step = eng.n_launches
+        p_host = torch.empty((B, OUT_HW * OUT_HW, N_LABELS), dtype=torch.float32).pin_memory()
+        v_host = torch.empty_like(p_host).pin_memory()
+
+        def step_e2e():
+            eng.x_in.copy_(x_host, non_blocking=True)
+            p, v = eng.forward_resident()
+            p_host.copy_(p, non_blocking=True)
+            v_host.copy_(v, non_blocking=True)
+    else:
+        x_dev = x_host.to(dev)
+        launches_per_step = None
+
+        def step():
+            with torch.no_grad():
+                return model(x_dev)
+        p_host = torch.empty((B, OUT_HW * OUT_HW, N_LABELS), dtype=torch.float32).pin_memory()
+        v_host = torch.empty_like(p_host).pin_memory()
+
+        def step_e2e():
+            with torch.no_grad():
+                p, v = model(x_host.to(dev, non_blocking=True))
+            p_host.copy_(p, non_blocking=True)
+            v_host.copy_(v, non_blocking=True)
+
+    def timed(fn, steps, warmup):
+        for _ in range(warmup):
+            fn()
+        barrier()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        for _ in range(steps):
+            fn()
+        e1.record()
+        barrier()
+        ms = e0.elapsed_time(e1)
+        if world > 1:
+            t = torch.tensor([ms], device=dev, dtype=torch.float64)
+            dist.all_reduce(t, op=dist.ReduceOp.MAX)
+            ms = float(t)
+        return ms
+
+    sampler = ClockSampler(local)
+    if rank == 0:
+        sampler.start()
+    ms = timed(step, args.steps, args.warmup)
+    clocks = sampler.stop() if rank == 0 else None
+    ms_e2e = timed(step_e2e, args.steps, args.warmup)
+
+    value = world * B * args.steps / (ms * 1e-3)
+    e2e = world * B * args.steps / (ms_e2e * 1e-3)
+
+    # ---- per-kernel pass (rank 0): every launch of the layer sequence timed alone with CUDA events ------------
+    roofline, kernels = None, None
+    if rank == 0 and args.mode == "fast":
+        reps = 5
+        per = []
+        for i, s in enumerate(eng._steps):
+            s()
+            torch.cuda.synchronize()
+            a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            a.record()
+            for _ in range(reps):
+                s()
+            b.record()
+            torch.cuda.synchronize()
+            per.append(a.elapsed_time(b) / reps)
+        names = eng.step_names
+        kernels = []
+        tc_ms, tc_flops, other_ms, other_bytes = 0.0, 0.0, 0.0, 0.0
+        tmap = {r["name"]: r for r in table}
+        for nm, t in zip(names, per):
+            row = {"name": nm, "ms": round(t, 4)}
+            if nm in tmap:
+                r = tmap[nm]
+                row["tflops"] = round(r["flops"] * B / (t * 1e-3) / 1e12, 1)
+                row["gbs"] = round(r["bytes"] * B / (t * 1e-3) / 1e9, 0)
+                if nm not in ("conv_input", "conv_final"):
+                    tc_ms += t
+                    tc_flops += r["flops"] * B
+                else:
+                    other_ms += t
+                    other_bytes += r["bytes"] * B
+            kernels.append(row)
+        achieved = tc_flops / (tc_ms * 1e-3) / 1e12
+        roofline = {"kernel": "conv_moments_tc_kernel (22 launches/step: all tcgen05 moment convs)", "bound": "tensor",
+                    "achieved": round(achieved, 1), "peak": pk["tf_sustained"], "unit": "TFLOP/s",
+                    "frac": round(achieved / pk["tf_sustained"], 4), "traffic": None,
+                    "peak_source": f"{pk['source']} bf16 sustained", "share_of_step": round(tc_ms / sum(per), 3),
+                    "algorithmic_gflop_per_slice": round(flops_slice / 1e9, 3)}
+
+    if rank == 0:
+        out = {
+            "metric": METRIC, "value": round(value, 1), "unit": UNIT, "n_gpus": world, "steps": args.steps,
+            "warmup": args.warmup, "ms_per_step": round(ms / args.steps, 4), "higher_is_better": True,
+            "scaling": "weak", "vs_baseline": None,
+            "dtype": "bf16x3 mean / bf16 variance operands, f32 accumulate" if args.mode == "fast" else "f32",
+            "data": "synthetic",
+            "config": {"workload": f"BraTS SUPER U-Net inference 204x204x4 -> 186x186x{N_LABELS} mean+variance maps, "
+                                   f"n_kernels {N_KERNELS}, random-init weights (BASELINE.json configs[1])",
+                       "batch_per_gpu": B, "global_batch": B * world, "mode": args.mode,
+                       "parallelism": f"batch-sharded x{world}, no data-path collective",
+                       "l2_policy": "per-step activation traffic (~%.1f GB) >> 126 MB L2, no flush needed"
+                                    % (sum(r["bytes"] for r in table) * B / 1e9)},
+            "e2e": {"value": round(e2e, 1), "unit": UNIT, "h2d_bytes_per_step": int(x_host.numel() * 4),
+                    "d2h_bytes_per_step": int(2 * p_host.numel() * 4), "ms_per_step": round(ms_e2e / args.steps, 4)},
+            "gpu_launches": (launches_per_step or 0) * args.steps,
+            "clocks": clocks,
+        }
+        if roofline:
+            out["roofline"] = roofline
+            out["kernels"] = kernels
+        if not args.no_cpu_baseline and world == 1:
+            out["cpu_baseline"] = cpu_baseline()
+        print(json.dumps(out))
+    if world > 1:
+        dist.destroy_process_group()
+
+
+if __name__ == "__main__":
+    main()

@@ -31,6 +31,7 @@ class InferenceEngine:
         self.use_graph = graph
         self._graph: Optional[torch.cuda.CUDAGraph] = None
         self._steps: List[Callable[[], None]] = []
+        self.step_names: List[str] = []
         self._weights_version = None
         self._build()
 
@@ -74,6 +75,7 @@ class InferenceEngine:
         def conv(name, src: PackedView, c0, h, w, k, dst: PackedView, relu, src1=None, c1=0, upconv=False):
             wp, s = self.prepared[name]
             cout = getattr(m, name).kernel_num
+            self.step_names.append(name)
             steps.append(lambda: F.conv_moments_tc(src, c0, B, h, w, k, cout, wp, s, dst=dst, relu=relu,
                                                    upconv=upconv, src1=src1, c1=c1))
 
@@ -81,6 +83,7 @@ class InferenceEngine:
         h, w = H - 2, W - 2
         a0 = new(h, w, n)
         w_in, ws_in = m.conv_input.weights()
+        self.step_names.append("conv_input")
         steps.append(lambda: F.first_conv_packed(self.x_in, w_in, ws_in, PackedView(a0), relu=True))
         skip = new(h - 2, w - 2, n)
         conv("conv1", PackedView(a0), n, h, w, 3, PackedView(skip), True)
@@ -97,6 +100,7 @@ class InferenceEngine:
             else:
                 pooled = new(ph, pw, c)
                 pview = PackedView(pooled)
+            self.step_names.append(f"pool{lvl}")
             steps.append(lambda s=PackedView(cur), hh=h, ww=w, cc=c, d=pview: F.maxpool2_packed(s, B, hh, ww, cc, d))
             h, w = ph, pw
             cur = pooled
@@ -138,6 +142,7 @@ class InferenceEngine:
         self.pre_v = torch.empty_like(self.p)
         wf, wsf = m.conv_final.weights()
         last, lc = cur, c
+        self.step_names.append("conv_final")
         steps.append(lambda: F.final_conv_softmax_packed(PackedView(last), B, h, w, lc, wf, wsf, self.p, self.v,
                                                          self.pre_m, self.pre_v))
         self.n_launches = len(steps)
