@@ -174,7 +174,7 @@ size_t sn_prepared_weight_bytes(int32_t ksize, int32_t cin, int32_t cout);
 int sn_prepare_weights(const float* w_mu, const float* w_sigma, int32_t ksize, int32_t cin, int32_t cout,
                        int32_t upconv, void* w_packed, float* s_out, sn_stream_t st);
 
-enum { SN_TC_RELU = 1, SN_TC_UPCONV = 2, SN_TC_DST_F32 = 4 };
+enum { SN_TC_RELU = 1, SN_TC_UPCONV = 2, SN_TC_DST_F32 = 4, SN_TC_IM2COL = 8 };
 
 /* One fused moment convolution on the tensor cores: myConv_intermediate.call (Brats.py:118-137), optionally
  * with the ReLU gate of Brats.py:233-238 (SN_TC_RELU), reading the channel-concat of up to two packed windows
@@ -183,7 +183,9 @@ enum { SN_TC_RELU = 1, SN_TC_UPCONV = 2, SN_TC_DST_F32 = 4 };
  *   - SN_TC_UPCONV (ksize must be 2, weights prepared with upconv = 1): myupsampling + the 2x2 conv
  *     (Brats.py:414-415) as four parity GEMMs; output pixel (2y+a, 2x+b) of a 2*in_h x 2*in_w window;
  *   - SN_TC_DST_F32: write fp32 NHWC mean/variance (dst_mu, dst_var: contiguous [batch,out_h,out_w,cout])
- *     instead of the packed window dst. */
+ *     instead of the packed window dst;
+ *   - SN_TC_IM2COL: run the first-generation kernel (one CTA per 128-pixel tile, TMA im2col loads per tap)
+ *     instead of the default persistent halo-tiled kernel; same results, kept for A/B measurements. */
 typedef struct sn_tc_conv_desc {
   sn_packed_view src[2];
   int32_t src_c[2];       /* channels taken from each source (src_c[1] == 0: single source) */

@@ -43,7 +43,7 @@ class sn_tc_conv_desc(C.Structure):
 
 
 SN_CONV_RELU = 1
-SN_TC_RELU, SN_TC_UPCONV, SN_TC_DST_F32 = 1, 2, 4
+SN_TC_RELU, SN_TC_UPCONV, SN_TC_DST_F32, SN_TC_IM2COL = 1, 2, 4, 8
 
 
 def header_path() -> str:

@@ -385,6 +385,8 @@ static int launch_tc(const TcMaps& maps, const TcP& p, int n_tiles, cudaStream_t
   return check_launch("conv_moments_tc");
 }
 
+int conv_moments_halo_dispatch(const sn_tc_conv_desc* d, cudaStream_t stream);   // sn_tc_halo.cu
+
 }  // namespace sn
 
 using namespace sn;
@@ -421,6 +423,8 @@ extern "C" int sn_conv_moments_fwd_tc(const sn_tc_conv_desc* d, sn_stream_t st) 
   } else {
     if ((rc = check_view(d->dst, d->batch, out_h, out_w, d->cout, "conv_tc dst"))) return rc;
   }
+
+  if (!(d->flags & SN_TC_IM2COL)) return conv_moments_halo_dispatch(d, as_stream(st));
 
   const int nt = d->cout % 128 == 0 ? 128 : (d->cout % 64 == 0 ? 64 : 32);
   const int groups = upconv ? 4 : 1;

@@ -1,0 +1,559 @@
+// FAST mode moment convolution, second generation: persistent, halo-tiled tcgen05 / TMEM kernel.
+//
+// The im2col kernel (sn_tc_conv.cu) pulls every input pixel k*k times from L2 -- measured on B200 the
+// 32/64-channel BraTS layers sit at the L2->SM feed limit (lts 57 %, tensor pipe 13 %, DRAM 15 %).  Here a
+// CTA loads one HALO box of the input per 32-channel block (TMA tiled 4-D box {32 ch, R cols, TH+k-1 rows, TN
+// images}; smem row = pixel, 64-byte swizzled rows) and all k*k filter taps read it IN PLACE: the A operand of
+// tap (kh,kw) is the same tile with its UMMA descriptor start address advanced by (kh*R + kw) rows.  (Probed
+// on B200: the swizzle XOR is applied to absolute smem address bits, so any row shift is legal with
+// base_offset = 0; tools/probe_shift.cu.)  GEMM row j of the 128-row tile is halo pixel j = (n*THb + y)*R + x;
+// rows with x >= R-(k-1) or y >= THb-(k-1) are junk and never stored.  Consequences:
+//   * L2->smem bytes per output pixel drop ~k*k-fold for A; for small layers the prepared weights stay
+//     RESIDENT in smem for the CTA's whole life (persistent tile loop), so only activations stream;
+//   * the rank-1 term needs q[pixel] = sum_c(mu^2+var) once per halo pixel (not once per tap):
+//     r[j] = sum_taps q[j + kh*R + kw] from a 1 KB smem array;
+//   * two TMEM accumulator stages + two epilogue warp groups: the epilogue of tile i overlaps the TMA/UMMA
+//     main loop of tile i+1.
+// Warp roles (320 threads): warp 0 TMA producer, warp 1 UMMA issuer (+TMEM alloc), warps 2-5 / 6-9 = group 0 / 1
+// (q reduction during the main loop of their tile, then epilogue).  Same math and data layout as sn_tc_conv.cu
+// (Brats.py:118-137 incl. ReLU :233-238, pad :159-163, concat :247-261, unpool+2x2 conv :178-203,414-415).
+#include "sn_common.cuh"
+#include "sn_sm100.cuh"
+
+#include <cuda.h>
+#include <mutex>
+
+namespace sn {
+
+constexpr int HL_BM = 128;
+constexpr int HL_KC = 32;
+constexpr int HL_THREADS = 320;
+constexpr int HL_MAX_BSLOTS = 36;
+constexpr int HL_MAX_ASTAGES = 4;
+constexpr int HL_SMEM = 232448;        // 227 KB: always requested so exactly one CTA owns an SM (and its TMEM)
+
+struct HlMaps {
+  CUtensorMap a[2][3];
+  CUtensorMap w;
+};
+
+struct HlP {
+  int tiles_x, tiles_y, tiles_b, tiles_n, total_tiles;
+  int TWo, THo;            // valid output columns / rows per tile
+  int R, THb, TN;          // halo box: columns, rows, images
+  int rows_box;            // R * THb * TN  (<= 254)
+  int a_plane;             // bytes reserved per A plane per stage (multiple of 1024)
+  int ksize, taps_w;       // K-side taps per dim; taps in the prepared weights
+  int cblk0, cblk1;
+  int Ho, Wo, B;           // valid output extents (upconv: the input grid)
+  int cout, relu, upconv, dst_f32;
+  int sa, sb, b_resident;  // A stages, B slots, weights resident?
+  __nv_bfloat16* dst;
+  int dh, dw, dc, dy0, dx0, dc0;
+  float* dst_mu;
+  float* dst_var;
+  int out_h, out_w;
+  const float* s;
+};
+
+__device__ __forceinline__ float hl_lo(uint32_t v) { return __uint_as_float(v << 16); }
+__device__ __forceinline__ float hl_hi(uint32_t v) { return __uint_as_float(v & 0xFFFF0000u); }
+__device__ __forceinline__ uint32_t hl_pack2(float a, float b) {
+  __nv_bfloat162 t = __floats2bfloat162_rn(a, b);
+  return *reinterpret_cast<uint32_t*>(&t);
+}
+__device__ __forceinline__ void named_bar_sync(int id, int threads) {
+  asm volatile("bar.sync %0, %1;" ::"r"(id), "r"(threads) : "memory");
+}
+
+template <int NT>
+__global__ void __launch_bounds__(HL_THREADS, 1) conv_moments_halo_kernel(const __grid_constant__ HlMaps maps,
+                                                                          const HlP p) {
+  constexpr int B_PLANE = NT * HL_KC * 2;
+  constexpr int B_SLOT = 3 * B_PLANE;
+  extern __shared__ uint8_t smem_raw[];
+  const uint32_t smem_base = (ptx::smem_u32(smem_raw) + 1023u) & ~1023u;
+  uint8_t* smem_gen = smem_raw + (smem_base - ptx::smem_u32(smem_raw));
+  const int a_stage = 3 * p.a_plane;
+  const uint32_t b_base = smem_base + p.sa * a_stage;
+  const uint32_t bar_base = b_base + p.sb * B_SLOT;           // 1 KB barrier block, then 2 KB q buffers
+  auto a_full = [&](int s) { return bar_base + 8u * s; };
+  auto a_empty = [&](int s) { return bar_base + 8u * (HL_MAX_ASTAGES + s); };
+  auto b_full = [&](int s) { return bar_base + 8u * (2 * HL_MAX_ASTAGES + s); };
+  auto b_empty = [&](int s) { return bar_base + 8u * (2 * HL_MAX_ASTAGES + HL_MAX_BSLOTS + s); };
+  auto acc_full = [&](int s) { return bar_base + 8u * (2 * HL_MAX_ASTAGES + 2 * HL_MAX_BSLOTS + s); };
+  auto acc_empty = [&](int s) { return bar_base + 8u * (2 * HL_MAX_ASTAGES + 2 * HL_MAX_BSLOTS + 2 + s); };
+  const uint32_t tmem_slot = bar_base + 8u * (2 * HL_MAX_ASTAGES + 2 * HL_MAX_BSLOTS + 4);
+  const int bar_off = p.sa * a_stage + p.sb * B_SLOT;
+  volatile uint32_t* tmem_slot_gen =
+      reinterpret_cast<volatile uint32_t*>(smem_gen + bar_off + 8 * (2 * HL_MAX_ASTAGES + 2 * HL_MAX_BSLOTS + 4));
+  float* qbuf = reinterpret_cast<float*>(smem_gen + bar_off + 1024);     // [2 groups][256]
+
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int cblk = p.cblk0 + p.cblk1;
+  const int taps = p.ksize * p.ksize;
+
+  if (warp == 0 && lane == 0) {
+    for (int s = 0; s < 2; ++s)
+      for (int pl = 0; pl < 3; ++pl) ptx::prefetch_tensormap(&maps.a[s][pl]);
+    ptx::prefetch_tensormap(&maps.w);
+    for (int s = 0; s < p.sa; ++s) {
+      ptx::mbar_init(a_full(s), 1);
+      ptx::mbar_init(a_empty(s), 5);          // UMMA commit + 4 warps of the reducing group
+    }
+    for (int s = 0; s < p.sb; ++s) {
+      ptx::mbar_init(b_full(s), 1);
+      ptx::mbar_init(b_empty(s), 1);
+    }
+    for (int s = 0; s < 2; ++s) {
+      ptx::mbar_init(acc_full(s), 1);
+      ptx::mbar_init(acc_empty(s), 4);        // 4 epilogue warps
+    }
+    ptx::fence_barrier_init();
+  }
+  if (warp == 1) {
+    ptx::tmem_alloc(tmem_slot, 4 * NT);       // 2 stages x (mean, var) x NT columns: 128 / 256 / 512
+    ptx::tmem_relinquish();
+  }
+  ptx::tc_fence_before();
+  __syncthreads();
+  ptx::tc_fence_after();
+  const uint32_t tmem_base = *tmem_slot_gen;
+
+  if (warp == 0) {
+    // ===================== TMA producer =====================
+    if (lane == 0) {
+      int ai = 0, bi = 0;     // running A-stage / B-slot fill counters
+      for (int tile = blockIdx.x, titer = 0; tile < p.total_tiles; tile += gridDim.x, ++titer) {
+        const int nt_i = tile % p.tiles_n;
+        int t = tile / p.tiles_n;
+        const int tx = t % p.tiles_x; t /= p.tiles_x;
+        const int ty = t % p.tiles_y;
+        const int tb = t / p.tiles_y;
+        const int ncol0 = nt_i * NT;
+        const int group = ncol0 / p.cout;
+        const int n0 = ncol0 - group * p.cout;
+        const int x0 = tx * p.TWo, y0 = ty * p.THo, b0 = tb * p.TN;
+        for (int cbt = 0; cbt < cblk; ++cbt) {
+          {
+            const int stage = ai % p.sa;
+            const uint32_t parity = (uint32_t)(ai / p.sa) & 1u;
+            ++ai;
+            ptx::mbar_wait(a_empty(stage), parity ^ 1u);
+            ptx::mbar_arrive_expect_tx(a_full(stage), (uint32_t)(3 * p.rows_box * 64));
+            const int src = cbt >= p.cblk0 ? 1 : 0;
+            const int cb = src ? cbt - p.cblk0 : cbt;
+            const uint32_t sa_addr = smem_base + stage * a_stage;
+#pragma unroll
+            for (int pl = 0; pl < 3; ++pl) {
+              asm volatile(
+                  "cp.async.bulk.tensor.4d.shared::cluster.global.mbarrier::complete_tx::bytes"
+                  " [%0], [%1, {%3, %4, %5, %6}], [%2];"
+                  :
+                  : "r"(sa_addr + pl * p.a_plane), "l"(reinterpret_cast<uint64_t>(&maps.a[src][pl])),
+                    "r"(a_full(stage)), "r"(cb * HL_KC), "r"(x0), "r"(y0), "r"(b0)
+                  : "memory");
+            }
+          }
+          if (!p.b_resident || titer == 0) {
+            for (int tap = 0; tap < taps; ++tap) {
+              int slot;
+              if (p.b_resident) {
+                slot = cbt * taps + tap;
+              } else {
+                slot = bi % p.sb;
+                const uint32_t parity = (uint32_t)(bi / p.sb) & 1u;
+                ++bi;
+                ptx::mbar_wait(b_empty(slot), parity ^ 1u);
+              }
+              ptx::mbar_arrive_expect_tx(b_full(slot), (uint32_t)B_SLOT);
+              const uint32_t sb_addr = b_base + slot * B_SLOT;
+              const int wtap = p.upconv ? group : tap;
+#pragma unroll
+              for (int pl = 0; pl < 3; ++pl)
+                ptx::tma_load_3d(sb_addr + pl * B_PLANE, &maps.w, b_full(slot), cbt * HL_KC, n0,
+                                 pl * p.taps_w + wtap);
+            }
+          }
+        }
+      }
+    }
+  } else if (warp == 1) {
+    // ===================== UMMA issuer =====================
+    if (lane == 0) {
+      constexpr uint32_t idesc = ptx::idesc_bf16_f32(HL_BM, NT);
+      int ai = 0, bi = 0;
+      for (int tile = blockIdx.x, titer = 0; tile < p.total_tiles; tile += gridDim.x, ++titer) {
+        const int as = titer & 1;
+        ptx::mbar_wait(acc_empty(as), (((uint32_t)titer >> 1) & 1u) ^ 1u);
+        ptx::tc_fence_after();
+        const uint32_t acc_mu = tmem_base + as * 2 * NT, acc_var = acc_mu + NT;
+        for (int cbt = 0; cbt < cblk; ++cbt) {
+          const int stage = ai % p.sa;
+          const uint32_t aparity = (uint32_t)(ai / p.sa) & 1u;
+          ++ai;
+          ptx::mbar_wait(a_full(stage), aparity);
+          ptx::tc_fence_after();
+          const uint32_t sa_addr = smem_base + stage * a_stage;
+          for (int tap = 0; tap < taps; ++tap) {
+            int slot;
+            if (p.b_resident) {
+              slot = cbt * taps + tap;
+              ptx::mbar_wait(b_full(slot), 0);
+            } else {
+              slot = bi % p.sb;
+              const uint32_t parity = (uint32_t)(bi / p.sb) & 1u;
+              ++bi;
+              ptx::mbar_wait(b_full(slot), parity);
+            }
+            ptx::tc_fence_after();
+            const int kh = tap / p.ksize, kw = tap - kh * p.ksize;
+            const uint32_t shift = (uint32_t)(kh * p.R + kw) * 64u;     // tap = row offset into the halo tile
+            const uint32_t sb_addr = b_base + slot * B_SLOT;
+#pragma unroll
+            for (int ks = 0; ks < HL_KC / 16; ++ks) {
+              const uint32_t koff = ks * 32;
+              const uint64_t a_hi = ptx::smem_desc_kmajor<64>(sa_addr + shift + koff);
+              const uint64_t a_lo = ptx::smem_desc_kmajor<64>(sa_addr + p.a_plane + shift + koff);
+              const uint64_t a_vr = ptx::smem_desc_kmajor<64>(sa_addr + 2 * p.a_plane + shift + koff);
+              const uint64_t b_hi = ptx::smem_desc_kmajor<64>(sb_addr + koff);
+              const uint64_t b_lo = ptx::smem_desc_kmajor<64>(sb_addr + B_PLANE + koff);
+              const uint64_t b_sq = ptx::smem_desc_kmajor<64>(sb_addr + 2 * B_PLANE + koff);
+              const uint32_t acc = (cbt > 0 || tap > 0 || ks > 0) ? 1u : 0u;
+              ptx::umma_bf16(acc_mu, a_hi, b_hi, idesc, acc);
+              ptx::umma_bf16(acc_mu, a_lo, b_hi, idesc, 1u);
+              ptx::umma_bf16(acc_mu, a_hi, b_lo, idesc, 1u);
+              ptx::umma_bf16(acc_var, a_vr, b_sq, idesc, acc);
+            }
+            if (!p.b_resident) ptx::umma_commit(b_empty(slot));
+          }
+          ptx::umma_commit(a_empty(stage));
+        }
+        ptx::umma_commit(acc_full(as));
+      }
+    }
+  } else {
+    // ===================== q reduction + epilogue (two alternating groups) =====================
+    const int grp = (warp - 2) >> 2;
+    const int q = warp & 3;
+    const int row = q * 32 + lane;            // GEMM row == TMEM lane == halo pixel index
+    float* myq = qbuf + grp * 256;
+    int x = row % p.R;
+    int yy = row / p.R;
+    const int y = yy % p.THb;
+    const int n = yy / p.THb;
+    const int nt_tiles = p.total_tiles;
+    for (int tile = blockIdx.x, titer = 0; tile < nt_tiles; tile += gridDim.x, ++titer) {
+      if ((titer & 1) != grp) continue;
+      // A-stage counter of this tile's first channel block: every tile consumes cblk stages
+      int ai = titer * cblk;
+      float q0 = 0.f, q1 = 0.f;
+      for (int cbt = 0; cbt < cblk; ++cbt, ++ai) {
+        const int stage = ai % p.sa;
+        const uint32_t parity = (uint32_t)(ai / p.sa) & 1u;
+        ptx::mbar_wait(a_full(stage), parity);
+        const uint8_t* a = smem_gen + stage * a_stage;
+#pragma unroll
+        for (int h = 0; h < 2; ++h) {
+          const int rr = row + h * 128;
+          if (rr < p.rows_box) {
+            const uint8_t* ar = a + rr * 64;
+            float acc = 0.f;
+#pragma unroll
+            for (int j = 0; j < 4; ++j) {
+              const int ch = ((j + (rr >> 1)) & 3) * 16;   // chunk rotation: conflict-free, order-insensitive sum
+              const uint4 hh4 = *reinterpret_cast<const uint4*>(ar + ch);
+              const uint4 ll4 = *reinterpret_cast<const uint4*>(ar + p.a_plane + ch);
+              const uint4 vv4 = *reinterpret_cast<const uint4*>(ar + 2 * p.a_plane + ch);
+              const uint32_t hh[4] = {hh4.x, hh4.y, hh4.z, hh4.w}, ll[4] = {ll4.x, ll4.y, ll4.z, ll4.w},
+                             vv[4] = {vv4.x, vv4.y, vv4.z, vv4.w};
+#pragma unroll
+              for (int e = 0; e < 4; ++e) {
+                const float m_a = hl_lo(hh[e]) + hl_lo(ll[e]);
+                const float m_b = hl_hi(hh[e]) + hl_hi(ll[e]);
+                acc = fmaf(m_a, m_a, acc);
+                acc = fmaf(m_b, m_b, acc);
+                acc += hl_lo(vv[e]) + hl_hi(vv[e]);
+              }
+            }
+            if (h == 0) q0 += acc; else q1 += acc;
+          }
+        }
+        __syncwarp();
+        if (lane == 0) ptx::mbar_arrive(a_empty(stage));
+      }
+      myq[row] = q0;
+      myq[row + 128] = q1;                     // rows >= rows_box hold 0
+      named_bar_sync(1 + grp, 128);
+      float r = 0.f;
+      for (int kh = 0; kh < p.ksize; ++kh)
+        for (int kw = 0; kw < p.ksize; ++kw) {
+          const int idx = row + kh * p.R + kw;
+          r += idx < 256 ? myq[idx] : 0.f;
+        }
+      named_bar_sync(1 + grp, 128);           // everyone has read before the next tile overwrites myq
+
+      // ---- tile coordinates
+      const int nt_i = tile % p.tiles_n;
+      int t = tile / p.tiles_n;
+      const int tx = t % p.tiles_x; t /= p.tiles_x;
+      const int ty = t % p.tiles_y;
+      const int tb = t / p.tiles_y;
+      const int ncol0 = nt_i * NT;
+      const int group = ncol0 / p.cout;
+      const int n0 = ncol0 - group * p.cout;
+      const int ox_i = tx * p.TWo + x, oy_i = ty * p.THo + y, ob = tb * p.TN + n;
+      const bool valid = x < p.TWo && y < p.THo && n < p.TN && ox_i < p.Wo && oy_i < p.Ho && ob < p.B;
+      int oy = oy_i, ox = ox_i;
+      if (p.upconv) { oy = 2 * oy_i + (group >> 1); ox = 2 * ox_i + (group & 1); }
+      __nv_bfloat16* d_hi = nullptr;
+      float *f_mu = nullptr, *f_var = nullptr;
+      if (valid) {
+        if (p.dst_f32) {
+          const size_t o = (((size_t)ob * p.out_h + oy) * p.out_w + ox) * p.cout + n0;
+          f_mu = p.dst_mu + o;
+          f_var = p.dst_var + o;
+        } else {
+          d_hi = p.dst + ((((size_t)ob * p.dh + oy + p.dy0) * p.dw + ox + p.dx0) * 3) * p.dc + p.dc0 + n0;
+        }
+      }
+      const int as = titer & 1;
+      ptx::mbar_wait(acc_full(as), ((uint32_t)titer >> 1) & 1u);
+      ptx::tc_fence_after();
+      const uint32_t lane_base = tmem_base + ((uint32_t)(q * 32) << 16) + as * 2 * NT;
+#pragma unroll 1
+      for (int c0 = 0; c0 < NT; c0 += 16) {
+        uint32_t am[16], av[16];
+        ptx::tmem_ld16(lane_base + c0, am);
+        ptx::tmem_ld16(lane_base + NT + c0, av);
+        ptx::tmem_ld_wait();
+        float mu[16], var[16];
+#pragma unroll
+        for (int j = 0; j < 16; ++j) {
+          const float sn = __ldg(p.s + n0 + c0 + j);
+          float mj = __uint_as_float(am[j]);
+          float vj = fmaxf(fmaf(sn, r, __uint_as_float(av[j])), 0.f);
+          if (p.relu) {
+            vj = mj > 0.f ? vj : 0.f;
+            mj = fmaxf(mj, 0.f);
+          }
+          mu[j] = mj;
+          var[j] = vj;
+        }
+        if (valid) {
+          if (p.dst_f32) {
+#pragma unroll
+            for (int j = 0; j < 16; j += 4) {
+              *reinterpret_cast<float4*>(f_mu + c0 + j) = make_float4(mu[j], mu[j + 1], mu[j + 2], mu[j + 3]);
+              *reinterpret_cast<float4*>(f_var + c0 + j) = make_float4(var[j], var[j + 1], var[j + 2], var[j + 3]);
+            }
+          } else {
+            uint32_t hi[8], lo[8], vr[8];
+#pragma unroll
+            for (int j = 0; j < 8; ++j) {
+              const float a0 = mu[2 * j], a1 = mu[2 * j + 1];
+              const __nv_bfloat16 h0 = __float2bfloat16_rn(a0), h1 = __float2bfloat16_rn(a1);
+              hi[j] = (uint32_t)__bfloat16_as_ushort(h0) | ((uint32_t)__bfloat16_as_ushort(h1) << 16);
+              lo[j] = hl_pack2(a0 - __bfloat162float(h0), a1 - __bfloat162float(h1));
+              vr[j] = hl_pack2(var[2 * j], var[2 * j + 1]);
+            }
+            uint4* ph = reinterpret_cast<uint4*>(d_hi + c0);
+            uint4* pl = reinterpret_cast<uint4*>(d_hi + p.dc + c0);
+            uint4* pv = reinterpret_cast<uint4*>(d_hi + 2 * p.dc + c0);
+            ph[0] = make_uint4(hi[0], hi[1], hi[2], hi[3]);
+            ph[1] = make_uint4(hi[4], hi[5], hi[6], hi[7]);
+            pl[0] = make_uint4(lo[0], lo[1], lo[2], lo[3]);
+            pl[1] = make_uint4(lo[4], lo[5], lo[6], lo[7]);
+            pv[0] = make_uint4(vr[0], vr[1], vr[2], vr[3]);
+            pv[1] = make_uint4(vr[4], vr[5], vr[6], vr[7]);
+          }
+        }
+      }
+      ptx::tc_fence_before();
+      __syncwarp();
+      if (lane == 0) ptx::mbar_arrive(acc_empty(as));    // this warp's TMEM reads of stage `as` are done
+    }
+  }
+
+  ptx::tc_fence_before();
+  __syncthreads();
+  if (warp == 1) ptx::tmem_dealloc(tmem_base, 4 * NT);
+}
+
+// ---------------------------------------------------------------------------------------------------------
+// host side
+// ---------------------------------------------------------------------------------------------------------
+typedef CUresult (*HlEncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*,
+                                    const cuuint64_t*, const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave,
+                                    CUtensorMapSwizzle, CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+
+static HlEncodeTiledFn hl_encode_tiled() {
+  static HlEncodeTiledFn fn = nullptr;
+  static std::once_flag once;
+  std::call_once(once, [] {
+    void* f = nullptr;
+    cudaDriverEntryPointQueryResult q;
+    if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &f, cudaEnableDefault, &q) == cudaSuccess &&
+        q == cudaDriverEntryPointSuccess)
+      fn = reinterpret_cast<HlEncodeTiledFn>(f);
+  });
+  return fn;
+}
+
+struct HaloTiling {
+  int R, THo, THb, TN, TWo, tiles_x, tiles_y, tiles_b;
+  double eff;
+};
+
+// Pick the halo box (R columns x THb rows x TN images, <= 128 GEMM rows of which THo*TWo*TN are useful) that
+// wastes the fewest GEMM rows over the whole layer.
+static HaloTiling choose_tiling(int batch, int in_h, int in_w, int k) {
+  const int Ho = in_h - k + 1, Wo = in_w - k + 1;
+  HaloTiling best{};
+  best.eff = -1.0;
+  // whole (small) images, several per tile
+  if (in_h * in_w <= HL_BM && in_w <= 62) {
+    HaloTiling t{};
+    t.R = in_w; t.THb = in_h; t.THo = Ho; t.TWo = Wo;
+    t.TN = HL_BM / (in_h * in_w);
+    if (t.TN > batch) t.TN = batch;
+    t.tiles_x = t.tiles_y = 1;
+    t.tiles_b = (batch + t.TN - 1) / t.TN;
+    t.eff = (double)batch * Ho * Wo / ((double)t.tiles_b * HL_BM);
+    best = t;
+  }
+  const int rmax = in_w < 62 ? in_w : 62;
+  for (int R = k; R <= rmax; ++R) {
+    HaloTiling t{};
+    t.R = R; t.TWo = R - (k - 1); t.TN = 1;
+    t.THo = HL_BM / R;
+    if (t.THo > Ho) t.THo = Ho;
+    if (t.THo < 1) continue;
+    t.THb = t.THo + k - 1;
+    t.tiles_x = (Wo + t.TWo - 1) / t.TWo;
+    t.tiles_y = (Ho + t.THo - 1) / t.THo;
+    t.tiles_b = batch;
+    t.eff = (double)Ho * Wo / ((double)t.tiles_x * t.tiles_y * HL_BM);
+    if (t.eff > best.eff + 1e-9) best = t;
+  }
+  return best;
+}
+
+static int hl_make_act_map(CUtensorMap* out, const sn_packed_view& v, int plane, int src_c, int batch, int in_h,
+                           int in_w, const HaloTiling& t) {
+  const size_t pix = (size_t)3 * v.c;
+  char* base = reinterpret_cast<char*>(v.base) +
+               ((((size_t)v.y0 * v.w + v.x0) * 3 + plane) * v.c + v.c0) * sizeof(__nv_bfloat16);
+  cuuint64_t dims[4] = {(cuuint64_t)src_c, (cuuint64_t)in_w, (cuuint64_t)in_h, (cuuint64_t)batch};
+  cuuint64_t strides[3] = {pix * 2, (cuuint64_t)v.w * pix * 2, (cuuint64_t)v.h * v.w * pix * 2};
+  cuuint32_t box[4] = {HL_KC, (cuuint32_t)t.R, (cuuint32_t)t.THb, (cuuint32_t)t.TN};
+  cuuint32_t estr[4] = {1, 1, 1, 1};
+  CUresult r = hl_encode_tiled()(out, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 4, base, dims, strides, box, estr,
+                                 CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_64B,
+                                 CU_TENSOR_MAP_L2_PROMOTION_L2_128B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  if (r != CUDA_SUCCESS) return fail(SN_ERR_DRIVER, "cuTensorMapEncodeTiled(activation) failed (%d)", (int)r);
+  return SN_OK;
+}
+
+static int hl_make_weight_map(CUtensorMap* out, const void* w_packed, int taps, int cout, int cin, int nt) {
+  cuuint64_t dims[3] = {(cuuint64_t)cin, (cuuint64_t)cout, (cuuint64_t)(3 * taps)};
+  cuuint64_t strides[2] = {(cuuint64_t)cin * 2, (cuuint64_t)cin * cout * 2};
+  cuuint32_t box[3] = {HL_KC, (cuuint32_t)nt, 1};
+  cuuint32_t estr[3] = {1, 1, 1};
+  CUresult r = hl_encode_tiled()(out, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 3, const_cast<void*>(w_packed), dims, strides,
+                                 box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_64B,
+                                 CU_TENSOR_MAP_L2_PROMOTION_L2_128B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  if (r != CUDA_SUCCESS) return fail(SN_ERR_DRIVER, "cuTensorMapEncodeTiled(weights) failed (%d)", (int)r);
+  return SN_OK;
+}
+
+template <int NT>
+static int hl_launch(const HlMaps& maps, const HlP& p, cudaStream_t st) {
+  static std::once_flag once;
+  static cudaError_t attr_err = cudaSuccess;
+  std::call_once(once, [] {
+    attr_err = cudaFuncSetAttribute(conv_moments_halo_kernel<NT>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                    HL_SMEM);
+  });
+  if (attr_err != cudaSuccess) return fail(SN_ERR_LAUNCH, "conv_halo: cannot reserve %d B of shared memory", HL_SMEM);
+  int grid = p.total_tiles < num_sms() ? p.total_tiles : num_sms();
+  conv_moments_halo_kernel<NT><<<grid, HL_THREADS, HL_SMEM, st>>>(maps, p);
+  return check_launch("conv_moments_halo");
+}
+
+// Called by sn_conv_moments_fwd_tc (sn_tc_conv.cu) after argument validation.
+int conv_moments_halo_dispatch(const sn_tc_conv_desc* d, cudaStream_t stream) {
+  SN_REQUIRE(hl_encode_tiled() != nullptr, SN_ERR_DRIVER, "conv_halo: cuTensorMapEncodeTiled unavailable");
+  const bool upconv = (d->flags & SN_TC_UPCONV) != 0;
+  const bool dst_f32 = (d->flags & SN_TC_DST_F32) != 0;
+  const int keff = upconv ? 1 : d->ksize;
+  const int Ho = d->in_h - keff + 1, Wo = d->in_w - keff + 1;
+  const int out_h = upconv ? 2 * d->in_h : Ho, out_w = upconv ? 2 * d->in_w : Wo;
+  const int nt = d->cout % 128 == 0 ? 128 : (d->cout % 64 == 0 ? 64 : 32);
+  const int groups = upconv ? 4 : 1;
+  const int taps_w = upconv ? 4 : d->ksize * d->ksize;
+  const int cin = d->src_c[0] + d->src_c[1];
+  const int cblk = cin / HL_KC;
+  const int taps = keff * keff;
+
+  const HaloTiling t = choose_tiling(d->batch, d->in_h, d->in_w, keff);
+  SN_REQUIRE(t.eff > 0, SN_ERR_UNSUPPORTED, "conv_halo: no tiling for %dx%d k=%d", d->in_h, d->in_w, keff);
+
+  HlP p{};
+  p.tiles_x = t.tiles_x; p.tiles_y = t.tiles_y; p.tiles_b = t.tiles_b;
+  p.tiles_n = groups * d->cout / nt;
+  const long long total = (long long)p.tiles_x * p.tiles_y * p.tiles_b * p.tiles_n;
+  SN_REQUIRE(total < (1ll << 30), SN_ERR_UNSUPPORTED, "conv_halo: too many tiles");
+  p.total_tiles = (int)total;
+  p.TWo = t.TWo; p.THo = t.THo; p.R = t.R; p.THb = t.THb; p.TN = t.TN;
+  p.rows_box = t.R * t.THb * t.TN;
+  const int rows_alloc = HL_BM + (keff - 1) * (t.R + 1);
+  const int rows_need = rows_alloc > p.rows_box ? rows_alloc : p.rows_box;
+  SN_REQUIRE(rows_need <= 256, SN_ERR_UNSUPPORTED, "conv_halo: halo tile of %d rows", rows_need);
+  p.a_plane = ((rows_need * 64 + 1023) / 1024) * 1024;
+  p.ksize = keff; p.taps_w = taps_w;
+  p.cblk0 = d->src_c[0] / HL_KC; p.cblk1 = d->src_c[1] / HL_KC;
+  p.Ho = Ho; p.Wo = Wo; p.B = d->batch;
+  p.cout = d->cout;
+  p.relu = (d->flags & SN_TC_RELU) ? 1 : 0; p.upconv = upconv ? 1 : 0; p.dst_f32 = dst_f32 ? 1 : 0;
+  p.dst = reinterpret_cast<__nv_bfloat16*>(d->dst.base);
+  p.dh = d->dst.h; p.dw = d->dst.w; p.dc = d->dst.c; p.dy0 = d->dst.y0; p.dx0 = d->dst.x0; p.dc0 = d->dst.c0;
+  p.dst_mu = d->dst_mu; p.dst_var = d->dst_var; p.out_h = out_h; p.out_w = out_w;
+  p.s = d->s;
+
+  // shared-memory plan: [A stages][B slots][1 KB barriers][2 KB q buffers], 1 KB alignment slack
+  const int avail = HL_SMEM - 1024 - 1024 - 2048;
+  const int a_stage = 3 * p.a_plane;
+  const int b_slot = 3 * nt * HL_KC * 2;
+  const int resident_slots = cblk * taps;
+  if (p.tiles_n == 1 && resident_slots <= HL_MAX_BSLOTS && resident_slots * b_slot + 2 * a_stage <= avail) {
+    p.b_resident = 1;
+    p.sb = resident_slots;
+    p.sa = (avail - resident_slots * b_slot) / a_stage;
+  } else {
+    p.b_resident = 0;
+    p.sa = 3;
+    if (3 * a_stage + 3 * b_slot > avail) p.sa = 2;
+    p.sb = (avail - p.sa * a_stage) / b_slot;
+    if (p.sb > HL_MAX_BSLOTS) p.sb = HL_MAX_BSLOTS;
+    SN_REQUIRE(p.sb >= 2, SN_ERR_UNSUPPORTED, "conv_halo: shared memory plan failed");
+  }
+  if (p.sa > HL_MAX_ASTAGES) p.sa = HL_MAX_ASTAGES;
+
+  HlMaps maps;
+  int rc;
+  for (int s = 0; s < 2; ++s) {
+    const int srcs = d->src_c[s] ? s : 0;
+    for (int pl = 0; pl < 3; ++pl)
+      if ((rc = hl_make_act_map(&maps.a[s][pl], d->src[srcs], pl, d->src_c[srcs], d->batch, d->in_h, d->in_w, t)))
+        return rc;
+  }
+  if ((rc = hl_make_weight_map(&maps.w, d->w_packed, taps_w, d->cout, cin, nt))) return rc;
+  switch (nt) {
+    case 128: return hl_launch<128>(maps, p, stream);
+    case 64: return hl_launch<64>(maps, p, stream);
+    default: return hl_launch<32>(maps, p, stream);
+  }
+}
+
+}  // namespace sn

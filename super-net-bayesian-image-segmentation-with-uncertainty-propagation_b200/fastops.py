@@ -12,7 +12,7 @@ from typing import Optional, Tuple
 import torch
 
 from . import _lib
-from ._lib import SN_TC_DST_F32, SN_TC_RELU, SN_TC_UPCONV, check, ptr, sn_packed_view, sn_tc_conv_desc, stream_ptr
+from ._lib import SN_TC_DST_F32, SN_TC_IM2COL, SN_TC_RELU, SN_TC_UPCONV, check, ptr, sn_packed_view, sn_tc_conv_desc, stream_ptr
 
 Tensor = torch.Tensor
 
@@ -72,13 +72,14 @@ def prepare_weights(w_mu: Tensor, w_sigma: Tensor, upconv: bool = False) -> Tupl
 def conv_moments_tc(src0: PackedView, c0: int, batch: int, in_h: int, in_w: int, ksize: int, cout: int,
                     w_packed: Tensor, s: Tensor, dst: Optional[PackedView] = None, relu: bool = False,
                     upconv: bool = False, src1: Optional[PackedView] = None, c1: int = 0,
-                    dst_f32: Optional[Tuple[Tensor, Tensor]] = None) -> None:
+                    dst_f32: Optional[Tuple[Tensor, Tensor]] = None, im2col: bool = False) -> None:
     d = sn_tc_conv_desc()
     d.src[0] = src0.c_view()
     d.src[1] = (src1 if src1 is not None else src0).c_view()
     d.src_c[0], d.src_c[1] = c0, c1
     d.batch, d.in_h, d.in_w, d.ksize, d.cout = batch, in_h, in_w, ksize, cout
-    d.flags = (SN_TC_RELU if relu else 0) | (SN_TC_UPCONV if upconv else 0) | (SN_TC_DST_F32 if dst_f32 else 0)
+    d.flags = ((SN_TC_RELU if relu else 0) | (SN_TC_UPCONV if upconv else 0) | (SN_TC_DST_F32 if dst_f32 else 0) |
+               (SN_TC_IM2COL if im2col else 0))
     d.w_packed = w_packed.data_ptr()
     d.s = s.data_ptr()
     if dst_f32 is not None:

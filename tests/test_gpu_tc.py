@@ -65,12 +65,16 @@ TC_CASES = [
     (2, 11, 13, 32, 64, 1),    # 1x1
     (2, 7, 8, 64, 32, 2),      # plain k = 2
     (1, 34, 33, 32, 96, 3),    # cout multiple of 32 only -> NT = 32, three N tiles
+    (2, 70, 150, 32, 32, 3),   # wide image: column tiles, resident weights, many tiles per persistent CTA
+    (9, 8, 8, 64, 64, 3),      # tiny images: several per 128-row tile
+    (40, 30, 30, 64, 32, 3),   # > 148 tiles with resident weights (18 slots)
 ]
 
 
 @pytest.mark.parametrize("case", TC_CASES)
 @pytest.mark.parametrize("relu", [False, True])
-def test_conv_tc_f32_dst(S, case, relu):
+@pytest.mark.parametrize("im2col", [False, True], ids=["halo", "im2col"])
+def test_conv_tc_f32_dst(S, case, relu, im2col):
     F = S.fastops
     B, H, W, cin, cout, k = case
     mu, var, w, ws = rand_layer(B, H, W, cin, cout, k, seed=sum(case))
@@ -82,7 +86,7 @@ def test_conv_tc_f32_dst(S, case, relu):
     Ho, Wo = H - k + 1, W - k + 1
     m = torch.full((B, Ho, Wo, cout), float("nan"), device="cuda")
     v = torch.full((B, Ho, Wo, cout), float("nan"), device="cuda")
-    F.conv_moments_tc(src, cin, B, H, W, k, cout, wp, s, relu=relu, dst_f32=(m, v))
+    F.conv_moments_tc(src, cin, B, H, W, k, cout, wp, s, relu=relu, dst_f32=(m, v), im2col=im2col)
     torch.cuda.synchronize()
     assert bool(torch.isfinite(m).all()) and bool(torch.isfinite(v).all())
     assert rel(m, m_ref) < MEAN_TOL, rel(m, m_ref)
@@ -90,7 +94,8 @@ def test_conv_tc_f32_dst(S, case, relu):
     assert float(v.min()) >= 0.0
 
 
-def test_conv_tc_packed_window_concat(S):
+@pytest.mark.parametrize("im2col", [False, True], ids=["halo", "im2col"])
+def test_conv_tc_packed_window_concat(S, im2col):
     """Two sources (decoder window + cropped encoder window), output into the interior of a padded buffer."""
     F = S.fastops
     B, H, W, k, cout = 2, 10, 10, 3, 64
@@ -109,14 +114,16 @@ def test_conv_tc_packed_window_concat(S):
     F.packed_fill(out, 0.1)
     wp, s = F.prepare_weights(dev(w), dev(ws))
     F.conv_moments_tc(F.PackedView(dbuf, 1, 2, 0), 64, B, H, W, k, cout, wp, s,
-                      dst=F.PackedView(out, 2, 2, 0), relu=True, src1=F.PackedView(ebuf, 2, 2, 0), c1=32)
+                      dst=F.PackedView(out, 2, 2, 0), relu=True, src1=F.PackedView(ebuf, 2, 2, 0), c1=32,
+                      im2col=im2col)
     m, v = F.unpack_moments(out)
     assert rel(m, m_ref) < MEAN_TOL and rel(v, v_ref) < VAR_TOL
     assert torch.equal(v[:, 0].cpu(), torch.full_like(v[:, 0].cpu(), float(torch.tensor(0.1).bfloat16())))
 
 
-@pytest.mark.parametrize("case", [(2, 6, 6, 64, 32), (1, 9, 7, 128, 64), (2, 5, 5, 256, 128)])
-def test_upconv_tc(S, case):
+@pytest.mark.parametrize("case", [(2, 6, 6, 64, 32), (1, 9, 7, 128, 64), (2, 5, 5, 256, 128), (3, 30, 41, 32, 32)])
+@pytest.mark.parametrize("im2col", [False, True], ids=["halo", "im2col"])
+def test_upconv_tc(S, case, im2col):
     """unpool + 2x2 VALID conv (Brats.py:414-415) == four parity GEMMs, scattered into a padded window."""
     F = S.fastops
     B, H, W, cin, cout = case
@@ -129,7 +136,7 @@ def test_upconv_tc(S, case):
     wp, s = F.prepare_weights(dev(w), dev(ws), upconv=True)
     out = F.packed_empty(B, 2 * H + 6, 2 * W + 6, cout, "cuda")
     F.packed_fill(out, 0.1)
-    F.conv_moments_tc(src, cin, B, H, W, 2, cout, wp, s, dst=F.PackedView(out, 3, 3, 0), upconv=True)
+    F.conv_moments_tc(src, cin, B, H, W, 2, cout, wp, s, dst=F.PackedView(out, 3, 3, 0), upconv=True, im2col=im2col)
     m, v = F.unpack_moments(out)
     assert rel(m, m_ref) < MEAN_TOL and rel(v, v_ref) < VAR_TOL
 
