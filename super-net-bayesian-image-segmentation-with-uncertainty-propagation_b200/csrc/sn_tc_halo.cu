@@ -12,10 +12,12 @@
 //     RESIDENT in smem for the CTA's whole life (persistent tile loop), so only activations stream;
 //   * the rank-1 term needs q[pixel] = sum_c(mu^2+var) once per halo pixel (not once per tap):
 //     r[j] = sum_taps q[j + kh*R + kw] from a 1 KB smem array;
-//   * two TMEM accumulator stages + two epilogue warp groups: the epilogue of tile i overlaps the TMA/UMMA
-//     main loop of tile i+1.
-// Warp roles (320 threads): warp 0 TMA producer, warp 1 UMMA issuer (+TMEM alloc), warps 2-5 / 6-9 = group 0 / 1
-// (q reduction during the main loop of their tile, then epilogue).  Same math and data layout as sn_tc_conv.cu
+//   * two TMEM accumulator stages: the epilogue of tile i overlaps the TMA/UMMA main loop of tile i+1.
+// Warp roles (448 threads): warp 0 TMA producer, warp 1 UMMA issuer (+TMEM alloc), warps 2-5 q reduction over
+// every A stage, warps 6-13 epilogue: two warps per TMEM lane quarter, each taking half of the tile's columns
+// (q arrives through a double-buffered smem array guarded by mbarriers).  Profiling the first version (4
+// epilogue warps, one per SM sub-partition) showed the epilogue, a long dependent instruction chain per pixel
+// row, as the critical path of the 32/64-channel layers; hence the second set of warps.  Same math and data layout as sn_tc_conv.cu
 // (Brats.py:118-137 incl. ReLU :233-238, pad :159-163, concat :247-261, unpool+2x2 conv :178-203,414-415).
 #include "sn_common.cuh"
 #include "sn_sm100.cuh"
@@ -27,7 +29,7 @@ namespace sn {
 
 constexpr int HL_BM = 128;
 constexpr int HL_KC = 32;
-constexpr int HL_THREADS = 320;
+constexpr int HL_THREADS = 448;       // 14 warps: TMA, UMMA, 4 x q reduction, 8 x epilogue
 constexpr int HL_MAX_BSLOTS = 36;
 constexpr int HL_MAX_ASTAGES = 4;
 constexpr int HL_SMEM = 232448;        // 227 KB: always requested so exactly one CTA owns an SM (and its TMEM)
@@ -62,15 +64,15 @@ __device__ __forceinline__ uint32_t hl_pack2(float a, float b) {
   __nv_bfloat162 t = __floats2bfloat162_rn(a, b);
   return *reinterpret_cast<uint32_t*>(&t);
 }
-__device__ __forceinline__ void named_bar_sync(int id, int threads) {
-  asm volatile("bar.sync %0, %1;" ::"r"(id), "r"(threads) : "memory");
-}
 
-template <int NT>
+template <int NT, int KS, bool RESIDENT>
 __global__ void __launch_bounds__(HL_THREADS, 1) conv_moments_halo_kernel(const __grid_constant__ HlMaps maps,
                                                                           const HlP p) {
   constexpr int B_PLANE = NT * HL_KC * 2;
   constexpr int B_SLOT = 3 * B_PLANE;
+  constexpr bool CONCAT = NT <= 64;                       // hi x [W_hi ; W_lo] as one UMMA of N = 2*NT
+  constexpr int ACC_STAGE = CONCAT ? 3 * NT : 2 * NT;     // TMEM columns per accumulator stage
+  constexpr int TMEM_COLS = NT == 32 ? 256 : 512;         // 2 stages, rounded up to a power of two
   extern __shared__ uint8_t smem_raw[];
   const uint32_t smem_base = (ptx::smem_u32(smem_raw) + 1023u) & ~1023u;
   uint8_t* smem_gen = smem_raw + (smem_base - ptx::smem_u32(smem_raw));
@@ -83,15 +85,19 @@ __global__ void __launch_bounds__(HL_THREADS, 1) conv_moments_halo_kernel(const 
   auto b_empty = [&](int s) { return bar_base + 8u * (2 * HL_MAX_ASTAGES + HL_MAX_BSLOTS + s); };
   auto acc_full = [&](int s) { return bar_base + 8u * (2 * HL_MAX_ASTAGES + 2 * HL_MAX_BSLOTS + s); };
   auto acc_empty = [&](int s) { return bar_base + 8u * (2 * HL_MAX_ASTAGES + 2 * HL_MAX_BSLOTS + 2 + s); };
-  const uint32_t tmem_slot = bar_base + 8u * (2 * HL_MAX_ASTAGES + 2 * HL_MAX_BSLOTS + 4);
+  auto q_full = [&](int s) { return bar_base + 8u * (2 * HL_MAX_ASTAGES + 2 * HL_MAX_BSLOTS + 4 + s); };
+  auto q_empty = [&](int s) { return bar_base + 8u * (2 * HL_MAX_ASTAGES + 2 * HL_MAX_BSLOTS + 6 + s); };
+  const uint32_t tmem_slot = bar_base + 8u * (2 * HL_MAX_ASTAGES + 2 * HL_MAX_BSLOTS + 8);
   const int bar_off = p.sa * a_stage + p.sb * B_SLOT;
   volatile uint32_t* tmem_slot_gen =
-      reinterpret_cast<volatile uint32_t*>(smem_gen + bar_off + 8 * (2 * HL_MAX_ASTAGES + 2 * HL_MAX_BSLOTS + 4));
-  float* qbuf = reinterpret_cast<float*>(smem_gen + bar_off + 1024);     // [2 groups][256]
+      reinterpret_cast<volatile uint32_t*>(smem_gen + bar_off + 8 * (2 * HL_MAX_ASTAGES + 2 * HL_MAX_BSLOTS + 8));
+  float* qbuf = reinterpret_cast<float*>(smem_gen + bar_off + 1024);     // [2 stages][256]
+  float* s_sm = qbuf + 512;                                              // softplus(w_sigma) [cout <= 512]
 
-  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int warp = __shfl_sync(0xffffffffu, (int)(threadIdx.x >> 5), 0);   // provably warp-uniform
+  const int lane = threadIdx.x & 31;
   const int cblk = p.cblk0 + p.cblk1;
-  const int taps = p.ksize * p.ksize;
+  constexpr int taps = KS * KS;
 
   if (warp == 0 && lane == 0) {
     for (int s = 0; s < 2; ++s)
@@ -99,7 +105,7 @@ __global__ void __launch_bounds__(HL_THREADS, 1) conv_moments_halo_kernel(const 
     ptx::prefetch_tensormap(&maps.w);
     for (int s = 0; s < p.sa; ++s) {
       ptx::mbar_init(a_full(s), 1);
-      ptx::mbar_init(a_empty(s), 5);          // UMMA commit + 4 warps of the reducing group
+      ptx::mbar_init(a_empty(s), 5);          // UMMA commit + the 4 reducer warps
     }
     for (int s = 0; s < p.sb; ++s) {
       ptx::mbar_init(b_full(s), 1);
@@ -107,14 +113,17 @@ __global__ void __launch_bounds__(HL_THREADS, 1) conv_moments_halo_kernel(const 
     }
     for (int s = 0; s < 2; ++s) {
       ptx::mbar_init(acc_full(s), 1);
-      ptx::mbar_init(acc_empty(s), 4);        // 4 epilogue warps
+      ptx::mbar_init(acc_empty(s), 8);        // 8 epilogue warps
+      ptx::mbar_init(q_full(s), 4);           // 4 reducer warps
+      ptx::mbar_init(q_empty(s), 8);          // 8 epilogue warps
     }
     ptx::fence_barrier_init();
   }
   if (warp == 1) {
-    ptx::tmem_alloc(tmem_slot, 4 * NT);       // 2 stages x (mean, var) x NT columns: 128 / 256 / 512
+    ptx::tmem_alloc(tmem_slot, TMEM_COLS);
     ptx::tmem_relinquish();
   }
+  for (int i = threadIdx.x; i < p.cout; i += HL_THREADS) s_sm[i] = p.s[i];
   ptx::tc_fence_before();
   __syncthreads();
   ptx::tc_fence_after();
@@ -155,10 +164,10 @@ __global__ void __launch_bounds__(HL_THREADS, 1) conv_moments_halo_kernel(const 
                   : "memory");
             }
           }
-          if (!p.b_resident || titer == 0) {
+          if (!RESIDENT || titer == 0) {
             for (int tap = 0; tap < taps; ++tap) {
               int slot;
-              if (p.b_resident) {
+              if (RESIDENT) {
                 slot = cbt * taps + tap;
               } else {
                 slot = bi % p.sb;
@@ -180,204 +189,257 @@ __global__ void __launch_bounds__(HL_THREADS, 1) conv_moments_halo_kernel(const 
     }
   } else if (warp == 1) {
     // ===================== UMMA issuer =====================
-    if (lane == 0) {
-      constexpr uint32_t idesc = ptx::idesc_bf16_f32(HL_BM, NT);
-      int ai = 0, bi = 0;
+    // UMMA cost measured on B200 (tools/probe_mma_rate.cu): M=128,K=16 takes 44.8 / 48.1 / 64.1 / 128.1 cycles at
+    // N = 32 / 64 / 128 / 256 -- a ~45-cycle floor per instruction (the 4 KB A-operand fetch).  For NT <= 64 the
+    // mean therefore uses TWO instructions instead of three: A_hi x [W_hi ; W_lo] as one N = 2*NT UMMA (the two
+    // weight planes are adjacent in the B slot) into columns [0, 2NT), and A_lo x W_hi into columns [0, NT);
+    // the epilogue adds the two column halves.  NT = 128 is already math-bound and keeps 3 + 1 N = 128 UMMAs.
+    {
+      // All 32 lanes run this loop (uniform control flow keeps the descriptor arithmetic in the uniform datapath);
+      // one elected lane issues the UMMAs and commits.  Taps and K steps are fully unrolled so every descriptor is
+      // "per-stage base + immediate": the issuing thread must sustain one UMMA per ~45 cycles.
+      constexpr uint32_t idesc_n = ptx::idesc_bf16_f32(HL_BM, NT);
+      constexpr uint32_t idesc_2n = ptx::idesc_bf16_f32(HL_BM, CONCAT ? 2 * NT : NT);
+      // descriptor = constant high word | (1 << 16 | address >> 4) in the low word (smem < 256 KB: 14 bits);
+      // high word of smem_desc_kmajor<64>: SBO = 512 B >> 4 at bits [32,46), version 1 at bit 46, SW64 (4) at [61,64)
+      constexpr uint32_t DESC_HI = 32u | (1u << 14) | (4u << 29);
+      auto desc = [&](uint32_t lo) { return ((uint64_t)DESC_HI << 32) | (uint64_t)lo; };
+      const bool leader = ptx::elect_one();
+      const uint32_t a_lo_base = 0x10000u | (smem_base >> 4);
+      const uint32_t b_lo_base = 0x10000u | (b_base >> 4);
+      const uint32_t stage16 = (uint32_t)a_stage >> 4, plane16 = (uint32_t)p.a_plane >> 4;
+      const uint32_t row_shift16 = (uint32_t)p.R * 4u;            // one halo row = R pixels x 64 B, in 16-byte units
+      constexpr uint32_t SLOT16 = B_SLOT >> 4, BPLANE16 = B_PLANE >> 4;
+      int a_stage_i = 0, b_slot_i = 0;
+      uint32_t a_par = 0, b_par = 0;
       for (int tile = blockIdx.x, titer = 0; tile < p.total_tiles; tile += gridDim.x, ++titer) {
         const int as = titer & 1;
         ptx::mbar_wait(acc_empty(as), (((uint32_t)titer >> 1) & 1u) ^ 1u);
-        ptx::tc_fence_after();
-        const uint32_t acc_mu = tmem_base + as * 2 * NT, acc_var = acc_mu + NT;
+        const uint32_t acc_mu = tmem_base + as * ACC_STAGE, acc_var = acc_mu + (CONCAT ? 2 * NT : NT);
         for (int cbt = 0; cbt < cblk; ++cbt) {
-          const int stage = ai % p.sa;
-          const uint32_t aparity = (uint32_t)(ai / p.sa) & 1u;
-          ++ai;
-          ptx::mbar_wait(a_full(stage), aparity);
-          ptx::tc_fence_after();
-          const uint32_t sa_addr = smem_base + stage * a_stage;
-          for (int tap = 0; tap < taps; ++tap) {
-            int slot;
-            if (p.b_resident) {
-              slot = cbt * taps + tap;
-              ptx::mbar_wait(b_full(slot), 0);
-            } else {
-              slot = bi % p.sb;
-              const uint32_t parity = (uint32_t)(bi / p.sb) & 1u;
-              ++bi;
-              ptx::mbar_wait(b_full(slot), parity);
-            }
-            ptx::tc_fence_after();
-            const int kh = tap / p.ksize, kw = tap - kh * p.ksize;
-            const uint32_t shift = (uint32_t)(kh * p.R + kw) * 64u;     // tap = row offset into the halo tile
-            const uint32_t sb_addr = b_base + slot * B_SLOT;
-#pragma unroll
-            for (int ks = 0; ks < HL_KC / 16; ++ks) {
-              const uint32_t koff = ks * 32;
-              const uint64_t a_hi = ptx::smem_desc_kmajor<64>(sa_addr + shift + koff);
-              const uint64_t a_lo = ptx::smem_desc_kmajor<64>(sa_addr + p.a_plane + shift + koff);
-              const uint64_t a_vr = ptx::smem_desc_kmajor<64>(sa_addr + 2 * p.a_plane + shift + koff);
-              const uint64_t b_hi = ptx::smem_desc_kmajor<64>(sb_addr + koff);
-              const uint64_t b_lo = ptx::smem_desc_kmajor<64>(sb_addr + B_PLANE + koff);
-              const uint64_t b_sq = ptx::smem_desc_kmajor<64>(sb_addr + 2 * B_PLANE + koff);
-              const uint32_t acc = (cbt > 0 || tap > 0 || ks > 0) ? 1u : 0u;
-              ptx::umma_bf16(acc_mu, a_hi, b_hi, idesc, acc);
-              ptx::umma_bf16(acc_mu, a_lo, b_hi, idesc, 1u);
-              ptx::umma_bf16(acc_mu, a_hi, b_lo, idesc, 1u);
-              ptx::umma_bf16(acc_var, a_vr, b_sq, idesc, acc);
-            }
-            if (!p.b_resident) ptx::umma_commit(b_empty(slot));
+          ptx::mbar_wait(a_full(a_stage_i), a_par);
+          if (RESIDENT && titer == 0) {
+            for (int tap = 0; tap < taps; ++tap) ptx::mbar_wait(b_full(cbt * taps + tap), 0);
           }
-          ptx::umma_commit(a_empty(stage));
+          ptx::tc_fence_after();
+          const uint32_t a_st = a_lo_base + a_stage_i * stage16;
+          uint32_t b_st = b_lo_base + (RESIDENT ? (uint32_t)(cbt * taps) * SLOT16 : 0u);
+#pragma unroll
+          for (int tap = 0; tap < taps; ++tap) {
+            const int kh = tap / KS, kw = tap % KS;                  // compile-time after unrolling
+            uint32_t b0;
+            int slot = 0;
+            if (RESIDENT) {
+              b0 = b_st + (uint32_t)tap * SLOT16;
+            } else {
+              slot = b_slot_i;
+              ptx::mbar_wait(b_full(slot), b_par);
+              ptx::tc_fence_after();
+              if (++b_slot_i == p.sb) { b_slot_i = 0; b_par ^= 1u; }
+              b0 = b_st + (uint32_t)slot * SLOT16;
+            }
+            const uint32_t a0 = a_st + (uint32_t)kh * row_shift16 + (uint32_t)kw * 4u;   // tap = row offset in the halo
+            if (leader) {
+#pragma unroll
+              for (int ks = 0; ks < HL_KC / 16; ++ks) {
+                const uint32_t k16 = ks * 2;                          // 16 bf16 = 32 B along K
+                const uint32_t acc = (cbt > 0 || tap > 0 || ks > 0) ? 1u : 0u;
+                if constexpr (CONCAT) {
+                  ptx::umma_bf16(acc_mu, desc(a0 + k16), desc(b0 + k16), idesc_2n, acc);                 // hi x [Whi;Wlo]
+                  ptx::umma_bf16(acc_mu, desc(a0 + plane16 + k16), desc(b0 + k16), idesc_n, 1u);        // lo x Whi
+                } else {
+                  ptx::umma_bf16(acc_mu, desc(a0 + k16), desc(b0 + k16), idesc_n, acc);
+                  ptx::umma_bf16(acc_mu, desc(a0 + plane16 + k16), desc(b0 + k16), idesc_n, 1u);
+                  ptx::umma_bf16(acc_mu, desc(a0 + k16), desc(b0 + BPLANE16 + k16), idesc_n, 1u);
+                }
+                ptx::umma_bf16(acc_var, desc(a0 + 2 * plane16 + k16), desc(b0 + 2 * BPLANE16 + k16), idesc_n, acc);
+              }
+              if (!RESIDENT) ptx::umma_commit(b_empty(slot));
+            }
+          }
+          if (leader) ptx::umma_commit(a_empty(a_stage_i));
+          if (++a_stage_i == p.sa) { a_stage_i = 0; a_par ^= 1u; }
         }
-        ptx::umma_commit(acc_full(as));
+        if (leader) ptx::umma_commit(acc_full(as));
       }
     }
   } else {
-    // ===================== q reduction + epilogue (two alternating groups) =====================
-    const int grp = (warp - 2) >> 2;
-    const int q = warp & 3;
-    const int row = q * 32 + lane;            // GEMM row == TMEM lane == halo pixel index
-    float* myq = qbuf + grp * 256;
-    int x = row % p.R;
-    int yy = row / p.R;
-    const int y = yy % p.THb;
-    const int n = yy / p.THb;
-    const int nt_tiles = p.total_tiles;
-    for (int tile = blockIdx.x, titer = 0; tile < nt_tiles; tile += gridDim.x, ++titer) {
-      if ((titer & 1) != grp) continue;
-      // A-stage counter of this tile's first channel block: every tile consumes cblk stages
-      int ai = titer * cblk;
-      float q0 = 0.f, q1 = 0.f;
-      for (int cbt = 0; cbt < cblk; ++cbt, ++ai) {
-        const int stage = ai % p.sa;
-        const uint32_t parity = (uint32_t)(ai / p.sa) & 1u;
-        ptx::mbar_wait(a_full(stage), parity);
-        const uint8_t* a = smem_gen + stage * a_stage;
+    if (warp < 6) {
+      // ===================== q reduction (warps 2-5): q[halo pixel] = sum_c (mu^2 + var) =====================
+      // These four warps consume EVERY A stage in order (so the stage barriers see one consistent consumer) and
+      // hand the per-tile q array to the epilogue warps through a double-buffered smem array.
+      const int row = (warp - 2) * 32 + lane;
+      int ai = 0;
+      for (int tile = blockIdx.x, titer = 0; tile < p.total_tiles; tile += gridDim.x, ++titer) {
+        float q0 = 0.f, q1 = 0.f;
+        for (int cbt = 0; cbt < cblk; ++cbt, ++ai) {
+          const int stage = ai % p.sa;
+          const uint32_t parity = (uint32_t)(ai / p.sa) & 1u;
+          ptx::mbar_wait(a_full(stage), parity);
+          const uint8_t* a = smem_gen + stage * a_stage;
 #pragma unroll
-        for (int h = 0; h < 2; ++h) {
-          const int rr = row + h * 128;
-          if (rr < p.rows_box) {
-            const uint8_t* ar = a + rr * 64;
-            float acc = 0.f;
+          for (int h = 0; h < 2; ++h) {
+            const int rr = row + h * 128;
+            if (rr < p.rows_box) {
+              const uint8_t* ar = a + rr * 64;
+              float acc = 0.f;
 #pragma unroll
-            for (int j = 0; j < 4; ++j) {
-              const int ch = ((j + (rr >> 1)) & 3) * 16;   // chunk rotation: conflict-free, order-insensitive sum
-              const uint4 hh4 = *reinterpret_cast<const uint4*>(ar + ch);
-              const uint4 ll4 = *reinterpret_cast<const uint4*>(ar + p.a_plane + ch);
-              const uint4 vv4 = *reinterpret_cast<const uint4*>(ar + 2 * p.a_plane + ch);
-              const uint32_t hh[4] = {hh4.x, hh4.y, hh4.z, hh4.w}, ll[4] = {ll4.x, ll4.y, ll4.z, ll4.w},
-                             vv[4] = {vv4.x, vv4.y, vv4.z, vv4.w};
+              for (int j = 0; j < 4; ++j) {
+                const int ch = ((j + (rr >> 1)) & 3) * 16;   // chunk rotation: conflict-free, order-insensitive sum
+                const uint4 hh4 = *reinterpret_cast<const uint4*>(ar + ch);
+                const uint4 ll4 = *reinterpret_cast<const uint4*>(ar + p.a_plane + ch);
+                const uint4 vv4 = *reinterpret_cast<const uint4*>(ar + 2 * p.a_plane + ch);
+                const uint32_t hh[4] = {hh4.x, hh4.y, hh4.z, hh4.w}, ll[4] = {ll4.x, ll4.y, ll4.z, ll4.w},
+                               vv[4] = {vv4.x, vv4.y, vv4.z, vv4.w};
 #pragma unroll
-              for (int e = 0; e < 4; ++e) {
-                const float m_a = hl_lo(hh[e]) + hl_lo(ll[e]);
-                const float m_b = hl_hi(hh[e]) + hl_hi(ll[e]);
-                acc = fmaf(m_a, m_a, acc);
-                acc = fmaf(m_b, m_b, acc);
-                acc += hl_lo(vv[e]) + hl_hi(vv[e]);
+                for (int e = 0; e < 4; ++e) {
+                  const float m_a = hl_lo(hh[e]) + hl_lo(ll[e]);
+                  const float m_b = hl_hi(hh[e]) + hl_hi(ll[e]);
+                  acc = fmaf(m_a, m_a, acc);
+                  acc = fmaf(m_b, m_b, acc);
+                  acc += hl_lo(vv[e]) + hl_hi(vv[e]);
+                }
               }
+              if (h == 0) q0 += acc; else q1 += acc;
             }
-            if (h == 0) q0 += acc; else q1 += acc;
           }
+          __syncwarp();
+          if (lane == 0) ptx::mbar_arrive(a_empty(stage));
         }
+        const int qs = titer & 1;
+        ptx::mbar_wait(q_empty(qs), (((uint32_t)titer >> 1) & 1u) ^ 1u);
+        float* myq = qbuf + qs * 256;
+        myq[row] = q0;
+        myq[row + 128] = q1;                     // rows >= rows_box hold 0
         __syncwarp();
-        if (lane == 0) ptx::mbar_arrive(a_empty(stage));
+        if (lane == 0) ptx::mbar_arrive(q_full(qs));
       }
-      myq[row] = q0;
-      myq[row + 128] = q1;                     // rows >= rows_box hold 0
-      named_bar_sync(1 + grp, 128);
-      float r = 0.f;
-      for (int kh = 0; kh < p.ksize; ++kh)
-        for (int kw = 0; kw < p.ksize; ++kw) {
-          const int idx = row + kh * p.R + kw;
-          r += idx < 256 ? myq[idx] : 0.f;
-        }
-      named_bar_sync(1 + grp, 128);           // everyone has read before the next tile overwrites myq
-
-      // ---- tile coordinates
-      const int nt_i = tile % p.tiles_n;
-      int t = tile / p.tiles_n;
-      const int tx = t % p.tiles_x; t /= p.tiles_x;
-      const int ty = t % p.tiles_y;
-      const int tb = t / p.tiles_y;
-      const int ncol0 = nt_i * NT;
-      const int group = ncol0 / p.cout;
-      const int n0 = ncol0 - group * p.cout;
-      const int ox_i = tx * p.TWo + x, oy_i = ty * p.THo + y, ob = tb * p.TN + n;
-      const bool valid = x < p.TWo && y < p.THo && n < p.TN && ox_i < p.Wo && oy_i < p.Ho && ob < p.B;
-      int oy = oy_i, ox = ox_i;
-      if (p.upconv) { oy = 2 * oy_i + (group >> 1); ox = 2 * ox_i + (group & 1); }
-      __nv_bfloat16* d_hi = nullptr;
-      float *f_mu = nullptr, *f_var = nullptr;
-      if (valid) {
-        if (p.dst_f32) {
-          const size_t o = (((size_t)ob * p.out_h + oy) * p.out_w + ox) * p.cout + n0;
-          f_mu = p.dst_mu + o;
-          f_var = p.dst_var + o;
-        } else {
-          d_hi = p.dst + ((((size_t)ob * p.dh + oy + p.dy0) * p.dw + ox + p.dx0) * 3) * p.dc + p.dc0 + n0;
-        }
-      }
-      const int as = titer & 1;
-      ptx::mbar_wait(acc_full(as), ((uint32_t)titer >> 1) & 1u);
-      ptx::tc_fence_after();
-      const uint32_t lane_base = tmem_base + ((uint32_t)(q * 32) << 16) + as * 2 * NT;
-#pragma unroll 1
-      for (int c0 = 0; c0 < NT; c0 += 16) {
-        uint32_t am[16], av[16];
-        ptx::tmem_ld16(lane_base + c0, am);
-        ptx::tmem_ld16(lane_base + NT + c0, av);
-        ptx::tmem_ld_wait();
-        float mu[16], var[16];
+    } else {
+      // ===================== epilogue (warps 6-13) =====================
+      const int q = warp & 3;                   // TMEM lane quarter this warp may access
+      const int half = (warp - 6) >> 2;         // which half of the tile's NT columns this warp converts
+      constexpr int NH = NT / 2;
+      const int row = q * 32 + lane;            // GEMM row == TMEM lane == halo pixel index
+      const int x = row % p.R;
+      const int yy = row / p.R;
+      const int y = yy % p.THb;
+      const int n = yy / p.THb;
+      for (int tile = blockIdx.x, titer = 0; tile < p.total_tiles; tile += gridDim.x, ++titer) {
+        const int as = titer & 1;
+        const uint32_t par = ((uint32_t)titer >> 1) & 1u;
+        ptx::mbar_wait(q_full(as), par);
+        const float* myq = qbuf + as * 256;
+        float qv[taps];
 #pragma unroll
-        for (int j = 0; j < 16; ++j) {
-          const float sn = __ldg(p.s + n0 + c0 + j);
-          float mj = __uint_as_float(am[j]);
-          float vj = fmaxf(fmaf(sn, r, __uint_as_float(av[j])), 0.f);
-          if (p.relu) {
-            vj = mj > 0.f ? vj : 0.f;
-            mj = fmaxf(mj, 0.f);
+        for (int kh = 0; kh < KS; ++kh)
+#pragma unroll
+          for (int kw = 0; kw < KS; ++kw) {
+            const int idx = row + kh * p.R + kw;        // independent loads first, then one short add chain
+            qv[kh * KS + kw] = idx < 256 ? myq[idx] : 0.f;
           }
-          mu[j] = mj;
-          var[j] = vj;
-        }
+        float r = 0.f;
+#pragma unroll
+        for (int i = 0; i < taps; ++i) r += qv[i];
+        __syncwarp();
+        if (lane == 0) ptx::mbar_arrive(q_empty(as));
+
+        // ---- tile coordinates
+        const int nt_i = tile % p.tiles_n;
+        int t = tile / p.tiles_n;
+        const int tx = t % p.tiles_x; t /= p.tiles_x;
+        const int ty = t % p.tiles_y;
+        const int tb = t / p.tiles_y;
+        const int ncol0 = nt_i * NT;
+        const int group = ncol0 / p.cout;
+        const int n0 = ncol0 - group * p.cout + half * NH;     // first output channel this warp writes
+        const int ox_i = tx * p.TWo + x, oy_i = ty * p.THo + y, ob = tb * p.TN + n;
+        const bool valid = x < p.TWo && y < p.THo && n < p.TN && ox_i < p.Wo && oy_i < p.Ho && ob < p.B;
+        int oy = oy_i, ox = ox_i;
+        if (p.upconv) { oy = 2 * oy_i + (group >> 1); ox = 2 * ox_i + (group & 1); }
+        __nv_bfloat16* d_hi = nullptr;
+        float *f_mu = nullptr, *f_var = nullptr;
         if (valid) {
           if (p.dst_f32) {
-#pragma unroll
-            for (int j = 0; j < 16; j += 4) {
-              *reinterpret_cast<float4*>(f_mu + c0 + j) = make_float4(mu[j], mu[j + 1], mu[j + 2], mu[j + 3]);
-              *reinterpret_cast<float4*>(f_var + c0 + j) = make_float4(var[j], var[j + 1], var[j + 2], var[j + 3]);
-            }
+            const size_t o = (((size_t)ob * p.out_h + oy) * p.out_w + ox) * p.cout + n0;
+            f_mu = p.dst_mu + o;
+            f_var = p.dst_var + o;
           } else {
-            uint32_t hi[8], lo[8], vr[8];
-#pragma unroll
-            for (int j = 0; j < 8; ++j) {
-              const float a0 = mu[2 * j], a1 = mu[2 * j + 1];
-              const __nv_bfloat16 h0 = __float2bfloat16_rn(a0), h1 = __float2bfloat16_rn(a1);
-              hi[j] = (uint32_t)__bfloat16_as_ushort(h0) | ((uint32_t)__bfloat16_as_ushort(h1) << 16);
-              lo[j] = hl_pack2(a0 - __bfloat162float(h0), a1 - __bfloat162float(h1));
-              vr[j] = hl_pack2(var[2 * j], var[2 * j + 1]);
-            }
-            uint4* ph = reinterpret_cast<uint4*>(d_hi + c0);
-            uint4* pl = reinterpret_cast<uint4*>(d_hi + p.dc + c0);
-            uint4* pv = reinterpret_cast<uint4*>(d_hi + 2 * p.dc + c0);
-            ph[0] = make_uint4(hi[0], hi[1], hi[2], hi[3]);
-            ph[1] = make_uint4(hi[4], hi[5], hi[6], hi[7]);
-            pl[0] = make_uint4(lo[0], lo[1], lo[2], lo[3]);
-            pl[1] = make_uint4(lo[4], lo[5], lo[6], lo[7]);
-            pv[0] = make_uint4(vr[0], vr[1], vr[2], vr[3]);
-            pv[1] = make_uint4(vr[4], vr[5], vr[6], vr[7]);
+            d_hi = p.dst + ((((size_t)ob * p.dh + oy + p.dy0) * p.dw + ox + p.dx0) * 3) * p.dc + p.dc0 + n0;
           }
         }
+        ptx::mbar_wait(acc_full(as), par);
+        ptx::tc_fence_after();
+        const uint32_t lane_base = tmem_base + ((uint32_t)(q * 32) << 16) + as * ACC_STAGE + half * NH;
+#pragma unroll 1
+        for (int c0 = 0; c0 < NH; c0 += 16) {
+          uint32_t am[16], av[16];
+          ptx::tmem_ld16(lane_base + c0, am);
+          ptx::tmem_ld16(lane_base + (CONCAT ? 2 * NT : NT) + c0, av);
+          if constexpr (CONCAT) {
+            uint32_t am2[16];
+            ptx::tmem_ld16(lane_base + NT + c0, am2);     // the hi x W_lo half of the mean
+            ptx::tmem_ld_wait();
+#pragma unroll
+            for (int j = 0; j < 16; ++j) am[j] = __float_as_uint(__uint_as_float(am[j]) + __uint_as_float(am2[j]));
+          } else {
+            ptx::tmem_ld_wait();
+          }
+          float mu[16], var[16];
+#pragma unroll
+          for (int j4 = 0; j4 < 16; j4 += 4) {
+            const float4 s4 = *reinterpret_cast<const float4*>(s_sm + n0 + c0 + j4);   // warp-uniform: broadcast
+            const float sv[4] = {s4.x, s4.y, s4.z, s4.w};
+#pragma unroll
+            for (int e = 0; e < 4; ++e) {
+              const int j = j4 + e;
+              float mj = __uint_as_float(am[j]);
+              float vj = fmaxf(fmaf(sv[e], r, __uint_as_float(av[j])), 0.f);   // all terms >= 0: clamp guards rounding
+              if (p.relu) {
+                vj = mj > 0.f ? vj : 0.f;
+                mj = fmaxf(mj, 0.f);
+              }
+              mu[j] = mj;
+              var[j] = vj;
+            }
+          }
+          if (valid) {
+            if (p.dst_f32) {
+#pragma unroll
+              for (int j = 0; j < 16; j += 4) {
+                *reinterpret_cast<float4*>(f_mu + c0 + j) = make_float4(mu[j], mu[j + 1], mu[j + 2], mu[j + 3]);
+                *reinterpret_cast<float4*>(f_var + c0 + j) = make_float4(var[j], var[j + 1], var[j + 2], var[j + 3]);
+              }
+            } else {
+              uint32_t hi[8], lo[8], vr[8];
+#pragma unroll
+              for (int j = 0; j < 8; ++j) {
+                const float a0 = mu[2 * j], a1 = mu[2 * j + 1];
+                hi[j] = hl_pack2(a0, a1);                                   // one packed convert
+                lo[j] = hl_pack2(a0 - hl_lo(hi[j]), a1 - hl_hi(hi[j]));
+                vr[j] = hl_pack2(var[2 * j], var[2 * j + 1]);
+              }
+              uint4* ph = reinterpret_cast<uint4*>(d_hi + c0);
+              uint4* pl = reinterpret_cast<uint4*>(d_hi + p.dc + c0);
+              uint4* pv = reinterpret_cast<uint4*>(d_hi + 2 * p.dc + c0);
+              ph[0] = make_uint4(hi[0], hi[1], hi[2], hi[3]);
+              ph[1] = make_uint4(hi[4], hi[5], hi[6], hi[7]);
+              pl[0] = make_uint4(lo[0], lo[1], lo[2], lo[3]);
+              pl[1] = make_uint4(lo[4], lo[5], lo[6], lo[7]);
+              pv[0] = make_uint4(vr[0], vr[1], vr[2], vr[3]);
+              pv[1] = make_uint4(vr[4], vr[5], vr[6], vr[7]);
+            }
+          }
+        }
+        ptx::tc_fence_before();
+        __syncwarp();
+        if (lane == 0) ptx::mbar_arrive(acc_empty(as));    // this warp's TMEM reads of stage `as` are done
       }
-      ptx::tc_fence_before();
-      __syncwarp();
-      if (lane == 0) ptx::mbar_arrive(acc_empty(as));    // this warp's TMEM reads of stage `as` are done
     }
   }
 
   ptx::tc_fence_before();
   __syncthreads();
-  if (warp == 1) ptx::tmem_dealloc(tmem_base, 4 * NT);
+  if (warp == 1) ptx::tmem_dealloc(tmem_base, TMEM_COLS);
 }
 
 // ---------------------------------------------------------------------------------------------------------
@@ -467,18 +529,30 @@ static int hl_make_weight_map(CUtensorMap* out, const void* w_packed, int taps, 
   return SN_OK;
 }
 
-template <int NT>
-static int hl_launch(const HlMaps& maps, const HlP& p, cudaStream_t st) {
+template <int NT, int KS, bool RESIDENT>
+static int hl_launch3(const HlMaps& maps, const HlP& p, cudaStream_t st) {
   static std::once_flag once;
   static cudaError_t attr_err = cudaSuccess;
   std::call_once(once, [] {
-    attr_err = cudaFuncSetAttribute(conv_moments_halo_kernel<NT>, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                    HL_SMEM);
+    attr_err = cudaFuncSetAttribute(conv_moments_halo_kernel<NT, KS, RESIDENT>,
+                                    cudaFuncAttributeMaxDynamicSharedMemorySize, HL_SMEM);
   });
   if (attr_err != cudaSuccess) return fail(SN_ERR_LAUNCH, "conv_halo: cannot reserve %d B of shared memory", HL_SMEM);
   int grid = p.total_tiles < num_sms() ? p.total_tiles : num_sms();
-  conv_moments_halo_kernel<NT><<<grid, HL_THREADS, HL_SMEM, st>>>(maps, p);
+  conv_moments_halo_kernel<NT, KS, RESIDENT><<<grid, HL_THREADS, HL_SMEM, st>>>(maps, p);
   return check_launch("conv_moments_halo");
+}
+
+template <int NT>
+static int hl_launch(const HlMaps& maps, const HlP& p, cudaStream_t st) {
+  switch (p.ksize * 2 + (p.b_resident ? 1 : 0)) {
+    case 2: return hl_launch3<NT, 1, false>(maps, p, st);
+    case 3: return hl_launch3<NT, 1, true>(maps, p, st);
+    case 4: return hl_launch3<NT, 2, false>(maps, p, st);
+    case 5: return hl_launch3<NT, 2, true>(maps, p, st);
+    case 6: return hl_launch3<NT, 3, false>(maps, p, st);
+    default: return hl_launch3<NT, 3, true>(maps, p, st);
+  }
 }
 
 // Called by sn_conv_moments_fwd_tc (sn_tc_conv.cu) after argument validation.
@@ -498,6 +572,7 @@ int conv_moments_halo_dispatch(const sn_tc_conv_desc* d, cudaStream_t stream) {
 
   const HaloTiling t = choose_tiling(d->batch, d->in_h, d->in_w, keff);
   SN_REQUIRE(t.eff > 0, SN_ERR_UNSUPPORTED, "conv_halo: no tiling for %dx%d k=%d", d->in_h, d->in_w, keff);
+  SN_REQUIRE(d->cout <= 512, SN_ERR_UNSUPPORTED, "conv_halo: cout %d > 512", d->cout);
 
   HlP p{};
   p.tiles_x = t.tiles_x; p.tiles_y = t.tiles_y; p.tiles_b = t.tiles_b;
@@ -521,8 +596,8 @@ int conv_moments_halo_dispatch(const sn_tc_conv_desc* d, cudaStream_t stream) {
   p.dst_mu = d->dst_mu; p.dst_var = d->dst_var; p.out_h = out_h; p.out_w = out_w;
   p.s = d->s;
 
-  // shared-memory plan: [A stages][B slots][1 KB barriers][2 KB q buffers], 1 KB alignment slack
-  const int avail = HL_SMEM - 1024 - 1024 - 2048;
+  // shared-memory plan: [A stages][B slots][1 KB barriers][2 KB q buffers][2 KB s], 1 KB alignment slack
+  const int avail = HL_SMEM - 1024 - 1024 - 2048 - 2048;
   const int a_stage = 3 * p.a_plane;
   const int b_slot = 3 * nt * HL_KC * 2;
   const int resident_slots = cblk * taps;

@@ -68,6 +68,9 @@ TC_CASES = [
     (2, 70, 150, 32, 32, 3),   # wide image: column tiles, resident weights, many tiles per persistent CTA
     (9, 8, 8, 64, 64, 3),      # tiny images: several per 128-row tile
     (40, 30, 30, 64, 32, 3),   # > 148 tiles with resident weights (18 slots)
+    (120, 30, 30, 64, 32, 3),  # ~6 tiles per persistent CTA, two channel blocks per tile, resident weights
+    (40, 40, 40, 64, 64, 3),   # ~3.5 tiles per CTA, streamed weights (18 x 12 KB does not fit)
+    (64, 24, 24, 128, 128, 3), # ~3 tiles per CTA, NT = 128, four channel blocks
 ]
 
 
