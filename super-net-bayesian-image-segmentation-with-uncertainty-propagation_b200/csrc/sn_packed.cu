@@ -196,6 +196,81 @@ __global__ void __launch_bounds__(256) first_conv_packed_kernel(int B, int H, in
   }
 }
 
+// Specialisation for the shapes the two networks use (k = 3, 32 output channels, Cin = 4 or 1): one thread owns
+// one output pixel and all 32 channels.  The 9*CIN input values sit in registers, the weights are read from shared
+// memory with warp-uniform (broadcast) 16-byte loads -- one LDS.128 per four FMAs -- and the pixel's
+// 3 x 64 B (hi, lo, var) go out as twelve 16-byte stores.
+template <int CIN>
+__global__ void __launch_bounds__(128) first_conv_k3c32_kernel(int B, int H, int W, const float* __restrict__ x,
+                                                               const float* __restrict__ w,
+                                                               const float* __restrict__ ws, sn_packed_view dst,
+                                                               int relu) {
+  constexpr int K = 9 * CIN, COUT = 32;
+  __shared__ __align__(16) float sw[K * COUT];
+  __shared__ float ss[COUT];
+  for (int i = threadIdx.x; i < K * COUT; i += blockDim.x) sw[i] = w[i];
+  if (threadIdx.x < COUT) ss[threadIdx.x] = softplus_f(ws[threadIdx.x]);
+  __syncthreads();
+  const int Ho = H - 2, Wo = W - 2;
+  const size_t total = (size_t)B * Ho * Wo;
+  const size_t stride = (size_t)gridDim.x * blockDim.x;
+  __nv_bfloat16* out = reinterpret_cast<__nv_bfloat16*>(dst.base);
+  for (size_t i = blockIdx.x * (size_t)blockDim.x + threadIdx.x; i < total; i += stride) {
+    const int xo = (int)(i % Wo);
+    size_t t = i / Wo;
+    const int yo = (int)(t % Ho);
+    const int b = (int)(t / Ho);
+    float xv[K];
+    float r = 0.f;
+#pragma unroll
+    for (int kh = 0; kh < 3; ++kh)
+#pragma unroll
+      for (int kw = 0; kw < 3; ++kw) {
+        const float* px = x + (((size_t)b * H + yo + kh) * W + xo + kw) * CIN;
+        if constexpr (CIN == 4) {
+          const float4 v = __ldg(reinterpret_cast<const float4*>(px));
+          xv[(kh * 3 + kw) * 4 + 0] = v.x; xv[(kh * 3 + kw) * 4 + 1] = v.y;
+          xv[(kh * 3 + kw) * 4 + 2] = v.z; xv[(kh * 3 + kw) * 4 + 3] = v.w;
+        } else {
+#pragma unroll
+          for (int c = 0; c < CIN; ++c) xv[(kh * 3 + kw) * CIN + c] = __ldg(px + c);
+        }
+      }
+#pragma unroll
+    for (int k = 0; k < K; ++k) r = fmaf(xv[k], xv[k], r);
+    __nv_bfloat16* o = out + ((((size_t)b * dst.h + yo + dst.y0) * dst.w + xo + dst.x0) * 3) * dst.c + dst.c0;
+#pragma unroll
+    for (int n8 = 0; n8 < COUT; n8 += 8) {
+      float acc[8];
+#pragma unroll
+      for (int j = 0; j < 8; ++j) acc[j] = 0.f;
+#pragma unroll
+      for (int k = 0; k < K; ++k) {
+        const float4 w0 = *reinterpret_cast<const float4*>(sw + k * COUT + n8);
+        const float4 w1 = *reinterpret_cast<const float4*>(sw + k * COUT + n8 + 4);
+        acc[0] = fmaf(xv[k], w0.x, acc[0]); acc[1] = fmaf(xv[k], w0.y, acc[1]);
+        acc[2] = fmaf(xv[k], w0.z, acc[2]); acc[3] = fmaf(xv[k], w0.w, acc[3]);
+        acc[4] = fmaf(xv[k], w1.x, acc[4]); acc[5] = fmaf(xv[k], w1.y, acc[5]);
+        acc[6] = fmaf(xv[k], w1.z, acc[6]); acc[7] = fmaf(xv[k], w1.w, acc[7]);
+      }
+      float var[8];
+#pragma unroll
+      for (int j = 0; j < 8; ++j) {
+        var[j] = ss[n8 + j] * r;
+        if (relu) {
+          var[j] = acc[j] > 0.f ? var[j] : 0.f;
+          acc[j] = fmaxf(acc[j], 0.f);
+        }
+      }
+      uint4 hi, lo;
+      split8(acc, hi, lo);
+      *reinterpret_cast<uint4*>(o + n8) = hi;
+      *reinterpret_cast<uint4*>(o + dst.c + n8) = lo;
+      *reinterpret_cast<uint4*>(o + 2 * dst.c + n8) = pack8(var);
+    }
+  }
+}
+
 // ---------------------------------------------------------------------------------------------------------
 // arg-max pooling on packed windows (Brats.py:171-174,206-216); thread = (output pixel, 8 channels)
 // ---------------------------------------------------------------------------------------------------------
@@ -404,10 +479,20 @@ int sn_first_conv_fwd_packed(int32_t batch, int32_t in_h, int32_t in_w, int32_t 
   const int Ho = in_h - ksize + 1, Wo = in_w - ksize + 1;
   int rc = check_pview(dst, batch, Ho, Wo, cout, "first_conv dst");
   if (rc) return rc;
+  const int relu = (flags & SN_TC_RELU) ? 1 : 0;
+  if (ksize == 3 && cout == 32 && (cin == 4 || cin == 1)) {
+    const size_t pixels = (size_t)batch * Ho * Wo;
+    const int grid = ew_grid(pixels, 128, 8);
+    if (cin == 4)
+      first_conv_k3c32_kernel<4><<<grid, 128, 0, as_stream(st)>>>(batch, in_h, in_w, x, w_mu, w_sigma, *dst, relu);
+    else
+      first_conv_k3c32_kernel<1><<<grid, 128, 0, as_stream(st)>>>(batch, in_h, in_w, x, w_mu, w_sigma, *dst, relu);
+    return check_launch("first_conv_k3c32");
+  }
   const size_t smem = ((size_t)ksize * ksize * cin * cout + cout) * sizeof(float);
   const size_t total = (size_t)batch * Ho * Wo * (cout / 8);
   first_conv_packed_kernel<<<ew_grid(total, 256, 4), 256, smem, as_stream(st)>>>(
-      batch, in_h, in_w, cin, cout, ksize, x, w_mu, w_sigma, *dst, (flags & SN_TC_RELU) ? 1 : 0);
+      batch, in_h, in_w, cin, cout, ksize, x, w_mu, w_sigma, *dst, relu);
   return check_launch("first_conv_packed");
 }
 

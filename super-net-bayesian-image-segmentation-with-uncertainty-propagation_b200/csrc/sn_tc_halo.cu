@@ -13,8 +13,9 @@
 //   * the rank-1 term needs q[pixel] = sum_c(mu^2+var) once per halo pixel (not once per tap):
 //     r[j] = sum_taps q[j + kh*R + kw] from a 1 KB smem array;
 //   * two TMEM accumulator stages: the epilogue of tile i overlaps the TMA/UMMA main loop of tile i+1.
-// Warp roles (448 threads): warp 0 TMA producer, warp 1 UMMA issuer (+TMEM alloc), warps 2-5 q reduction over
-// every A stage, warps 6-13 epilogue: two warps per TMEM lane quarter, each taking half of the tile's columns
+// Warp roles (576 threads): warp 0 TMA producer, warp 1 UMMA issuer (+TMEM alloc), warps 2-9 q reduction over
+// every A stage (thread = halo pixel), warps 10-17 epilogue: two warps per TMEM lane quarter, each taking half of
+// the tile's columns
 // (q arrives through a double-buffered smem array guarded by mbarriers).  Profiling the first version (4
 // epilogue warps, one per SM sub-partition) showed the epilogue, a long dependent instruction chain per pixel
 // row, as the critical path of the 32/64-channel layers; hence the second set of warps.  Same math and data layout as sn_tc_conv.cu
@@ -29,7 +30,7 @@ namespace sn {
 
 constexpr int HL_BM = 128;
 constexpr int HL_KC = 32;
-constexpr int HL_THREADS = 448;       // 14 warps: TMA, UMMA, 4 x q reduction, 8 x epilogue
+constexpr int HL_THREADS = 576;       // 18 warps: TMA, UMMA, 8 x q reduction, 8 x epilogue
 constexpr int HL_MAX_BSLOTS = 36;
 constexpr int HL_MAX_ASTAGES = 4;
 constexpr int HL_SMEM = 232448;        // 227 KB: always requested so exactly one CTA owns an SM (and its TMEM)
@@ -64,6 +65,30 @@ __device__ __forceinline__ uint32_t hl_pack2(float a, float b) {
   __nv_bfloat162 t = __floats2bfloat162_rn(a, b);
   return *reinterpret_cast<uint32_t*>(&t);
 }
+
+// Mixed-radix walk over (n-tile, x-tile, y-tile, image-tile) in steps of gridDim.x: no divisions per tile.
+struct TileIt {
+  int nt, tx, ty, tb, dn, dx, dy, db;
+  __device__ __forceinline__ void init(int tile0, int step, const HlP& p) {
+    int t = tile0;
+    nt = t % p.tiles_n; t /= p.tiles_n;
+    tx = t % p.tiles_x; t /= p.tiles_x;
+    ty = t % p.tiles_y; tb = t / p.tiles_y;
+    t = step;
+    dn = t % p.tiles_n; t /= p.tiles_n;
+    dx = t % p.tiles_x; t /= p.tiles_x;
+    dy = t % p.tiles_y; db = t / p.tiles_y;
+  }
+  __device__ __forceinline__ void next(const HlP& p) {
+    nt += dn;
+    int c = nt >= p.tiles_n; nt -= c ? p.tiles_n : 0;
+    tx += dx + c;
+    c = tx >= p.tiles_x; tx -= c ? p.tiles_x : 0;
+    ty += dy + c;
+    c = ty >= p.tiles_y; ty -= c ? p.tiles_y : 0;
+    tb += db + c;
+  }
+};
 
 template <int NT, int KS, bool RESIDENT>
 __global__ void __launch_bounds__(HL_THREADS, 1) conv_moments_halo_kernel(const __grid_constant__ HlMaps maps,
@@ -105,7 +130,7 @@ __global__ void __launch_bounds__(HL_THREADS, 1) conv_moments_halo_kernel(const 
     ptx::prefetch_tensormap(&maps.w);
     for (int s = 0; s < p.sa; ++s) {
       ptx::mbar_init(a_full(s), 1);
-      ptx::mbar_init(a_empty(s), 5);          // UMMA commit + the 4 reducer warps
+      ptx::mbar_init(a_empty(s), 9);          // UMMA commit + the 8 reducer warps
     }
     for (int s = 0; s < p.sb; ++s) {
       ptx::mbar_init(b_full(s), 1);
@@ -114,7 +139,7 @@ __global__ void __launch_bounds__(HL_THREADS, 1) conv_moments_halo_kernel(const 
     for (int s = 0; s < 2; ++s) {
       ptx::mbar_init(acc_full(s), 1);
       ptx::mbar_init(acc_empty(s), 8);        // 8 epilogue warps
-      ptx::mbar_init(q_full(s), 4);           // 4 reducer warps
+      ptx::mbar_init(q_full(s), 8);           // 8 reducer warps
       ptx::mbar_init(q_empty(s), 8);          // 8 epilogue warps
     }
     ptx::fence_barrier_init();
@@ -133,12 +158,10 @@ __global__ void __launch_bounds__(HL_THREADS, 1) conv_moments_halo_kernel(const 
     // ===================== TMA producer =====================
     if (lane == 0) {
       int ai = 0, bi = 0;     // running A-stage / B-slot fill counters
-      for (int tile = blockIdx.x, titer = 0; tile < p.total_tiles; tile += gridDim.x, ++titer) {
-        const int nt_i = tile % p.tiles_n;
-        int t = tile / p.tiles_n;
-        const int tx = t % p.tiles_x; t /= p.tiles_x;
-        const int ty = t % p.tiles_y;
-        const int tb = t / p.tiles_y;
+      TileIt it;
+      it.init(blockIdx.x, gridDim.x, p);
+      for (int tile = blockIdx.x, titer = 0; tile < p.total_tiles; tile += gridDim.x, ++titer, it.next(p)) {
+        const int nt_i = it.nt, tx = it.tx, ty = it.ty, tb = it.tb;
         const int ncol0 = nt_i * NT;
         const int group = ncol0 / p.cout;
         const int n0 = ncol0 - group * p.cout;
@@ -177,11 +200,12 @@ __global__ void __launch_bounds__(HL_THREADS, 1) conv_moments_halo_kernel(const 
               }
               ptx::mbar_arrive_expect_tx(b_full(slot), (uint32_t)B_SLOT);
               const uint32_t sb_addr = b_base + slot * B_SLOT;
-              const int wtap = p.upconv ? group : tap;
+              // regular conv: weights [3*taps][cout][cin], rows n0.. of tap `tap`; up-conv: [3][4*cout][cin], the N
+              // tile may span several parity groups (rows ncol0.. of the (parity, channel) axis)
 #pragma unroll
               for (int pl = 0; pl < 3; ++pl)
-                ptx::tma_load_3d(sb_addr + pl * B_PLANE, &maps.w, b_full(slot), cbt * HL_KC, n0,
-                                 pl * p.taps_w + wtap);
+                ptx::tma_load_3d(sb_addr + pl * B_PLANE, &maps.w, b_full(slot), cbt * HL_KC,
+                                 p.upconv ? ncol0 : n0, p.upconv ? pl : pl * p.taps_w + tap);
             }
           }
         }
@@ -264,67 +288,62 @@ __global__ void __launch_bounds__(HL_THREADS, 1) conv_moments_halo_kernel(const 
       }
     }
   } else {
-    if (warp < 6) {
-      // ===================== q reduction (warps 2-5): q[halo pixel] = sum_c (mu^2 + var) =====================
-      // These four warps consume EVERY A stage in order (so the stage barriers see one consistent consumer) and
-      // hand the per-tile q array to the epilogue warps through a double-buffered smem array.
+    if (warp < 10) {
+      // ===================== q reduction (warps 2-9): q[halo pixel] = sum_c (mu^2 + var) =====================
+      // These eight warps (thread = halo pixel row) consume EVERY A stage in order, so the stage barriers see one
+      // consistent consumer, and hand the per-tile q array to the epilogue warps through a double-buffered smem
+      // array.  (With four warps this role was the critical path of the 32-channel layers.)
       const int row = (warp - 2) * 32 + lane;
-      int ai = 0;
+      int a_stage_i = 0;
+      uint32_t a_par = 0;
       for (int tile = blockIdx.x, titer = 0; tile < p.total_tiles; tile += gridDim.x, ++titer) {
-        float q0 = 0.f, q1 = 0.f;
-        for (int cbt = 0; cbt < cblk; ++cbt, ++ai) {
-          const int stage = ai % p.sa;
-          const uint32_t parity = (uint32_t)(ai / p.sa) & 1u;
-          ptx::mbar_wait(a_full(stage), parity);
-          const uint8_t* a = smem_gen + stage * a_stage;
+        float qa = 0.f, qb = 0.f, qc = 0.f, qd = 0.f;         // four chains for ILP
+        for (int cbt = 0; cbt < cblk; ++cbt) {
+          ptx::mbar_wait(a_full(a_stage_i), a_par);
+          if (row < p.rows_box) {
+            const uint8_t* ar = smem_gen + a_stage_i * a_stage + row * 64;
 #pragma unroll
-          for (int h = 0; h < 2; ++h) {
-            const int rr = row + h * 128;
-            if (rr < p.rows_box) {
-              const uint8_t* ar = a + rr * 64;
-              float acc = 0.f;
+            for (int j = 0; j < 4; ++j) {
+              const int ch = ((j + (row >> 1)) & 3) * 16;   // chunk rotation: conflict-free, order-insensitive sum
+              const uint4 hh4 = *reinterpret_cast<const uint4*>(ar + ch);
+              const uint4 ll4 = *reinterpret_cast<const uint4*>(ar + p.a_plane + ch);
+              const uint4 vv4 = *reinterpret_cast<const uint4*>(ar + 2 * p.a_plane + ch);
+              const uint32_t hh[4] = {hh4.x, hh4.y, hh4.z, hh4.w}, ll[4] = {ll4.x, ll4.y, ll4.z, ll4.w},
+                             vv[4] = {vv4.x, vv4.y, vv4.z, vv4.w};
 #pragma unroll
-              for (int j = 0; j < 4; ++j) {
-                const int ch = ((j + (rr >> 1)) & 3) * 16;   // chunk rotation: conflict-free, order-insensitive sum
-                const uint4 hh4 = *reinterpret_cast<const uint4*>(ar + ch);
-                const uint4 ll4 = *reinterpret_cast<const uint4*>(ar + p.a_plane + ch);
-                const uint4 vv4 = *reinterpret_cast<const uint4*>(ar + 2 * p.a_plane + ch);
-                const uint32_t hh[4] = {hh4.x, hh4.y, hh4.z, hh4.w}, ll[4] = {ll4.x, ll4.y, ll4.z, ll4.w},
-                               vv[4] = {vv4.x, vv4.y, vv4.z, vv4.w};
-#pragma unroll
-                for (int e = 0; e < 4; ++e) {
-                  const float m_a = hl_lo(hh[e]) + hl_lo(ll[e]);
-                  const float m_b = hl_hi(hh[e]) + hl_hi(ll[e]);
-                  acc = fmaf(m_a, m_a, acc);
-                  acc = fmaf(m_b, m_b, acc);
-                  acc += hl_lo(vv[e]) + hl_hi(vv[e]);
-                }
+              for (int e = 0; e < 4; ++e) {
+                const float m_a = hl_lo(hh[e]) + hl_lo(ll[e]);
+                const float m_b = hl_hi(hh[e]) + hl_hi(ll[e]);
+                qa = fmaf(m_a, m_a, qa);
+                qb = fmaf(m_b, m_b, qb);
+                qc += hl_lo(vv[e]);
+                qd += hl_hi(vv[e]);
               }
-              if (h == 0) q0 += acc; else q1 += acc;
             }
           }
           __syncwarp();
-          if (lane == 0) ptx::mbar_arrive(a_empty(stage));
+          if (lane == 0) ptx::mbar_arrive(a_empty(a_stage_i));
+          if (++a_stage_i == p.sa) { a_stage_i = 0; a_par ^= 1u; }
         }
         const int qs = titer & 1;
         ptx::mbar_wait(q_empty(qs), (((uint32_t)titer >> 1) & 1u) ^ 1u);
-        float* myq = qbuf + qs * 256;
-        myq[row] = q0;
-        myq[row + 128] = q1;                     // rows >= rows_box hold 0
+        qbuf[qs * 256 + row] = (qa + qb) + (qc + qd);        // rows >= rows_box hold 0
         __syncwarp();
         if (lane == 0) ptx::mbar_arrive(q_full(qs));
       }
     } else {
-      // ===================== epilogue (warps 6-13) =====================
+      // ===================== epilogue (warps 10-17) =====================
       const int q = warp & 3;                   // TMEM lane quarter this warp may access
-      const int half = (warp - 6) >> 2;         // which half of the tile's NT columns this warp converts
+      const int half = (warp - 10) >> 2;        // which half of the tile's NT columns this warp converts
       constexpr int NH = NT / 2;
       const int row = q * 32 + lane;            // GEMM row == TMEM lane == halo pixel index
       const int x = row % p.R;
       const int yy = row / p.R;
       const int y = yy % p.THb;
       const int n = yy / p.THb;
-      for (int tile = blockIdx.x, titer = 0; tile < p.total_tiles; tile += gridDim.x, ++titer) {
+      TileIt it;
+      it.init(blockIdx.x, gridDim.x, p);
+      for (int tile = blockIdx.x, titer = 0; tile < p.total_tiles; tile += gridDim.x, ++titer, it.next(p)) {
         const int as = titer & 1;
         const uint32_t par = ((uint32_t)titer >> 1) & 1u;
         ptx::mbar_wait(q_full(as), par);
@@ -344,34 +363,33 @@ __global__ void __launch_bounds__(HL_THREADS, 1) conv_moments_halo_kernel(const 
         if (lane == 0) ptx::mbar_arrive(q_empty(as));
 
         // ---- tile coordinates
-        const int nt_i = tile % p.tiles_n;
-        int t = tile / p.tiles_n;
-        const int tx = t % p.tiles_x; t /= p.tiles_x;
-        const int ty = t % p.tiles_y;
-        const int tb = t / p.tiles_y;
-        const int ncol0 = nt_i * NT;
-        const int group = ncol0 / p.cout;
-        const int n0 = ncol0 - group * p.cout + half * NH;     // first output channel this warp writes
+        const int nt_i = it.nt, tx = it.tx, ty = it.ty, tb = it.tb;
+        const int gcol0 = nt_i * NT + half * NH;               // first column (parity group, channel) of this warp
         const int ox_i = tx * p.TWo + x, oy_i = ty * p.THo + y, ob = tb * p.TN + n;
         const bool valid = x < p.TWo && y < p.THo && n < p.TN && ox_i < p.Wo && oy_i < p.Ho && ob < p.B;
-        int oy = oy_i, ox = ox_i;
-        if (p.upconv) { oy = 2 * oy_i + (group >> 1); ox = 2 * ox_i + (group & 1); }
-        __nv_bfloat16* d_hi = nullptr;
-        float *f_mu = nullptr, *f_var = nullptr;
-        if (valid) {
-          if (p.dst_f32) {
-            const size_t o = (((size_t)ob * p.out_h + oy) * p.out_w + ox) * p.cout + n0;
-            f_mu = p.dst_mu + o;
-            f_var = p.dst_var + o;
-          } else {
-            d_hi = p.dst + ((((size_t)ob * p.dh + oy + p.dy0) * p.dw + ox + p.dx0) * 3) * p.dc + p.dc0 + n0;
-          }
-        }
         ptx::mbar_wait(acc_full(as), par);
         ptx::tc_fence_after();
         const uint32_t lane_base = tmem_base + ((uint32_t)(q * 32) << 16) + as * ACC_STAGE + half * NH;
 #pragma unroll 1
         for (int c0 = 0; c0 < NH; c0 += 16) {
+          // destination of this 16-channel chunk (an up-conv tile may span several parity groups; cout % 32 == 0,
+          // so a chunk never straddles two)
+          const int gcol = gcol0 + c0;
+          const int group = p.upconv ? gcol / p.cout : 0;
+          const int nch = gcol - group * p.cout;               // first output channel of the chunk
+          int oy = oy_i, ox = ox_i;
+          if (p.upconv) { oy = 2 * oy_i + (group >> 1); ox = 2 * ox_i + (group & 1); }
+          __nv_bfloat16* d_hi = nullptr;
+          float *f_mu = nullptr, *f_var = nullptr;
+          if (valid) {
+            if (p.dst_f32) {
+              const size_t o = (((size_t)ob * p.out_h + oy) * p.out_w + ox) * p.cout + nch;
+              f_mu = p.dst_mu + o;
+              f_var = p.dst_var + o;
+            } else {
+              d_hi = p.dst + ((((size_t)ob * p.dh + oy + p.dy0) * p.dw + ox + p.dx0) * 3) * p.dc + p.dc0 + nch;
+            }
+          }
           uint32_t am[16], av[16];
           ptx::tmem_ld16(lane_base + c0, am);
           ptx::tmem_ld16(lane_base + (CONCAT ? 2 * NT : NT) + c0, av);
@@ -387,7 +405,7 @@ __global__ void __launch_bounds__(HL_THREADS, 1) conv_moments_halo_kernel(const 
           float mu[16], var[16];
 #pragma unroll
           for (int j4 = 0; j4 < 16; j4 += 4) {
-            const float4 s4 = *reinterpret_cast<const float4*>(s_sm + n0 + c0 + j4);   // warp-uniform: broadcast
+            const float4 s4 = *reinterpret_cast<const float4*>(s_sm + nch + j4);   // warp-uniform: broadcast
             const float sv[4] = {s4.x, s4.y, s4.z, s4.w};
 #pragma unroll
             for (int e = 0; e < 4; ++e) {
@@ -406,8 +424,8 @@ __global__ void __launch_bounds__(HL_THREADS, 1) conv_moments_halo_kernel(const 
             if (p.dst_f32) {
 #pragma unroll
               for (int j = 0; j < 16; j += 4) {
-                *reinterpret_cast<float4*>(f_mu + c0 + j) = make_float4(mu[j], mu[j + 1], mu[j + 2], mu[j + 3]);
-                *reinterpret_cast<float4*>(f_var + c0 + j) = make_float4(var[j], var[j + 1], var[j + 2], var[j + 3]);
+                *reinterpret_cast<float4*>(f_mu + j) = make_float4(mu[j], mu[j + 1], mu[j + 2], mu[j + 3]);
+                *reinterpret_cast<float4*>(f_var + j) = make_float4(var[j], var[j + 1], var[j + 2], var[j + 3]);
               }
             } else {
               uint32_t hi[8], lo[8], vr[8];
@@ -418,9 +436,9 @@ __global__ void __launch_bounds__(HL_THREADS, 1) conv_moments_halo_kernel(const 
                 lo[j] = hl_pack2(a0 - hl_lo(hi[j]), a1 - hl_hi(hi[j]));
                 vr[j] = hl_pack2(var[2 * j], var[2 * j + 1]);
               }
-              uint4* ph = reinterpret_cast<uint4*>(d_hi + c0);
-              uint4* pl = reinterpret_cast<uint4*>(d_hi + p.dc + c0);
-              uint4* pv = reinterpret_cast<uint4*>(d_hi + 2 * p.dc + c0);
+              uint4* ph = reinterpret_cast<uint4*>(d_hi);
+              uint4* pl = reinterpret_cast<uint4*>(d_hi + p.dc);
+              uint4* pv = reinterpret_cast<uint4*>(d_hi + 2 * p.dc);
               ph[0] = make_uint4(hi[0], hi[1], hi[2], hi[3]);
               ph[1] = make_uint4(hi[4], hi[5], hi[6], hi[7]);
               pl[0] = make_uint4(lo[0], lo[1], lo[2], lo[3]);
@@ -563,8 +581,9 @@ int conv_moments_halo_dispatch(const sn_tc_conv_desc* d, cudaStream_t stream) {
   const int keff = upconv ? 1 : d->ksize;
   const int Ho = d->in_h - keff + 1, Wo = d->in_w - keff + 1;
   const int out_h = upconv ? 2 * d->in_h : Ho, out_w = upconv ? 2 * d->in_w : Wo;
-  const int nt = d->cout % 128 == 0 ? 128 : (d->cout % 64 == 0 ? 64 : 32);
   const int groups = upconv ? 4 : 1;
+  const int ncols = groups * d->cout;               // GEMM N: an up-conv tile may cover several parity groups
+  const int nt = ncols % 128 == 0 ? 128 : (ncols % 64 == 0 ? 64 : 32);
   const int taps_w = upconv ? 4 : d->ksize * d->ksize;
   const int cin = d->src_c[0] + d->src_c[1];
   const int cblk = cin / HL_KC;
@@ -576,7 +595,7 @@ int conv_moments_halo_dispatch(const sn_tc_conv_desc* d, cudaStream_t stream) {
 
   HlP p{};
   p.tiles_x = t.tiles_x; p.tiles_y = t.tiles_y; p.tiles_b = t.tiles_b;
-  p.tiles_n = groups * d->cout / nt;
+  p.tiles_n = ncols / nt;
   const long long total = (long long)p.tiles_x * p.tiles_y * p.tiles_b * p.tiles_n;
   SN_REQUIRE(total < (1ll << 30), SN_ERR_UNSUPPORTED, "conv_halo: too many tiles");
   p.total_tiles = (int)total;
@@ -623,7 +642,9 @@ int conv_moments_halo_dispatch(const sn_tc_conv_desc* d, cudaStream_t stream) {
       if ((rc = hl_make_act_map(&maps.a[s][pl], d->src[srcs], pl, d->src_c[srcs], d->batch, d->in_h, d->in_w, t)))
         return rc;
   }
-  if ((rc = hl_make_weight_map(&maps.w, d->w_packed, taps_w, d->cout, cin, nt))) return rc;
+  // regular: [3*taps][cout][cin]; up-conv: [3][4*cout][cin] (same memory, parity and channel fused into one axis)
+  if ((rc = hl_make_weight_map(&maps.w, d->w_packed, upconv ? 1 : taps_w, upconv ? ncols : d->cout, cin, nt)))
+    return rc;
   switch (nt) {
     case 128: return hl_launch<128>(maps, p, stream);
     case 64: return hl_launch<64>(maps, p, stream);
