@@ -204,22 +204,28 @@ template <int CIN>
 __global__ void __launch_bounds__(128) first_conv_k3c32_kernel(int B, int H, int W, const float* __restrict__ x,
                                                                const float* __restrict__ w,
                                                                const float* __restrict__ ws, sn_packed_view dst,
-                                                               int relu) {
+                                                               int relu, int contiguous) {
   constexpr int K = 9 * CIN, COUT = 32;
+  constexpr int ROWB = 3 * COUT * 2 + 16;          // one pixel = 192 B, padded to 208 B: conflict-free 16-B accesses
   __shared__ __align__(16) float sw[K * COUT];
   __shared__ float ss[COUT];
+  __shared__ __align__(16) uint8_t stage[128 * ROWB];
   for (int i = threadIdx.x; i < K * COUT; i += blockDim.x) sw[i] = w[i];
   if (threadIdx.x < COUT) ss[threadIdx.x] = softplus_f(ws[threadIdx.x]);
   __syncthreads();
   const int Ho = H - 2, Wo = W - 2;
   const size_t total = (size_t)B * Ho * Wo;
-  const size_t stride = (size_t)gridDim.x * blockDim.x;
   __nv_bfloat16* out = reinterpret_cast<__nv_bfloat16*>(dst.base);
-  for (size_t i = blockIdx.x * (size_t)blockDim.x + threadIdx.x; i < total; i += stride) {
-    const int xo = (int)(i % Wo);
-    size_t t = i / Wo;
-    const int yo = (int)(t % Ho);
-    const int b = (int)(t / Ho);
+  for (size_t base = (size_t)blockIdx.x * 128; base < total; base += (size_t)gridDim.x * 128) {
+    const size_t i = base + threadIdx.x;
+    const bool live = i < total;
+    int xo = 0, yo = 0, b = 0;
+    if (live) {
+      xo = (int)(i % Wo);
+      size_t t = i / Wo;
+      yo = (int)(t % Ho);
+      b = (int)(t / Ho);
+    }
     float xv[K];
     float r = 0.f;
 #pragma unroll
@@ -238,7 +244,12 @@ __global__ void __launch_bounds__(128) first_conv_k3c32_kernel(int B, int H, int
       }
 #pragma unroll
     for (int k = 0; k < K; ++k) r = fmaf(xv[k], xv[k], r);
-    __nv_bfloat16* o = out + ((((size_t)b * dst.h + yo + dst.y0) * dst.w + xo + dst.x0) * 3) * dst.c + dst.c0;
+    // destination of this thread's pixel: the staging row (contiguous output) or global memory (windowed output)
+    uint8_t* o = contiguous
+                     ? stage + threadIdx.x * ROWB
+                     : reinterpret_cast<uint8_t*>(out + ((((size_t)b * dst.h + yo + dst.y0) * dst.w + xo + dst.x0) * 3) *
+                                                            dst.c + dst.c0);
+    const int plane_b = contiguous ? COUT * 2 : dst.c * 2;
 #pragma unroll
     for (int n8 = 0; n8 < COUT; n8 += 8) {
       float acc[8];
@@ -264,9 +275,23 @@ __global__ void __launch_bounds__(128) first_conv_k3c32_kernel(int B, int H, int
       }
       uint4 hi, lo;
       split8(acc, hi, lo);
-      *reinterpret_cast<uint4*>(o + n8) = hi;
-      *reinterpret_cast<uint4*>(o + dst.c + n8) = lo;
-      *reinterpret_cast<uint4*>(o + 2 * dst.c + n8) = pack8(var);
+      if (live || contiguous) {
+        *reinterpret_cast<uint4*>(o + n8 * 2) = hi;
+        *reinterpret_cast<uint4*>(o + plane_b + n8 * 2) = lo;
+        *reinterpret_cast<uint4*>(o + 2 * plane_b + n8 * 2) = pack8(var);
+      }
+    }
+    if (contiguous) {
+      // 128 pixels x 192 B are one contiguous 24 KB run of the output: copy it out with fully coalesced stores
+      __syncthreads();
+      const size_t remain = total - base;
+      const int chunks = (int)(remain < 128 ? remain : 128) * 12;
+      uint4* g = reinterpret_cast<uint4*>(out + base * 3 * COUT);
+      for (int c = threadIdx.x; c < chunks; c += 128) {
+        const int pix = c / 12, part = c - pix * 12;
+        g[c] = *reinterpret_cast<const uint4*>(stage + pix * ROWB + part * 16);
+      }
+      __syncthreads();
     }
   }
 }
@@ -482,11 +507,15 @@ int sn_first_conv_fwd_packed(int32_t batch, int32_t in_h, int32_t in_w, int32_t 
   const int relu = (flags & SN_TC_RELU) ? 1 : 0;
   if (ksize == 3 && cout == 32 && (cin == 4 || cin == 1)) {
     const size_t pixels = (size_t)batch * Ho * Wo;
-    const int grid = ew_grid(pixels, 128, 8);
+    const int grid = ew_grid(pixels, 128, 6);
+    // the output is one contiguous run when the destination window is the whole buffer
+    const int contiguous = dst->y0 == 0 && dst->x0 == 0 && dst->c0 == 0 && dst->h == Ho && dst->w == Wo && dst->c == cout;
     if (cin == 4)
-      first_conv_k3c32_kernel<4><<<grid, 128, 0, as_stream(st)>>>(batch, in_h, in_w, x, w_mu, w_sigma, *dst, relu);
+      first_conv_k3c32_kernel<4><<<grid, 128, 0, as_stream(st)>>>(batch, in_h, in_w, x, w_mu, w_sigma, *dst, relu,
+                                                                  contiguous);
     else
-      first_conv_k3c32_kernel<1><<<grid, 128, 0, as_stream(st)>>>(batch, in_h, in_w, x, w_mu, w_sigma, *dst, relu);
+      first_conv_k3c32_kernel<1><<<grid, 128, 0, as_stream(st)>>>(batch, in_h, in_w, x, w_mu, w_sigma, *dst, relu,
+                                                                  contiguous);
     return check_launch("first_conv_k3c32");
   }
   const size_t smem = ((size_t)ksize * ksize * cin * cout + cout) * sizeof(float);

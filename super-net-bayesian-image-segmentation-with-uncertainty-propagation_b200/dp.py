@@ -1,0 +1,116 @@
+"""Batch-sharded data parallelism for the moment-propagation path (one process per GPU, torch.distributed).
+
+The reference has no distributed code; this is the B200 scale-out of its two step functions:
+  * inference / noise sweep / FGSM (Brats.py:742,999,1289,582-596): slices are independent -> shard the batch,
+    replicate the weights, NO collective on the data path;
+  * ELBO training (Brats.py:569-580): the NLL is a mean over B*HW (Brats.py:301-302,309) and the regularisers
+    depend on weights only, so with shard sizes n_r the global gradient is sum_r (n_r / N) * grad(loss_r); one
+    all-reduce(sum) of the flat fp32 gradient (7.76 M elements, 31 MB for BraTS) over NCCL/NVLink, bucketed in
+    reverse layer order.  Keras' Adam(clipnorm=1.0) clips PER VARIABLE and is applied after the reduction
+    (Brats.py:566,579).
+Nothing here touches CUDA directly, so the logic is testable with the gloo backend on CPU.
+"""
+from __future__ import annotations
+
+from typing import Iterable, List, Optional, Sequence, Tuple
+
+import torch
+import torch.distributed as dist
+
+Tensor = torch.Tensor
+
+
+def shard_bounds(global_batch: int, world_size: int, rank: int) -> Tuple[int, int]:
+    """[start, stop) of `rank`'s slices: per-GPU batch = ceil(global / world); the last ranks may
+    get fewer (or zero) slices."""
+    if global_batch < 0 or world_size < 1 or not (0 <= rank < world_size):
+        raise ValueError("bad shard arguments")
+    per = -(-global_batch // world_size)
+    start = min(rank * per, global_batch)
+    return start, min(start + per, global_batch)
+
+
+def shard_batch(x: Tensor, world_size: int, rank: int) -> Tensor:
+    a, b = shard_bounds(x.shape[0], world_size, rank)
+    return x[a:b]
+
+
+def allreduce_gradients(params: Sequence[Tensor], local_count: int, global_count: int,
+                        group: Optional[dist.ProcessGroup] = None, bucket_bytes: int = 8 << 20) -> None:
+    """In-place: p.grad <- sum_r (n_r / N) p.grad_r, through flat buckets filled in REVERSE parameter order (the
+    order backward produces them, so early buckets can overlap with the remaining wgrad kernels)."""
+    if not dist.is_available() or not dist.is_initialized() or dist.get_world_size(group) == 1:
+        return
+    if global_count <= 0:
+        raise ValueError("global_count must be positive")
+    scale = float(local_count) / float(global_count)
+    todo = [p for p in reversed(list(params)) if p.grad is not None]
+    bucket: List[Tensor] = []
+    size = 0
+    handles = []
+
+    def flush():
+        nonlocal bucket, size
+        if not bucket:
+            return
+        flat = torch.cat([p.grad.reshape(-1) for p in bucket]).mul_(scale)
+        h = dist.all_reduce(flat, op=dist.ReduceOp.SUM, group=group, async_op=True)
+        handles.append((h, flat, bucket))
+        bucket, size = [], 0
+
+    for p in todo:
+        bucket.append(p)
+        size += p.grad.numel() * p.grad.element_size()
+        if size >= bucket_bytes:
+            flush()
+    flush()
+    for h, flat, ps in handles:
+        h.wait()
+        off = 0
+        for p in ps:
+            n = p.grad.numel()
+            p.grad.copy_(flat[off:off + n].view_as(p.grad))
+            off += n
+
+
+def clip_by_norm_per_variable_(params: Iterable[Tensor], clipnorm: float = 1.0) -> None:
+    """Keras optimizer `clipnorm`: every variable's gradient is rescaled to L2 norm <= clipnorm on its own
+    (Brats.py:566), unlike torch's clip_grad_norm_ which uses the global norm."""
+    for p in params:
+        if p.grad is None:
+            continue
+        n = p.grad.norm()
+        p.grad.mul_(torch.clamp(clipnorm / (n + 1e-12), max=1.0))
+
+
+def make_adam(params: Iterable[Tensor], lr: float = 1e-3) -> torch.optim.Adam:
+    """tf.keras.optimizers.Adam defaults (beta 0.9/0.999, epsilon 1e-7) (Brats.py:566)."""
+    return torch.optim.Adam(list(params), lr=lr, betas=(0.9, 0.999), eps=1e-7)
+
+
+class DataParallelTrainer:
+    """train_on_batch (Brats.py:569-580) over a sharded batch: forward/backward on the local slices, weighted
+    gradient all-reduce, per-variable clipnorm, Adam."""
+
+    def __init__(self, model, lr: float = 1e-3, kl_factor: float = 1e-5, clipnorm: float = 1.0,
+                 group: Optional[dist.ProcessGroup] = None):
+        self.model = model
+        self.kl_factor = kl_factor
+        self.clipnorm = clipnorm
+        self.group = group
+        self.opt = make_adam(model.parameters(), lr)
+
+    def step(self, x_local: Tensor, y_local: Tensor, global_batch: int) -> Tensor:
+        params = [p for p in self.model.parameters() if p.requires_grad]
+        self.opt.zero_grad(set_to_none=True)
+        if x_local.shape[0] > 0:
+            loss = self.model.elbo_loss(x_local, y_local, self.kl_factor)
+            loss.backward()
+        else:                       # an empty shard still takes part in the collective
+            loss = torch.zeros((), device=params[0].device)
+            for p in params:
+                p.grad = torch.zeros_like(p)
+        allreduce_gradients(params, x_local.shape[0], global_batch, self.group)
+        clip_by_norm_per_variable_(params, self.clipnorm)
+        self.opt.step()
+        return loss.detach()

@@ -154,6 +154,20 @@ def test_first_conv_pool_final(S):
     F.first_conv_packed(dev(x), dev(w), dev(ws), F.PackedView(buf), relu=True)
     m, v = F.unpack_moments(buf)
     assert rel(m, m_ref) < 2e-5 and rel(v, v_ref) < VAR_TOL
+    # same conv written into a window of a larger buffer (non-contiguous destination path), and Cin = 1
+    big = F.packed_empty(2, 13, 15, 64, "cuda")
+    F.packed_fill(big, 0.5)
+    F.first_conv_packed(dev(x), dev(w), dev(ws), F.PackedView(big, 2, 1, 32), relu=True)
+    mb, vb = F.unpack_moments(big)
+    assert torch.equal(mb[:, 2:12, 1:13, 32:], m) and torch.equal(vb[:, 2:12, 1:13, 32:], v)
+    assert float(mb[:, :, :, :32].abs().max()) == 0.0 and torch.equal(vb[:, 0], torch.full_like(vb[:, 0], 0.5))
+    x1 = torch.rand(3, 9, 11, 1, generator=g, dtype=torch.float64).float().double()
+    _, _, w1, ws1 = rand_layer(3, 9, 11, 1, 32, 3, seed=10)
+    m1_ref, v1_ref = O.relu(*O.conv_input_conv_form(x1, w1, ws1))
+    b1 = F.packed_empty(3, 7, 9, 32, "cuda")
+    F.first_conv_packed(dev(x1), dev(w1), dev(ws1), F.PackedView(b1), relu=True)
+    m1, v1 = F.unpack_moments(b1)
+    assert rel(m1, m1_ref) < 2e-5 and rel(v1, v1_ref) < VAR_TOL
     # pooling on the packed tensor == oracle pooling of the unpacked (bf16-rounded) values, exactly
     pm_ref, pv_ref = O.maxpooling(m.cpu(), v.cpu())
     pbuf = F.packed_empty(2, 6, 7, 32, "cuda")            # written at offset (1,1) like mypad1's interior
