@@ -179,3 +179,58 @@ class InferenceEngine:
         if return_presoftmax:
             return p.clone(), v.clone(), self.pre_m.clone(), self.pre_v.clone()
         return p.clone(), v.clone()
+
+
+class StreamingPipeline:
+    """Host-facing inference: pinned host batch -> H2D -> forward -> D2H of both maps, software-pipelined.
+
+    `depth` engines (each with its own buffers, CUDA graph and stream) are used round-robin, so the H2D copy of
+    batch i+1 and the D2H copies of batch i-1 overlap the kernels of batch i (B200 has separate copy engines per
+    direction).  This is the e2e path bench.py times; testing()'s loop (Brats.py:1197-1298) maps onto
+    submit()/result()."""
+
+    def __init__(self, model, batch: int, in_h: int, in_w: int, in_c: int, device, depth: int = 2):
+        self.device = torch.device(device)
+        self.engines = [InferenceEngine(model, batch, in_h, in_w, in_c, device, graph=True) for _ in range(depth)]
+        self.streams = [torch.cuda.Stream(device=self.device) for _ in range(depth)]
+        self.done = [torch.cuda.Event() for _ in range(depth)]
+        e0 = self.engines[0]
+        self.p_host = [torch.empty(e0.p.shape, dtype=torch.float32).pin_memory() for _ in range(depth)]
+        self.v_host = [torch.empty(e0.p.shape, dtype=torch.float32).pin_memory() for _ in range(depth)]
+        self._next = 0
+        self._busy = [False] * depth
+        for eng, st in zip(self.engines, self.streams):          # capture each graph on its own stream
+            st.wait_stream(torch.cuda.current_stream(self.device))
+            with torch.cuda.stream(st):
+                eng.forward_resident()
+        torch.cuda.synchronize(self.device)
+
+    @property
+    def n_launches(self) -> int:
+        return self.engines[0].n_launches
+
+    def submit(self, x_host: Tensor) -> int:
+        """Enqueue one batch (a pinned host tensor); returns the slot to pass to result()."""
+        slot = self._next
+        self._next = (slot + 1) % len(self.engines)
+        if self._busy[slot]:
+            self.done[slot].synchronize()        # the slot's previous outputs must have landed before reuse
+        eng, st = self.engines[slot], self.streams[slot]
+        with torch.cuda.stream(st):
+            eng.x_in.copy_(x_host, non_blocking=True)
+            p, v = eng.forward_resident()
+            self.p_host[slot].copy_(p, non_blocking=True)
+            self.v_host[slot].copy_(v, non_blocking=True)
+            self.done[slot].record(st)
+        self._busy[slot] = True
+        return slot
+
+    def result(self, slot: int) -> Tuple[Tensor, Tensor]:
+        self.done[slot].synchronize()
+        return self.p_host[slot], self.v_host[slot]
+
+    def join(self) -> None:
+        """Make the current stream wait for everything submitted so far."""
+        cur = torch.cuda.current_stream(self.device)
+        for st in self.streams:
+            cur.wait_stream(st)

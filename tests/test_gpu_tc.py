@@ -247,3 +247,25 @@ def test_fast_matches_fp32_mode_at_full_scale_input(S):
         _, _, mf, sf = fast(x, return_presoftmax=True)
         _, _, mf2, sf2 = slow(x, return_presoftmax=True)
     assert rel(mf.reshape(mf2.shape), mf2) < 1e-3 and rel(sf.reshape(sf2.shape), sf2) < 1e-2
+
+
+def test_streaming_pipeline_matches_engine(S):
+    """The host-facing e2e path (pinned host in, pinned host out, two engines round-robin) returns what the model
+    call returns, batch after batch."""
+    from supernet_b200.engine import StreamingPipeline
+    w32 = O.make_weights("hippocampus", 32, 3, 1)
+    model = S.Density_prop_with_pad_UNET(32, 3, variant="hippocampus", mode="fast").load_weight_dict(w32, device="cuda")
+    pipe = StreamingPipeline(model, 4, 64, 64, 1, "cuda", depth=2)
+    xs = [O.make_input("hippocampus", 4, seed=100 + i).pin_memory() for i in range(5)]
+    slots, outs = [], []
+    for i, x in enumerate(xs):
+        slots.append(pipe.submit(x))
+        if i >= 1:                      # consume with a lag of one batch, like a real consumer would
+            p, v = pipe.result(slots[i - 1])
+            outs.append((p.clone(), v.clone()))
+    p, v = pipe.result(slots[-1])
+    outs.append((p.clone(), v.clone()))
+    for x, (p, v) in zip(xs, outs):
+        with torch.no_grad():
+            p_ref, v_ref = model(x.cuda())
+        assert torch.equal(p, p_ref.cpu()) and torch.equal(v, v_ref.cpu())
