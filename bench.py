@@ -242,7 +242,7 @@ def main():
 
     if args.mode == "fast":
         from supernet_b200.engine import InferenceEngine, StreamingPipeline
-        eng = InferenceEngine(model, B, IN_HW, IN_HW, IN_CH, dev, graph=True)
+        eng = InferenceEngine(model, B, IN_HW, IN_HW, IN_CH, dev, graph=True, keep_presoftmax=False)
         eng.x_in.copy_(x_host, non_blocking=True)
         step = eng.forward_resident
         launches_per_step = eng.n_launches

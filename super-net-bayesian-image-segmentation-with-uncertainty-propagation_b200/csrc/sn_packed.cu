@@ -4,6 +4,8 @@
 // pooling and the final 1x1 convolution fused with the softmax-Jacobian variance.
 #include "sn_common.cuh"
 
+#include <mutex>
+
 namespace sn {
 
 __device__ __forceinline__ float blo(uint32_t v) { return __uint_as_float(v << 16); }
@@ -197,97 +199,117 @@ __global__ void __launch_bounds__(256) first_conv_packed_kernel(int B, int H, in
 }
 
 // Specialisation for the shapes the two networks use (k = 3, 32 output channels, Cin = 4 or 1): one thread owns
-// one output pixel and all 32 channels.  The 9*CIN input values sit in registers, the weights are read from shared
-// memory with warp-uniform (broadcast) 16-byte loads -- one LDS.128 per four FMAs -- and the pixel's
-// 3 x 64 B (hi, lo, var) go out as twelve 16-byte stores.
+// PPT = 2 output pixels and all 32 channels.  The 9*CIN input values of each pixel sit in registers; the weights
+// are read from shared memory with warp-uniform (broadcast) 16-byte loads, one LDS.128 per 4*PPT FMAs, which is
+// what makes the kernel FMA-bound rather than LDS-bound.  When the destination is a whole buffer the block's
+// 256 pixels x 192 B are one contiguous 48 KB run: they are staged in shared memory and written with fully
+// coalesced 16-byte stores.
+constexpr int FC_PPT = 2, FC_THREADS = 128, FC_PIX = FC_PPT * FC_THREADS;
+
 template <int CIN>
-__global__ void __launch_bounds__(128) first_conv_k3c32_kernel(int B, int H, int W, const float* __restrict__ x,
-                                                               const float* __restrict__ w,
-                                                               const float* __restrict__ ws, sn_packed_view dst,
-                                                               int relu, int contiguous) {
+__global__ void __launch_bounds__(FC_THREADS) first_conv_k3c32_kernel(int B, int H, int W,
+                                                                      const float* __restrict__ x,
+                                                                      const float* __restrict__ w,
+                                                                      const float* __restrict__ ws,
+                                                                      sn_packed_view dst, int relu, int contiguous) {
   constexpr int K = 9 * CIN, COUT = 32;
   constexpr int ROWB = 3 * COUT * 2 + 16;          // one pixel = 192 B, padded to 208 B: conflict-free 16-B accesses
-  __shared__ __align__(16) float sw[K * COUT];
-  __shared__ float ss[COUT];
-  __shared__ __align__(16) uint8_t stage[128 * ROWB];
+  extern __shared__ __align__(16) uint8_t fc_smem[];
+  float* sw = reinterpret_cast<float*>(fc_smem);               // [K][COUT]
+  float* ss = sw + K * COUT;                                   // [COUT]
+  uint8_t* stage = fc_smem + (K * COUT + COUT) * sizeof(float);  // [FC_PIX][ROWB]
   for (int i = threadIdx.x; i < K * COUT; i += blockDim.x) sw[i] = w[i];
   if (threadIdx.x < COUT) ss[threadIdx.x] = softplus_f(ws[threadIdx.x]);
   __syncthreads();
   const int Ho = H - 2, Wo = W - 2;
   const size_t total = (size_t)B * Ho * Wo;
   __nv_bfloat16* out = reinterpret_cast<__nv_bfloat16*>(dst.base);
-  for (size_t base = (size_t)blockIdx.x * 128; base < total; base += (size_t)gridDim.x * 128) {
-    const size_t i = base + threadIdx.x;
-    const bool live = i < total;
-    int xo = 0, yo = 0, b = 0;
-    if (live) {
-      xo = (int)(i % Wo);
-      size_t t = i / Wo;
-      yo = (int)(t % Ho);
-      b = (int)(t / Ho);
-    }
-    float xv[K];
-    float r = 0.f;
+  for (size_t base = (size_t)blockIdx.x * FC_PIX; base < total; base += (size_t)gridDim.x * FC_PIX) {
+    float xv[FC_PPT][K];
+    float r[FC_PPT];
+    uint8_t* o[FC_PPT];
+    bool live[FC_PPT];
 #pragma unroll
-    for (int kh = 0; kh < 3; ++kh)
-#pragma unroll
-      for (int kw = 0; kw < 3; ++kw) {
-        const float* px = x + (((size_t)b * H + yo + kh) * W + xo + kw) * CIN;
-        if constexpr (CIN == 4) {
-          const float4 v = __ldg(reinterpret_cast<const float4*>(px));
-          xv[(kh * 3 + kw) * 4 + 0] = v.x; xv[(kh * 3 + kw) * 4 + 1] = v.y;
-          xv[(kh * 3 + kw) * 4 + 2] = v.z; xv[(kh * 3 + kw) * 4 + 3] = v.w;
-        } else {
-#pragma unroll
-          for (int c = 0; c < CIN; ++c) xv[(kh * 3 + kw) * CIN + c] = __ldg(px + c);
-        }
+    for (int q = 0; q < FC_PPT; ++q) {
+      const int lp = threadIdx.x + q * FC_THREADS;             // pixel slot inside the block's run
+      const size_t i = base + lp;
+      live[q] = i < total;
+      int xo = 0, yo = 0, b = 0;
+      if (live[q]) {
+        xo = (int)(i % Wo);
+        size_t t = i / Wo;
+        yo = (int)(t % Ho);
+        b = (int)(t / Ho);
       }
 #pragma unroll
-    for (int k = 0; k < K; ++k) r = fmaf(xv[k], xv[k], r);
-    // destination of this thread's pixel: the staging row (contiguous output) or global memory (windowed output)
-    uint8_t* o = contiguous
-                     ? stage + threadIdx.x * ROWB
-                     : reinterpret_cast<uint8_t*>(out + ((((size_t)b * dst.h + yo + dst.y0) * dst.w + xo + dst.x0) * 3) *
-                                                            dst.c + dst.c0);
+      for (int kh = 0; kh < 3; ++kh)
+#pragma unroll
+        for (int kw = 0; kw < 3; ++kw) {
+          const float* px = x + (((size_t)b * H + yo + kh) * W + xo + kw) * CIN;
+          if constexpr (CIN == 4) {
+            const float4 v = __ldg(reinterpret_cast<const float4*>(px));
+            xv[q][(kh * 3 + kw) * 4 + 0] = v.x; xv[q][(kh * 3 + kw) * 4 + 1] = v.y;
+            xv[q][(kh * 3 + kw) * 4 + 2] = v.z; xv[q][(kh * 3 + kw) * 4 + 3] = v.w;
+          } else {
+#pragma unroll
+            for (int c = 0; c < CIN; ++c) xv[q][(kh * 3 + kw) * CIN + c] = __ldg(px + c);
+          }
+        }
+      float rr = 0.f;
+#pragma unroll
+      for (int k = 0; k < K; ++k) rr = fmaf(xv[q][k], xv[q][k], rr);
+      r[q] = rr;
+      o[q] = contiguous ? stage + lp * ROWB
+                        : reinterpret_cast<uint8_t*>(
+                              out + ((((size_t)b * dst.h + yo + dst.y0) * dst.w + xo + dst.x0) * 3) * dst.c + dst.c0);
+    }
     const int plane_b = contiguous ? COUT * 2 : dst.c * 2;
 #pragma unroll
     for (int n8 = 0; n8 < COUT; n8 += 8) {
-      float acc[8];
+      float acc[FC_PPT][8];
 #pragma unroll
-      for (int j = 0; j < 8; ++j) acc[j] = 0.f;
+      for (int q = 0; q < FC_PPT; ++q)
+#pragma unroll
+        for (int j = 0; j < 8; ++j) acc[q][j] = 0.f;
 #pragma unroll
       for (int k = 0; k < K; ++k) {
         const float4 w0 = *reinterpret_cast<const float4*>(sw + k * COUT + n8);
         const float4 w1 = *reinterpret_cast<const float4*>(sw + k * COUT + n8 + 4);
-        acc[0] = fmaf(xv[k], w0.x, acc[0]); acc[1] = fmaf(xv[k], w0.y, acc[1]);
-        acc[2] = fmaf(xv[k], w0.z, acc[2]); acc[3] = fmaf(xv[k], w0.w, acc[3]);
-        acc[4] = fmaf(xv[k], w1.x, acc[4]); acc[5] = fmaf(xv[k], w1.y, acc[5]);
-        acc[6] = fmaf(xv[k], w1.z, acc[6]); acc[7] = fmaf(xv[k], w1.w, acc[7]);
-      }
-      float var[8];
 #pragma unroll
-      for (int j = 0; j < 8; ++j) {
-        var[j] = ss[n8 + j] * r;
-        if (relu) {
-          var[j] = acc[j] > 0.f ? var[j] : 0.f;
-          acc[j] = fmaxf(acc[j], 0.f);
+        for (int q = 0; q < FC_PPT; ++q) {
+          const float xk = xv[q][k];
+          acc[q][0] = fmaf(xk, w0.x, acc[q][0]); acc[q][1] = fmaf(xk, w0.y, acc[q][1]);
+          acc[q][2] = fmaf(xk, w0.z, acc[q][2]); acc[q][3] = fmaf(xk, w0.w, acc[q][3]);
+          acc[q][4] = fmaf(xk, w1.x, acc[q][4]); acc[q][5] = fmaf(xk, w1.y, acc[q][5]);
+          acc[q][6] = fmaf(xk, w1.z, acc[q][6]); acc[q][7] = fmaf(xk, w1.w, acc[q][7]);
         }
       }
-      uint4 hi, lo;
-      split8(acc, hi, lo);
-      if (live || contiguous) {
-        *reinterpret_cast<uint4*>(o + n8 * 2) = hi;
-        *reinterpret_cast<uint4*>(o + plane_b + n8 * 2) = lo;
-        *reinterpret_cast<uint4*>(o + 2 * plane_b + n8 * 2) = pack8(var);
+#pragma unroll
+      for (int q = 0; q < FC_PPT; ++q) {
+        float var[8];
+#pragma unroll
+        for (int j = 0; j < 8; ++j) {
+          var[j] = ss[n8 + j] * r[q];
+          if (relu) {
+            var[j] = acc[q][j] > 0.f ? var[j] : 0.f;
+            acc[q][j] = fmaxf(acc[q][j], 0.f);
+          }
+        }
+        uint4 hi, lo;
+        split8(acc[q], hi, lo);
+        if (live[q] || contiguous) {
+          *reinterpret_cast<uint4*>(o[q] + n8 * 2) = hi;
+          *reinterpret_cast<uint4*>(o[q] + plane_b + n8 * 2) = lo;
+          *reinterpret_cast<uint4*>(o[q] + 2 * plane_b + n8 * 2) = pack8(var);
+        }
       }
     }
     if (contiguous) {
-      // 128 pixels x 192 B are one contiguous 24 KB run of the output: copy it out with fully coalesced stores
       __syncthreads();
       const size_t remain = total - base;
-      const int chunks = (int)(remain < 128 ? remain : 128) * 12;
+      const int chunks = (int)(remain < FC_PIX ? remain : FC_PIX) * 12;
       uint4* g = reinterpret_cast<uint4*>(out + base * 3 * COUT);
-      for (int c = threadIdx.x; c < chunks; c += 128) {
+      for (int c = threadIdx.x; c < chunks; c += FC_THREADS) {
         const int pix = c / 12, part = c - pix * 12;
         g[c] = *reinterpret_cast<const uint4*>(stage + pix * ROWB + part * 16);
       }
@@ -360,11 +382,13 @@ __global__ void __launch_bounds__(128) final_conv_softmax_kernel(sn_packed_view 
                                                                  float* __restrict__ p_out,
                                                                  float* __restrict__ v_out,
                                                                  float* __restrict__ pre_mu,
-                                                                 float* __restrict__ pre_var) {
-  extern __shared__ float sm[];            // W [cin][C], W^2 [cin][C], s [C]
+                                                                 float* __restrict__ pre_var, int contiguous) {
+  extern __shared__ __align__(16) float sm[];   // W [cin][C], W^2 [cin][C], s [C] (padded to 4), then the pixel stage
   float* sw = sm;
   float* sw2 = sm + cin * C;
   float* ss = sm + 2 * cin * C;
+  const int rowb = 6 * cin + 16;                // one pixel's (hi|lo|var) + 16 B pad: conflict-free 16-B row reads
+  uint8_t* stage = reinterpret_cast<uint8_t*>(sm + ((2 * cin * C + C + 3) & ~3));
   for (int i = threadIdx.x; i < cin * C; i += blockDim.x) {
     const float v = w[i];
     sw[i] = v;
@@ -373,61 +397,98 @@ __global__ void __launch_bounds__(128) final_conv_softmax_kernel(sn_packed_view 
   for (int i = threadIdx.x; i < C; i += blockDim.x) ss[i] = softplus_f(ws[i]);
   __syncthreads();
   const size_t total = (size_t)B * H * W;
-  const size_t stride = (size_t)gridDim.x * blockDim.x;
   const __nv_bfloat16* in = reinterpret_cast<const __nv_bfloat16*>(src.base);
-  for (size_t i = blockIdx.x * (size_t)blockDim.x + threadIdx.x; i < total; i += stride) {
-    const int xx = (int)(i % W);
-    size_t t = i / W;
-    const int y = (int)(t % H);
-    const int b = (int)(t / H);
-    const __nv_bfloat16* s = in + ((((size_t)b * src.h + y + src.y0) * src.w + xx + src.x0) * 3) * src.c + src.c0;
-    float m[C], v[C];
+  for (size_t base = (size_t)blockIdx.x * 128; base < total; base += (size_t)gridDim.x * 128) {
+    const size_t i = base + threadIdx.x;
+    const bool live = i < total;
+    const uint8_t* s8;
+    int plane_b;
+    if (contiguous) {
+      // the block's 128 pixels are one contiguous run of the source: fully coalesced 16-byte loads into smem
+      const int cpp = (6 * cin) / 16;           // 16-byte chunks per pixel
+      const size_t remain = total - base;
+      const int chunks = (int)(remain < 128 ? remain : 128) * cpp;
+      const uint4* g = reinterpret_cast<const uint4*>(in + base * 3 * cin);
+      for (int c = threadIdx.x; c < chunks; c += 128) {
+        const int pix = c / cpp, part = c - pix * cpp;
+        *reinterpret_cast<uint4*>(stage + pix * rowb + part * 16) = __ldg(g + c);
+      }
+      __syncthreads();
+      s8 = stage + threadIdx.x * rowb;
+      plane_b = cin * 2;
+    } else {
+      int xx = 0, y = 0, b = 0;
+      if (live) {
+        xx = (int)(i % W);
+        size_t t = i / W;
+        y = (int)(t % H);
+        b = (int)(t / H);
+      }
+      s8 = reinterpret_cast<const uint8_t*>(in + ((((size_t)b * src.h + y + src.y0) * src.w + xx + src.x0) * 3) * src.c +
+                                            src.c0);
+      plane_b = src.c * 2;
+    }
+    if (live) {
+      float m[C], v[C];
 #pragma unroll
-    for (int j = 0; j < C; ++j) m[j] = v[j] = 0.f;
-    float r = 0.f;
-    for (int c8 = 0; c8 < cin; c8 += 8) {
-      float h[8], l[8], vv[8];
-      unpack8(*reinterpret_cast<const uint4*>(s + c8), h);
-      unpack8(*reinterpret_cast<const uint4*>(s + src.c + c8), l);
-      unpack8(*reinterpret_cast<const uint4*>(s + 2 * src.c + c8), vv);
+      for (int j = 0; j < C; ++j) m[j] = v[j] = 0.f;
+      float r = 0.f;
+      for (int c8 = 0; c8 < cin; c8 += 8) {
+        float h[8], l[8], vv[8];
+        unpack8(*reinterpret_cast<const uint4*>(s8 + c8 * 2), h);
+        unpack8(*reinterpret_cast<const uint4*>(s8 + plane_b + c8 * 2), l);
+        unpack8(*reinterpret_cast<const uint4*>(s8 + 2 * plane_b + c8 * 2), vv);
 #pragma unroll
-      for (int e = 0; e < 8; ++e) {
-        const float mu = h[e] + l[e];
-        r += fmaf(mu, mu, vv[e]);
+        for (int e = 0; e < 8; ++e) {
+          const float mu = h[e] + l[e];
+          r += fmaf(mu, mu, vv[e]);
+#pragma unroll
+          for (int j = 0; j < C; ++j) {
+            m[j] = fmaf(mu, sw[(c8 + e) * C + j], m[j]);
+            v[j] = fmaf(vv[e], sw2[(c8 + e) * C + j], v[j]);
+          }
+        }
+      }
+      float mx = -INFINITY;
+#pragma unroll
+      for (int j = 0; j < C; ++j) {
+        v[j] = fmaxf(fmaf(ss[j], r, v[j]), 0.f);
+        mx = fmaxf(mx, m[j]);
+      }
+      float p[C], sum = 0.f;
+#pragma unroll
+      for (int j = 0; j < C; ++j) { p[j] = expf(m[j] - mx); sum += p[j]; }
+      const float inv = 1.f / sum;
+#pragma unroll
+      for (int j = 0; j < C; ++j) p[j] *= inv;
+      float vo[C];
+#pragma unroll
+      for (int a = 0; a < C; ++a) {
+        float acc = 0.f;   // sum_j (p_a (delta_aj - p_j))^2 v_j : non-negative terms only
 #pragma unroll
         for (int j = 0; j < C; ++j) {
-          m[j] = fmaf(mu, sw[(c8 + e) * C + j], m[j]);
-          v[j] = fmaf(vv[e], sw2[(c8 + e) * C + j], v[j]);
+          const float J = p[a] * ((a == j ? 1.f : 0.f) - p[j]);
+          acc = fmaf(J * J, v[j], acc);
+        }
+        vo[a] = acc;
+      }
+      if constexpr (C == 4) {
+        reinterpret_cast<float4*>(p_out)[i] = make_float4(p[0], p[1], p[2], p[3]);
+        reinterpret_cast<float4*>(v_out)[i] = make_float4(vo[0], vo[1], vo[2], vo[3]);
+        if (pre_mu) {
+          reinterpret_cast<float4*>(pre_mu)[i] = make_float4(m[0], m[1], m[2], m[3]);
+          reinterpret_cast<float4*>(pre_var)[i] = make_float4(v[0], v[1], v[2], v[3]);
+        }
+      } else {
+#pragma unroll
+        for (int a = 0; a < C; ++a) { p_out[i * C + a] = p[a]; v_out[i * C + a] = vo[a]; }
+        if (pre_mu) {
+#pragma unroll
+          for (int j = 0; j < C; ++j) { pre_mu[i * C + j] = m[j]; pre_var[i * C + j] = v[j]; }
         }
       }
     }
-    float mx = -INFINITY;
-#pragma unroll
-    for (int j = 0; j < C; ++j) {
-      v[j] = fmaxf(fmaf(ss[j], r, v[j]), 0.f);
-      mx = fmaxf(mx, m[j]);
-    }
-    float p[C], sum = 0.f;
-#pragma unroll
-    for (int j = 0; j < C; ++j) { p[j] = expf(m[j] - mx); sum += p[j]; }
-    const float inv = 1.f / sum;
-#pragma unroll
-    for (int j = 0; j < C; ++j) p[j] *= inv;
-#pragma unroll
-    for (int a = 0; a < C; ++a) {
-      float acc = 0.f;   // sum_j (p_a (delta_aj - p_j))^2 v_j : non-negative terms only
-#pragma unroll
-      for (int j = 0; j < C; ++j) {
-        const float J = p[a] * ((a == j ? 1.f : 0.f) - p[j]);
-        acc = fmaf(J * J, v[j], acc);
-      }
-      p_out[i * C + a] = p[a];
-      v_out[i * C + a] = acc;
-    }
-    if (pre_mu) {
-#pragma unroll
-      for (int j = 0; j < C; ++j) { pre_mu[i * C + j] = m[j]; pre_var[i * C + j] = v[j]; }
-    }
+    if (contiguous) __syncthreads();
   }
 }
 
@@ -507,15 +568,21 @@ int sn_first_conv_fwd_packed(int32_t batch, int32_t in_h, int32_t in_w, int32_t 
   const int relu = (flags & SN_TC_RELU) ? 1 : 0;
   if (ksize == 3 && cout == 32 && (cin == 4 || cin == 1)) {
     const size_t pixels = (size_t)batch * Ho * Wo;
-    const int grid = ew_grid(pixels, 128, 6);
+    const int fc_smem_bytes = (9 * cin * 32 + 32) * (int)sizeof(float) + FC_PIX * (3 * 32 * 2 + 16);
+    static std::once_flag fc_once;
+    std::call_once(fc_once, [] {
+      cudaFuncSetAttribute(first_conv_k3c32_kernel<4>, cudaFuncAttributeMaxDynamicSharedMemorySize, 60 * 1024);
+      cudaFuncSetAttribute(first_conv_k3c32_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, 60 * 1024);
+    });
+    const int grid = ew_grid(pixels, FC_PIX, 3);
     // the output is one contiguous run when the destination window is the whole buffer
     const int contiguous = dst->y0 == 0 && dst->x0 == 0 && dst->c0 == 0 && dst->h == Ho && dst->w == Wo && dst->c == cout;
     if (cin == 4)
-      first_conv_k3c32_kernel<4><<<grid, 128, 0, as_stream(st)>>>(batch, in_h, in_w, x, w_mu, w_sigma, *dst, relu,
-                                                                  contiguous);
+      first_conv_k3c32_kernel<4><<<grid, FC_THREADS, fc_smem_bytes, as_stream(st)>>>(batch, in_h, in_w, x, w_mu,
+                                                                                      w_sigma, *dst, relu, contiguous);
     else
-      first_conv_k3c32_kernel<1><<<grid, 128, 0, as_stream(st)>>>(batch, in_h, in_w, x, w_mu, w_sigma, *dst, relu,
-                                                                  contiguous);
+      first_conv_k3c32_kernel<1><<<grid, FC_THREADS, fc_smem_bytes, as_stream(st)>>>(batch, in_h, in_w, x, w_mu,
+                                                                                      w_sigma, *dst, relu, contiguous);
     return check_launch("first_conv_k3c32");
   }
   const size_t smem = ((size_t)ksize * ksize * cin * cout + cout) * sizeof(float);
@@ -548,13 +615,20 @@ int sn_final_conv_softmax_packed(const sn_packed_view* src, int32_t batch, int32
   int rc = check_pview(src, batch, in_h, in_w, cin, "final_conv src");
   if (rc) return rc;
   const size_t total = (size_t)batch * in_h * in_w;
-  const size_t smem = ((size_t)2 * cin * n_labels + n_labels) * sizeof(float);
-  const int grid = ew_grid(total, 128, 8);
+  SN_REQUIRE(aligned16(p_out) && aligned16(var_out) && (!presoftmax_mu || (aligned16(presoftmax_mu) &&
+                                                                            aligned16(presoftmax_var))),
+             SN_ERR_MISALIGNED, "final_conv: outputs must be 16-byte aligned");
+  const int contiguous = src->y0 == 0 && src->x0 == 0 && src->c0 == 0 && src->h == in_h && src->w == in_w &&
+                         src->c == cin;
+  const size_t smem = (((size_t)2 * cin * n_labels + n_labels + 3) & ~(size_t)3) * sizeof(float) +
+                      (contiguous ? (size_t)128 * (6 * cin + 16) : 0);
+  SN_REQUIRE(smem <= 48 * 1024, SN_ERR_UNSUPPORTED, "final_conv: cin %d too large", cin);
+  const int grid = ew_grid((total + 127) / 128 * 128, 128, 6);
 #define SN_FINAL(CC)                                                                                           \
   case CC:                                                                                                     \
     final_conv_softmax_kernel<CC><<<grid, 128, smem, as_stream(st)>>>(*src, batch, in_h, in_w, cin, w_mu, w_sigma, \
                                                                        p_out, var_out, presoftmax_mu,          \
-                                                                       presoftmax_var);                        \
+                                                                       presoftmax_var, contiguous);            \
     break;
   switch (n_labels) {
     SN_FINAL(1) SN_FINAL(2) SN_FINAL(3) SN_FINAL(4) SN_FINAL(5) SN_FINAL(6) SN_FINAL(7) SN_FINAL(8)

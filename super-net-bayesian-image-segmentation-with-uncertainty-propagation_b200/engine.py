@@ -24,8 +24,10 @@ Tensor = torch.Tensor
 
 
 class InferenceEngine:
-    def __init__(self, model, batch: int, in_h: int, in_w: int, in_c: int, device, graph: bool = True):
+    def __init__(self, model, batch: int, in_h: int, in_w: int, in_c: int, device, graph: bool = True,
+                 keep_presoftmax: bool = True):
         self.model = model
+        self.keep_presoftmax = keep_presoftmax
         self.shape = (batch, in_h, in_w, in_c)
         self.device = torch.device(device)
         self.use_graph = graph
@@ -143,8 +145,9 @@ class InferenceEngine:
         wf, wsf = m.conv_final.weights()
         last, lc = cur, c
         self.step_names.append("conv_final")
+        pre = (self.pre_m, self.pre_v) if self.keep_presoftmax else (None, None)
         steps.append(lambda: F.final_conv_softmax_packed(PackedView(last), B, h, w, lc, wf, wsf, self.p, self.v,
-                                                         self.pre_m, self.pre_v))
+                                                         pre[0], pre[1]))
         self.n_launches = len(steps)
 
     # ------------------------------------------------------------------------------------------------
@@ -177,6 +180,8 @@ class InferenceEngine:
         self.x_in.copy_(x, non_blocking=True)
         p, v = self.forward_resident()
         if return_presoftmax:
+            if not self.keep_presoftmax:
+                raise RuntimeError("engine was built with keep_presoftmax=False")
             return p.clone(), v.clone(), self.pre_m.clone(), self.pre_v.clone()
         return p.clone(), v.clone()
 
@@ -191,7 +196,8 @@ class StreamingPipeline:
 
     def __init__(self, model, batch: int, in_h: int, in_w: int, in_c: int, device, depth: int = 2):
         self.device = torch.device(device)
-        self.engines = [InferenceEngine(model, batch, in_h, in_w, in_c, device, graph=True) for _ in range(depth)]
+        self.engines = [InferenceEngine(model, batch, in_h, in_w, in_c, device, graph=True, keep_presoftmax=False)
+                        for _ in range(depth)]
         self.streams = [torch.cuda.Stream(device=self.device) for _ in range(depth)]
         self.done = [torch.cuda.Event() for _ in range(depth)]
         e0 = self.engines[0]
