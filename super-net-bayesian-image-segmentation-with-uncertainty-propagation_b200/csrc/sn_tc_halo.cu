@@ -14,12 +14,19 @@
 //     r[j] = sum_taps q[j + kh*R + kw] from a 1 KB smem array;
 //   * two TMEM accumulator stages: the epilogue of tile i overlaps the TMA/UMMA main loop of tile i+1.
 // Warp roles (576 threads): warp 0 TMA producer, warp 1 UMMA issuer (+TMEM alloc), warps 2-9 q reduction over
-// every A stage (thread = halo pixel), warps 10-25 epilogue: two SETS of eight warps, set s owning the tiles (and
-// the TMEM accumulator stage) of parity s; inside a set two warps per TMEM lane quarter, each taking half of the
-// tile's columns
+// every A stage (thread = halo pixel), warps 10-17 epilogue: two warps per TMEM lane quarter, each taking half of
+// the tile's columns
 // (q arrives through a double-buffered smem array guarded by mbarriers).  Profiling the first version (4
 // epilogue warps, one per SM sub-partition) showed the epilogue, a long dependent instruction chain per pixel
-// row, as the critical path of the 32/64-channel layers; hence the second set of warps.  Same math and data layout as sn_tc_conv.cu
+// row, as the critical path of the 32/64-channel layers; hence the second set of warps.
+//
+// What bounds it now (measured, round 1): shared-memory bandwidth.  A per-role clock64 trace of conv1 gives a tile
+// period of ~3650 cycles for 54 UMMAs; every UMMA streams its 4 KB A operand (+1-4 KB of B) from smem, the TMA fill
+// writes 40 KB and the q reduction re-reads 40 KB per tile: ~380 KB per tile = 104 B/clk of the SM's 128 B/clk.  More
+// epilogue warps, 4 accumulator stages and two alternating issuer warps (all tried, all parity-green) left the
+// period unchanged, which is what a bandwidth bound looks like; they were dropped again.  The levers that remain are
+// the ones that remove smem bytes: q computed by the producing layer's epilogue, and cta_group::2 UMMAs that halve
+// the B-operand traffic per SM for the NT = 128 layers.  Same math and data layout as sn_tc_conv.cu
 // (Brats.py:118-137 incl. ReLU :233-238, pad :159-163, concat :247-261, unpool+2x2 conv :178-203,414-415).
 #include "sn_common.cuh"
 #include "sn_sm100.cuh"
@@ -31,7 +38,7 @@ namespace sn {
 
 constexpr int HL_BM = 128;
 constexpr int HL_KC = 32;
-constexpr int HL_THREADS = 832;       // 26 warps: TMA, UMMA, 8 x q reduction, 2 sets x 8 epilogue
+constexpr int HL_THREADS = 576;       // 18 warps: TMA, UMMA, 8 x q reduction, 8 x epilogue
 constexpr int HL_MAX_BSLOTS = 36;
 constexpr int HL_MAX_ASTAGES = 4;
 constexpr int HL_SMEM = 232448;        // 227 KB: always requested so exactly one CTA owns an SM (and its TMEM)
@@ -333,13 +340,9 @@ __global__ void __launch_bounds__(HL_THREADS, 1) conv_moments_halo_kernel(const 
         if (lane == 0) ptx::mbar_arrive(q_full(qs));
       }
     } else {
-      // ===================== epilogue (warps 10-25, two sets) =====================
-      // Knob experiments on B200 showed two ~equal critical paths per tile for the 32-channel layers: UMMA issue and
-      // this role's per-warp dependent chain (barrier waits, TMEM loads, convert, stores).  Two sets working on
-      // alternate tiles halve the second one.
-      const int eset = (warp - 10) >> 3;
+      // ===================== epilogue (warps 10-17) =====================
       const int q = warp & 3;                   // TMEM lane quarter this warp may access
-      const int half = ((warp - 10) >> 2) & 1;  // which half of the tile's NT columns this warp converts
+      const int half = (warp - 10) >> 2;        // which half of the tile's NT columns this warp converts
       constexpr int NH = NT / 2;
       const int row = q * 32 + lane;            // GEMM row == TMEM lane == halo pixel index
       const int x = row % p.R;
@@ -349,8 +352,7 @@ __global__ void __launch_bounds__(HL_THREADS, 1) conv_moments_halo_kernel(const 
       TileIt it;
       it.init(blockIdx.x, gridDim.x, p);
       for (int tile = blockIdx.x, titer = 0; tile < p.total_tiles; tile += gridDim.x, ++titer, it.next(p)) {
-        if ((titer & 1) != eset) continue;       // the other set's tile
-        const int as = eset;                      // == titer & 1: this set always drains the same accumulator stage
+        const int as = titer & 1;
         const uint32_t par = ((uint32_t)titer >> 1) & 1u;
         ptx::mbar_wait(q_full(as), par);
         const float* myq = qbuf + as * 256;
