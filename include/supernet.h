@@ -211,6 +211,66 @@ int sn_final_conv_softmax_packed(const sn_packed_view* src, int32_t batch, int32
                                  int32_t n_labels, const float* w_mu, const float* w_sigma, float* p_out,
                                  float* var_out, float* presoftmax_mu, float* presoftmax_var, sn_stream_t st);
 
+/* ------------------------------------------------------------------------------------------------
+ * FAST mode backward: the input-gradient chain tf.GradientTape derives for create_adversarial_pattern
+ * (Brats.py:582-596) and, layer by layer, for train_on_batch (Brats.py:569-580); formulas in SURVEY.md A.3.
+ * A gradient tensor uses the packed layout of the tensor it belongs to: planes g_mean_hi, g_mean_lo
+ * (g_mean = hi + lo) and g_variance, bf16.  Every kernel recomputes gates / arg-max routing from the SAVED
+ * forward activations (the packed buffers the forward wrote), so no masks or indices are stored.
+ * ------------------------------------------------------------------------------------------------ */
+
+/* Once per weight update: HWIO fp32 w_mu -> the data-gradient operands [3][taps][cin][K] bf16 (W_hi, W_lo, bf16(W^2)):
+ * regular conv: taps = k*k, K = cout, tap (kh',kw') holds W[k-1-kh', k-1-kw', ci, n] (the flipped, transposed filter
+ * of the full correlation g (*)^T W); upconv != 0 (ksize == 2): taps = 1, K = 4*cout ordered (parity 2a+b, n),
+ * holding W[1-a, 1-b, ci, n] -- the adjoint of the four parity GEMMs of sn_conv_moments_fwd_tc(SN_TC_UPCONV).
+ * Same byte size as sn_prepared_weight_bytes(). */
+int sn_prepare_weights_bwd(const float* w_mu, int32_t ksize, int32_t cin, int32_t cout, int32_t upconv,
+                           void* wt_packed, sn_stream_t st);
+
+/* Data gradient of sn_conv_moments_fwd_tc on the tensor cores (same persistent halo kernel, gradient as the A operand):
+ *   g_mu_in = g_mu_out (*)^T W + 2 mu_in . box^T(t),  g_var_in = g_var_out (*)^T W^2 + box^T(t),  t = sum_n g_var_out s_n,
+ * followed, per forward source i with gate[i] != 0, by the ReLU gate of the layer that produced that source
+ * (g = 0 where the saved mean is not > 0; Brats.py:233-238 -- the gate is a constant for autodiff).
+ *   g_out : window (out_h x out_w x cout) of the packed gradient w.r.t. the conv output (SN_TC_UPCONV: 2in_h x 2in_w);
+ *   in[i] : the forward's source windows (saved activations), in_c[i] channels each (in_c[1] == 0: single source);
+ *   g_in[i]: destination windows (in_h x in_w x in_c[i]), fully overwritten.
+ * The adjoints of mypadding / crop_tensor / myConc / unpool are address arithmetic: pass the matching windows. */
+typedef struct sn_tc_dgrad_desc {
+  sn_packed_view g_out;
+  sn_packed_view in[2];
+  sn_packed_view g_in[2];
+  int32_t in_c[2];
+  int32_t gate[2];
+  int32_t batch, in_h, in_w, ksize, cout, flags; /* forward geometry; flags: SN_TC_UPCONV only */
+  const void* wt_packed;                         /* from sn_prepare_weights_bwd */
+  const float* s;                                /* softplus(w_sigma) [cout] */
+} sn_tc_dgrad_desc;
+int sn_conv_moments_bwd_data_tc(const sn_tc_dgrad_desc* d, sn_stream_t st);
+
+/* Adjoint of sn_maxpool2_packed (Brats.py:171-174,206-216): routes g_out (ceil(in_h/2) x ceil(in_w/2) x c) to the
+ * arg-max position recomputed from the saved pool input `in` (first maximum in row-major window order).  g_in
+ * (in_h x in_w x c window) is overwritten, EXCEPT inside the sub-window (keep_y0, keep_x0, keep_h, keep_w), where
+ * the routed gradient is added to what is already there: that is how the skip connection's second consumer
+ * (the cropped encoder half of myConc, Brats.py:247-261) is summed in.  keep_h == 0: plain overwrite. */
+int sn_maxpool2_bwd_packed(const sn_packed_view* in, int32_t batch, int32_t in_h, int32_t in_w, int32_t c,
+                           const sn_packed_view* g_out, const sn_packed_view* g_in, int32_t keep_y0, int32_t keep_x0,
+                           int32_t keep_h, int32_t keep_w, sn_stream_t st);
+
+/* Backward of the fused head: loss_scale * nll_gaussian(y, p, clip(var)) (Brats.py:293-311; clips :573-574 / :588-589)
+ * -> mysoftmax (Brats.py:269-283) -> conv_final (k = 1) -> ReLU gate of the tensor feeding conv_final, in one pass.
+ * The forward quantities are recomputed from the saved packed input `in`; `acc` is the workspace sn_nll_gaussian_fwd
+ * filled for this batch (NaN/Inf -> 0 rule of Brats.py:304-305).  Writes the packed gradient window g_in. */
+int sn_head_bwd_packed(const sn_packed_view* in, int32_t batch, int32_t in_h, int32_t in_w, int32_t cin,
+                       int32_t n_labels, const float* w_mu, const float* w_sigma, const float* y, float clip_lo,
+                       float clip_hi, const double* acc, float loss_scale, const sn_packed_view* g_in, sn_stream_t st);
+
+/* Input gradient of myConv_input (Brats.py:65-76; what create_adversarial_pattern returns the sign of):
+ *   g_x = g_mu_out (*)^T W + 2 x . box^T(t),  t = sum_n g_var_out s_n;  g_out: packed (in_h-k+1 x in_w-k+1 x cout)
+ * window (already gated by the first ReLU), g_x: fp32 NHWC [batch,in_h,in_w,cin], cin <= 8. */
+int sn_first_conv_bwd_data_packed(int32_t batch, int32_t in_h, int32_t in_w, int32_t cin, int32_t cout, int32_t ksize,
+                                  const float* x, const float* w_mu, const float* w_sigma,
+                                  const sn_packed_view* g_out, float* g_x, sn_stream_t st);
+
 #ifdef __cplusplus
 }
 #endif

@@ -42,6 +42,14 @@ class sn_tc_conv_desc(C.Structure):
                 ("dst", sn_packed_view), ("dst_mu", C.c_void_p), ("dst_var", C.c_void_p)]
 
 
+class sn_tc_dgrad_desc(C.Structure):
+    _fields_ = [("g_out", sn_packed_view), ("in_", sn_packed_view * 2), ("g_in", sn_packed_view * 2),
+                ("in_c", C.c_int32 * 2), ("gate", C.c_int32 * 2),
+                ("batch", C.c_int32), ("in_h", C.c_int32), ("in_w", C.c_int32), ("ksize", C.c_int32),
+                ("cout", C.c_int32), ("flags", C.c_int32),
+                ("wt_packed", C.c_void_p), ("s", C.c_void_p)]
+
+
 SN_CONV_RELU = 1
 SN_TC_RELU, SN_TC_UPCONV, SN_TC_DST_F32, SN_TC_IM2COL = 1, 2, 4, 8
 

@@ -1,0 +1,435 @@
+// FAST mode backward, bandwidth-bound kernels around the tensor-core data gradient (sn_tc_halo.cu, DGRAD):
+// transposed weight preparation, arg-max pooling adjoint, the fused head backward (NLL -> softmax Jacobian ->
+// 1x1 conv -> ReLU gate) and the input gradient of the first convolution.  Gradients use the packed layout
+// [n][h][w][3][c] bf16 (planes g_mean_hi, g_mean_lo, g_variance); gates and arg-max routing are recomputed from
+// the saved forward activations.  Formulas: SURVEY.md A.3 (what tf.GradientTape derives at Brats.py:578,593).
+#include "sn_common.cuh"
+
+namespace sn {
+
+__device__ __forceinline__ float b_lo(uint32_t v) { return __uint_as_float(v << 16); }
+__device__ __forceinline__ float b_hi(uint32_t v) { return __uint_as_float(v & 0xFFFF0000u); }
+__device__ __forceinline__ uint32_t b_pk2(float a, float b) {
+  __nv_bfloat162 t = __floats2bfloat162_rn(a, b);
+  return *reinterpret_cast<uint32_t*>(&t);
+}
+__device__ __forceinline__ void b_unpack8(const uint4& u, float (&f)[8]) {
+  f[0] = b_lo(u.x); f[1] = b_hi(u.x); f[2] = b_lo(u.y); f[3] = b_hi(u.y);
+  f[4] = b_lo(u.z); f[5] = b_hi(u.z); f[6] = b_lo(u.w); f[7] = b_hi(u.w);
+}
+__device__ __forceinline__ void b_split8(const float (&m)[8], uint4& hi, uint4& lo) {
+  uint32_t h[4], l[4];
+#pragma unroll
+  for (int j = 0; j < 4; ++j) {
+    h[j] = b_pk2(m[2 * j], m[2 * j + 1]);
+    l[j] = b_pk2(m[2 * j] - b_lo(h[j]), m[2 * j + 1] - b_hi(h[j]));
+  }
+  hi = make_uint4(h[0], h[1], h[2], h[3]);
+  lo = make_uint4(l[0], l[1], l[2], l[3]);
+}
+__device__ __forceinline__ uint4 b_pack8(const float (&v)[8]) {
+  return make_uint4(b_pk2(v[0], v[1]), b_pk2(v[2], v[3]), b_pk2(v[4], v[5]), b_pk2(v[6], v[7]));
+}
+__device__ __forceinline__ size_t pv_off(const sn_packed_view& v, int b, int y, int x) {
+  return ((((size_t)b * v.h + y + v.y0) * v.w + x + v.x0) * 3) * v.c + v.c0;
+}
+
+// ---------------------------------------------------------------------------------------------------------
+// transposed weights for the data gradient: out[pl][tap'][ci][kcol]
+// ---------------------------------------------------------------------------------------------------------
+__global__ void prepare_weights_bwd_kernel(const float* __restrict__ w, int k, int cin, int cout, int upconv,
+                                           __nv_bfloat16* __restrict__ out) {
+  const int taps = upconv ? 1 : k * k;
+  const int K = upconv ? 4 * cout : cout;
+  const size_t plane = (size_t)taps * cin * K;
+  const size_t stride = (size_t)gridDim.x * blockDim.x;
+  for (size_t i = blockIdx.x * (size_t)blockDim.x + threadIdx.x; i < plane; i += stride) {
+    const int kc = (int)(i % K);
+    size_t t = i / K;
+    const int ci = (int)(t % cin);
+    const int tap = (int)(t / cin);
+    int kh, kw, n;
+    if (upconv) {
+      const int par = kc / cout;
+      n = kc - par * cout;
+      kh = 1 - (par >> 1); kw = 1 - (par & 1);           // parity (a,b) <- W[1-a, 1-b]
+    } else {
+      n = kc;
+      kh = k - 1 - tap / k; kw = k - 1 - tap % k;        // full correlation: flipped filter
+    }
+    const float v = w[(((size_t)kh * k + kw) * cin + ci) * cout + n];
+    __nv_bfloat16 hi, lo;
+    split_bf16(v, hi, lo);
+    out[i] = hi;
+    out[plane + i] = lo;
+    out[2 * plane + i] = __float2bfloat16_rn(v * v);
+  }
+}
+
+// ---------------------------------------------------------------------------------------------------------
+// arg-max pooling adjoint; thread = (output pixel, 8 channels)
+// ---------------------------------------------------------------------------------------------------------
+__global__ void maxpool_bwd_packed_kernel(sn_packed_view in, int B, int H, int W, int c, sn_packed_view gout,
+                                          sn_packed_view gin, int ky0, int kx0, int kh, int kw) {
+  const int Ho = (H + 1) / 2, Wo = (W + 1) / 2;
+  const int g = c / 8;
+  const size_t total = (size_t)B * Ho * Wo * g;
+  const size_t stride = (size_t)gridDim.x * blockDim.x;
+  const __nv_bfloat16* src = reinterpret_cast<const __nv_bfloat16*>(in.base);
+  const __nv_bfloat16* go = reinterpret_cast<const __nv_bfloat16*>(gout.base);
+  __nv_bfloat16* gi = reinterpret_cast<__nv_bfloat16*>(gin.base);
+  for (size_t i = blockIdx.x * (size_t)blockDim.x + threadIdx.x; i < total; i += stride) {
+    const int c8 = (int)(i % g) * 8;
+    size_t t = i / g;
+    const int xo = (int)(t % Wo);
+    t /= Wo;
+    const int yo = (int)(t % Ho);
+    const int b = (int)(t / Ho);
+    float best[8];
+    int arg[8];
+#pragma unroll
+    for (int j = 0; j < 8; ++j) { best[j] = -INFINITY; arg[j] = 0; }
+#pragma unroll
+    for (int d = 0; d < 4; ++d) {
+      const int y = 2 * yo + (d >> 1), x = 2 * xo + (d & 1);
+      if (y < H && x < W) {
+        const __nv_bfloat16* s = src + pv_off(in, b, y, x) + c8;
+        float h[8], l[8];
+        b_unpack8(*reinterpret_cast<const uint4*>(s), h);
+        b_unpack8(*reinterpret_cast<const uint4*>(s + in.c), l);
+#pragma unroll
+        for (int j = 0; j < 8; ++j) {
+          const float m = h[j] + l[j];
+          if (m > best[j]) { best[j] = m; arg[j] = d; }     // first maximum wins, like the forward
+        }
+      }
+    }
+    const __nv_bfloat16* gp = go + pv_off(gout, b, yo, xo) + c8;
+    float gh[8], gl[8], gv[8];
+    b_unpack8(*reinterpret_cast<const uint4*>(gp), gh);
+    b_unpack8(*reinterpret_cast<const uint4*>(gp + gout.c), gl);
+    b_unpack8(*reinterpret_cast<const uint4*>(gp + 2 * gout.c), gv);
+#pragma unroll
+    for (int d = 0; d < 4; ++d) {
+      const int y = 2 * yo + (d >> 1), x = 2 * xo + (d & 1);
+      if (y < H && x < W) {
+        __nv_bfloat16* o = gi + pv_off(gin, b, y, x) + c8;
+        float m[8], v[8];
+        const bool keep = y >= ky0 && y < ky0 + kh && x >= kx0 && x < kx0 + kw;
+        if (keep) {
+          float h[8], l[8];
+          b_unpack8(*reinterpret_cast<const uint4*>(o), h);
+          b_unpack8(*reinterpret_cast<const uint4*>(o + gin.c), l);
+          b_unpack8(*reinterpret_cast<const uint4*>(o + 2 * gin.c), v);
+#pragma unroll
+          for (int j = 0; j < 8; ++j) m[j] = h[j] + l[j];
+        } else {
+#pragma unroll
+          for (int j = 0; j < 8; ++j) m[j] = v[j] = 0.f;
+        }
+#pragma unroll
+        for (int j = 0; j < 8; ++j)
+          if (arg[j] == d) { m[j] += gh[j] + gl[j]; v[j] += gv[j]; }
+        uint4 hi, lo;
+        b_split8(m, hi, lo);
+        *reinterpret_cast<uint4*>(o) = hi;
+        *reinterpret_cast<uint4*>(o + gin.c) = lo;
+        *reinterpret_cast<uint4*>(o + 2 * gin.c) = b_pack8(v);
+      }
+    }
+  }
+}
+
+// ---------------------------------------------------------------------------------------------------------
+// fused head backward; thread = pixel
+// ---------------------------------------------------------------------------------------------------------
+constexpr float kHeadEps = 1e-3f;     // nll_gaussian's epsilon (Brats.py:298)
+
+template <int C>
+__global__ void __launch_bounds__(128) head_bwd_kernel(sn_packed_view in, int B, int H, int W, int cin,
+                                                       const float* __restrict__ w, const float* __restrict__ ws,
+                                                       const float* __restrict__ y, float clip_lo, float clip_hi,
+                                                       const double* __restrict__ acc, float loss_scale,
+                                                       sn_packed_view gin) {
+  extern __shared__ __align__(16) float hsm[];   // W [cin][C], W^2 [cin][C], s [C]
+  float* sw = hsm;
+  float* sw2 = hsm + cin * C;
+  float* ss = hsm + 2 * cin * C;
+  for (int i = threadIdx.x; i < cin * C; i += blockDim.x) {
+    const float v = w[i];
+    sw[i] = v;
+    sw2[i] = v * v;
+  }
+  for (int i = threadIdx.x; i < C; i += blockDim.x) ss[i] = softplus_f(ws[i]);
+  __syncthreads();
+  const size_t total = (size_t)B * H * W;
+  const float qmean = (float)(acc[0] / (double)total);
+  const float qon = (isnan(qmean) || isinf(qmean)) ? 0.f : 1.f;      // Brats.py:304-305
+  const float g = 0.5f * loss_scale / (float)total;
+  const __nv_bfloat16* src = reinterpret_cast<const __nv_bfloat16*>(in.base);
+  __nv_bfloat16* dst = reinterpret_cast<__nv_bfloat16*>(gin.base);
+  for (size_t i = blockIdx.x * (size_t)blockDim.x + threadIdx.x; i < total; i += (size_t)gridDim.x * blockDim.x) {
+    const int xx = (int)(i % W);
+    size_t t = i / W;
+    const int yy = (int)(t % H);
+    const int b = (int)(t / H);
+    const __nv_bfloat16* s = src + pv_off(in, b, yy, xx);
+    // ---- forward recompute: conv_final (k = 1) + softmax moments
+    float m[C], v[C];
+#pragma unroll
+    for (int j = 0; j < C; ++j) m[j] = v[j] = 0.f;
+    float r = 0.f;
+    for (int c8 = 0; c8 < cin; c8 += 8) {
+      float h[8], l[8], vv[8];
+      b_unpack8(*reinterpret_cast<const uint4*>(s + c8), h);
+      b_unpack8(*reinterpret_cast<const uint4*>(s + in.c + c8), l);
+      b_unpack8(*reinterpret_cast<const uint4*>(s + 2 * in.c + c8), vv);
+#pragma unroll
+      for (int e = 0; e < 8; ++e) {
+        const float mu = h[e] + l[e];
+        r += fmaf(mu, mu, vv[e]);
+#pragma unroll
+        for (int j = 0; j < C; ++j) {
+          m[j] = fmaf(mu, sw[(c8 + e) * C + j], m[j]);
+          v[j] = fmaf(vv[e], sw2[(c8 + e) * C + j], v[j]);
+        }
+      }
+    }
+    float mx = -INFINITY;
+#pragma unroll
+    for (int j = 0; j < C; ++j) {
+      v[j] = fmaxf(fmaf(ss[j], r, v[j]), 0.f);
+      mx = fmaxf(mx, m[j]);
+    }
+    float p[C], sum = 0.f;
+#pragma unroll
+    for (int j = 0; j < C; ++j) { p[j] = expf(m[j] - mx); sum += p[j]; }
+    const float inv = 1.f / sum;
+#pragma unroll
+    for (int j = 0; j < C; ++j) p[j] *= inv;
+    // ---- NLL gradient w.r.t. (p, softmax variance) on the clipped variance (Brats.py:293-311)
+    float gp[C], gvo[C];
+#pragma unroll
+    for (int a = 0; a < C; ++a) {
+      float vo = 0.f;
+#pragma unroll
+      for (int j = 0; j < C; ++j) {
+        const float J = p[a] * ((a == j ? 1.f : 0.f) - p[j]);
+        vo = fmaf(J * J, v[j], vo);
+      }
+      const float vc = fminf(fmaxf(vo, clip_lo), clip_hi) + kHeadEps;
+      const float iv = 1.f / vc;
+      const float d = p[a] - y[i * C + a];
+      gp[a] = qon * g * 2.f * d * iv;
+      const bool pass = vo >= clip_lo && vo <= clip_hi;
+      gvo[a] = pass ? g * (iv - qon * d * d * iv * iv) : 0.f;
+    }
+    // ---- softmax-Jacobian VJP
+    float gv[C], gpt[C];
+#pragma unroll
+    for (int j = 0; j < C; ++j) { gv[j] = 0.f; gpt[j] = gp[j]; }
+#pragma unroll
+    for (int a = 0; a < C; ++a) {
+      float sa = 0.f;
+#pragma unroll
+      for (int j = 0; j < C; ++j) {
+        const float d = (a == j ? 1.f : 0.f) - p[j];
+        const float J = p[a] * d;
+        gv[j] += gvo[a] * J * J;
+        sa += J * v[j] * d;
+        gpt[j] -= gvo[a] * 2.f * J * v[j] * p[a];
+      }
+      gpt[a] += gvo[a] * 2.f * sa;
+    }
+    float dot = 0.f;
+#pragma unroll
+    for (int k = 0; k < C; ++k) dot += gpt[k] * p[k];
+    float gm[C];
+    float tt = 0.f;                         // t = sum_n g_var_n s_n
+#pragma unroll
+    for (int j = 0; j < C; ++j) {
+      gm[j] = p[j] * (gpt[j] - dot);
+      tt = fmaf(gv[j], ss[j], tt);
+    }
+    // ---- conv_final data gradient + ReLU gate of its (post-ReLU) input
+    __nv_bfloat16* o = dst + pv_off(gin, b, yy, xx);
+    for (int c8 = 0; c8 < cin; c8 += 8) {
+      float h[8], l[8];
+      b_unpack8(*reinterpret_cast<const uint4*>(s + c8), h);
+      b_unpack8(*reinterpret_cast<const uint4*>(s + in.c + c8), l);
+      float om[8], ov[8];
+#pragma unroll
+      for (int e = 0; e < 8; ++e) {
+        const float mu = h[e] + l[e];
+        float a = 2.f * mu * tt, vv = tt;
+#pragma unroll
+        for (int j = 0; j < C; ++j) {
+          a = fmaf(gm[j], sw[(c8 + e) * C + j], a);
+          vv = fmaf(gv[j], sw2[(c8 + e) * C + j], vv);
+        }
+        const bool on = mu > 0.f;
+        om[e] = on ? a : 0.f;
+        ov[e] = on ? vv : 0.f;
+      }
+      uint4 hi, lo;
+      b_split8(om, hi, lo);
+      *reinterpret_cast<uint4*>(o + c8) = hi;
+      *reinterpret_cast<uint4*>(o + gin.c + c8) = lo;
+      *reinterpret_cast<uint4*>(o + 2 * gin.c + c8) = b_pack8(ov);
+    }
+  }
+}
+
+// ---------------------------------------------------------------------------------------------------------
+// input gradient of the first convolution; thread = input pixel
+// ---------------------------------------------------------------------------------------------------------
+template <int CIN>
+__global__ void __launch_bounds__(128) first_conv_bwd_kernel(int B, int H, int W, int cout, int k,
+                                                             const float* __restrict__ x,
+                                                             const float* __restrict__ w,
+                                                             const float* __restrict__ ws, sn_packed_view gout,
+                                                             float* __restrict__ gx) {
+  extern __shared__ __align__(16) float fsm[];   // W [tap][cout][CIN], s [cout]
+  float* sw = fsm;
+  float* ss = fsm + k * k * cout * CIN;
+  for (int i = threadIdx.x; i < k * k * cout * CIN; i += blockDim.x) {
+    const int ci = i % CIN;
+    const int n = (i / CIN) % cout;
+    const int tap = i / (CIN * cout);
+    sw[i] = w[((size_t)tap * CIN + ci) * cout + n];
+  }
+  for (int i = threadIdx.x; i < cout; i += blockDim.x) ss[i] = softplus_f(ws[i]);
+  __syncthreads();
+  const int Ho = H - k + 1, Wo = W - k + 1;
+  const size_t total = (size_t)B * H * W;
+  const __nv_bfloat16* go = reinterpret_cast<const __nv_bfloat16*>(gout.base);
+  for (size_t i = blockIdx.x * (size_t)blockDim.x + threadIdx.x; i < total; i += (size_t)gridDim.x * blockDim.x) {
+    const int xx = (int)(i % W);
+    size_t t = i / W;
+    const int yy = (int)(t % H);
+    const int b = (int)(t / H);
+    float acc[CIN];
+#pragma unroll
+    for (int c = 0; c < CIN; ++c) acc[c] = 0.f;
+    float T = 0.f;
+    for (int kh = 0; kh < k; ++kh) {
+      const int oy = yy - kh;
+      if (oy < 0 || oy >= Ho) continue;
+      for (int kw = 0; kw < k; ++kw) {
+        const int ox = xx - kw;
+        if (ox < 0 || ox >= Wo) continue;
+        const __nv_bfloat16* gp = go + pv_off(gout, b, oy, ox);
+        const float* wt = sw + (kh * k + kw) * cout * CIN;
+        for (int n8 = 0; n8 < cout; n8 += 8) {
+          float h[8], l[8], v[8];
+          b_unpack8(*reinterpret_cast<const uint4*>(gp + n8), h);
+          b_unpack8(*reinterpret_cast<const uint4*>(gp + gout.c + n8), l);
+          b_unpack8(*reinterpret_cast<const uint4*>(gp + 2 * gout.c + n8), v);
+#pragma unroll
+          for (int e = 0; e < 8; ++e) {
+            const float gm = h[e] + l[e];
+            T = fmaf(v[e], ss[n8 + e], T);
+#pragma unroll
+            for (int c = 0; c < CIN; ++c) acc[c] = fmaf(gm, wt[(n8 + e) * CIN + c], acc[c]);
+          }
+        }
+      }
+    }
+#pragma unroll
+    for (int c = 0; c < CIN; ++c) gx[i * CIN + c] = fmaf(2.f * x[i * CIN + c], T, acc[c]);
+  }
+}
+
+static int check_pv(const sn_packed_view* v, int batch, int h, int w, int c, const char* who) {
+  SN_REQUIRE(v && v->base && aligned16(v->base), SN_ERR_BAD_ARG, "%s: null/misaligned packed view", who);
+  SN_REQUIRE(v->n >= batch && v->c % 8 == 0 && v->c0 % 8 == 0 && c % 8 == 0, SN_ERR_MISALIGNED,
+             "%s: channel counts/offsets must be multiples of 8", who);
+  SN_REQUIRE(v->y0 >= 0 && v->x0 >= 0 && v->c0 >= 0 && v->y0 + h <= v->h && v->x0 + w <= v->w && v->c0 + c <= v->c,
+             SN_ERR_BAD_ARG, "%s: window outside the buffer", who);
+  return SN_OK;
+}
+
+}  // namespace sn
+
+using namespace sn;
+
+extern "C" {
+
+int sn_prepare_weights_bwd(const float* w_mu, int32_t ksize, int32_t cin, int32_t cout, int32_t upconv,
+                           void* wt_packed, sn_stream_t st) {
+  SN_REQUIRE(w_mu && wt_packed, SN_ERR_BAD_ARG, "prepare_weights_bwd: null pointer");
+  SN_REQUIRE(ksize >= 1 && ksize <= 3 && cin > 0 && cout > 0, SN_ERR_BAD_ARG, "prepare_weights_bwd: bad sizes");
+  SN_REQUIRE(!upconv || ksize == 2, SN_ERR_BAD_ARG, "prepare_weights_bwd: upconv needs ksize == 2");
+  const size_t n = (size_t)ksize * ksize * cin * cout;
+  prepare_weights_bwd_kernel<<<ew_grid(n, 256), 256, 0, as_stream(st)>>>(w_mu, ksize, cin, cout, upconv,
+                                                                          reinterpret_cast<__nv_bfloat16*>(wt_packed));
+  return check_launch("prepare_weights_bwd");
+}
+
+int sn_maxpool2_bwd_packed(const sn_packed_view* in, int32_t batch, int32_t in_h, int32_t in_w, int32_t c,
+                           const sn_packed_view* g_out, const sn_packed_view* g_in, int32_t keep_y0, int32_t keep_x0,
+                           int32_t keep_h, int32_t keep_w, sn_stream_t st) {
+  SN_REQUIRE(batch > 0 && in_h > 0 && in_w > 0 && c > 0, SN_ERR_BAD_ARG, "maxpool_bwd_packed: bad shape");
+  SN_REQUIRE(keep_h >= 0 && keep_w >= 0 && keep_y0 >= 0 && keep_x0 >= 0 && keep_y0 + keep_h <= in_h &&
+                 keep_x0 + keep_w <= in_w, SN_ERR_BAD_ARG, "maxpool_bwd_packed: keep window outside the tensor");
+  int rc = check_pv(in, batch, in_h, in_w, c, "maxpool_bwd_packed in");
+  if (rc) return rc;
+  const int Ho = (in_h + 1) / 2, Wo = (in_w + 1) / 2;
+  if ((rc = check_pv(g_out, batch, Ho, Wo, c, "maxpool_bwd_packed g_out"))) return rc;
+  if ((rc = check_pv(g_in, batch, in_h, in_w, c, "maxpool_bwd_packed g_in"))) return rc;
+  const size_t total = (size_t)batch * Ho * Wo * (c / 8);
+  maxpool_bwd_packed_kernel<<<ew_grid(total, 256), 256, 0, as_stream(st)>>>(*in, batch, in_h, in_w, c, *g_out, *g_in,
+                                                                             keep_y0, keep_x0, keep_h, keep_w);
+  return check_launch("maxpool_bwd_packed");
+}
+
+int sn_head_bwd_packed(const sn_packed_view* in, int32_t batch, int32_t in_h, int32_t in_w, int32_t cin,
+                       int32_t n_labels, const float* w_mu, const float* w_sigma, const float* y, float clip_lo,
+                       float clip_hi, const double* acc, float loss_scale, const sn_packed_view* g_in, sn_stream_t st) {
+  SN_REQUIRE(w_mu && w_sigma && y && acc, SN_ERR_BAD_ARG, "head_bwd: null pointer");
+  SN_REQUIRE(n_labels >= 1 && n_labels <= 8, SN_ERR_UNSUPPORTED, "head_bwd: %d classes (max 8)", n_labels);
+  SN_REQUIRE(cin > 0 && cin % 8 == 0 && cin <= 256, SN_ERR_UNSUPPORTED, "head_bwd: cin %d", cin);
+  int rc = check_pv(in, batch, in_h, in_w, cin, "head_bwd in");
+  if (rc) return rc;
+  if ((rc = check_pv(g_in, batch, in_h, in_w, cin, "head_bwd g_in"))) return rc;
+  const size_t total = (size_t)batch * in_h * in_w;
+  const size_t smem = ((size_t)2 * cin * n_labels + n_labels) * sizeof(float);
+  const int grid = ew_grid(total, 128, 8);
+#define SN_HEAD(CC)                                                                                              \
+  case CC:                                                                                                       \
+    head_bwd_kernel<CC><<<grid, 128, smem, as_stream(st)>>>(*in, batch, in_h, in_w, cin, w_mu, w_sigma, y, clip_lo, \
+                                                             clip_hi, acc, loss_scale, *g_in);                   \
+    break;
+  switch (n_labels) {
+    SN_HEAD(1) SN_HEAD(2) SN_HEAD(3) SN_HEAD(4) SN_HEAD(5) SN_HEAD(6) SN_HEAD(7) SN_HEAD(8)
+  }
+#undef SN_HEAD
+  return check_launch("head_bwd");
+}
+
+int sn_first_conv_bwd_data_packed(int32_t batch, int32_t in_h, int32_t in_w, int32_t cin, int32_t cout, int32_t ksize,
+                                  const float* x, const float* w_mu, const float* w_sigma,
+                                  const sn_packed_view* g_out, float* g_x, sn_stream_t st) {
+  SN_REQUIRE(x && w_mu && w_sigma && g_x, SN_ERR_BAD_ARG, "first_conv_bwd: null pointer");
+  SN_REQUIRE(batch > 0 && cin >= 1 && cin <= 8 && ksize >= 1 && ksize <= 3 && in_h >= ksize && in_w >= ksize,
+             SN_ERR_UNSUPPORTED, "first_conv_bwd: needs cin <= 8 and k <= 3 (got cin %d, k %d)", cin, ksize);
+  SN_REQUIRE(cout % 8 == 0 && cout <= 256, SN_ERR_UNSUPPORTED, "first_conv_bwd: cout %d", cout);
+  int rc = check_pv(g_out, batch, in_h - ksize + 1, in_w - ksize + 1, cout, "first_conv_bwd g_out");
+  if (rc) return rc;
+  const size_t total = (size_t)batch * in_h * in_w;
+  const size_t smem = ((size_t)ksize * ksize * cout * cin + cout) * sizeof(float);
+  SN_REQUIRE(smem <= 48 * 1024, SN_ERR_UNSUPPORTED, "first_conv_bwd: weights do not fit shared memory");
+  const int grid = ew_grid(total, 128, 8);
+#define SN_FCB(CC)                                                                                                  \
+  case CC:                                                                                                          \
+    first_conv_bwd_kernel<CC><<<grid, 128, smem, as_stream(st)>>>(batch, in_h, in_w, cout, ksize, x, w_mu, w_sigma, \
+                                                                   *g_out, g_x);                                    \
+    break;
+  switch (cin) {
+    SN_FCB(1) SN_FCB(2) SN_FCB(3) SN_FCB(4) SN_FCB(5) SN_FCB(6) SN_FCB(7) SN_FCB(8)
+  }
+#undef SN_FCB
+  return check_launch("first_conv_bwd");
+}
+
+}  // extern "C"

@@ -458,3 +458,34 @@ extern "C" int sn_conv_moments_fwd_tc(const sn_tc_conv_desc* d, sn_stream_t st) 
     default: return launch_tc<32>(maps, p, n_tiles, stream);
   }
 }
+
+namespace sn {
+int conv_moments_halo_dgrad_dispatch(const sn_tc_dgrad_desc* d, cudaStream_t stream);   // sn_tc_halo.cu
+}
+
+// Data gradient of the fused moment convolution (the chain tf.GradientTape builds at Brats.py:578,593).
+extern "C" int sn_conv_moments_bwd_data_tc(const sn_tc_dgrad_desc* d, sn_stream_t st) {
+  SN_REQUIRE(d, SN_ERR_BAD_ARG, "dgrad_tc: null descriptor");
+  const bool upconv = (d->flags & SN_TC_UPCONV) != 0;
+  SN_REQUIRE((d->flags & ~SN_TC_UPCONV) == 0, SN_ERR_BAD_ARG, "dgrad_tc: only SN_TC_UPCONV is a valid flag");
+  SN_REQUIRE(d->batch > 0 && d->in_h > 0 && d->in_w > 0 && d->cout > 0, SN_ERR_BAD_ARG, "dgrad_tc: bad geometry");
+  SN_REQUIRE(d->ksize >= 1 && d->ksize <= 3, SN_ERR_UNSUPPORTED, "dgrad_tc: kernel size %d", d->ksize);
+  SN_REQUIRE(!upconv || d->ksize == 2, SN_ERR_BAD_ARG, "dgrad_tc: SN_TC_UPCONV needs ksize == 2");
+  SN_REQUIRE(d->in_c[0] > 0 && d->in_c[0] % TC_KC == 0 && d->in_c[1] >= 0 && d->in_c[1] % TC_KC == 0,
+             SN_ERR_UNSUPPORTED, "dgrad_tc: source channels (%d, %d) must be multiples of %d", d->in_c[0], d->in_c[1],
+             TC_KC);
+  SN_REQUIRE(d->cout % TC_KC == 0, SN_ERR_UNSUPPORTED, "dgrad_tc: cout %d must be a multiple of %d", d->cout, TC_KC);
+  SN_REQUIRE(d->wt_packed && d->s && aligned16(d->wt_packed), SN_ERR_BAD_ARG, "dgrad_tc: weights missing/misaligned");
+  const int keff = upconv ? 1 : d->ksize;
+  SN_REQUIRE(d->in_h >= keff && d->in_w >= keff, SN_ERR_BAD_ARG, "dgrad_tc: input smaller than the kernel");
+  const int Ho = d->in_h - keff + 1, Wo = d->in_w - keff + 1;
+  const int out_h = upconv ? 2 * d->in_h : Ho, out_w = upconv ? 2 * d->in_w : Wo;
+  int rc;
+  if ((rc = check_view(d->g_out, d->batch, out_h, out_w, d->cout, "dgrad_tc g_out"))) return rc;
+  for (int s = 0; s < 2; ++s) {
+    if (d->in_c[s] == 0) continue;
+    if ((rc = check_view(d->in[s], d->batch, d->in_h, d->in_w, d->in_c[s], "dgrad_tc in"))) return rc;
+    if ((rc = check_view(d->g_in[s], d->batch, d->in_h, d->in_w, d->in_c[s], "dgrad_tc g_in"))) return rc;
+  }
+  return conv_moments_halo_dgrad_dispatch(d, as_stream(st));
+}

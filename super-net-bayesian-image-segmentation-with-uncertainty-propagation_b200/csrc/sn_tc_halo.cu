@@ -44,8 +44,13 @@ constexpr int HL_MAX_ASTAGES = 4;
 constexpr int HL_SMEM = 232448;        // 227 KB: always requested so exactly one CTA owns an SM (and its TMEM)
 
 struct HlMaps {
-  CUtensorMap a[2][3];
+  CUtensorMap a[4][3];     // forward: up to two concatenated sources; data gradient of an up-conv: four parity views
   CUtensorMap w;
+};
+
+struct HlView {            // a window of a packed buffer, device side
+  __nv_bfloat16* base;
+  int h, w, c, y0, x0, c0;
 };
 
 struct HlP {
@@ -55,7 +60,8 @@ struct HlP {
   int rows_box;            // R * THb * TN  (<= 254)
   int a_plane;             // bytes reserved per A plane per stage (multiple of 1024)
   int ksize, taps_w;       // K-side taps per dim; taps in the prepared weights
-  int cblk0, cblk1;
+  int cblk_s[4];           // 32-channel K blocks taken from each source
+  int pad;                 // data gradient: the box origin is shifted by -(k-1); TMA zero-fills outside the window
   int Ho, Wo, B;           // valid output extents (upconv: the input grid)
   int cout, relu, upconv, dst_f32;
   int sa, sb, b_resident;  // A stages, B slots, weights resident?
@@ -65,6 +71,10 @@ struct HlP {
   float* dst_var;
   int out_h, out_w;
   const float* s;
+  int s_len;               // forward: cout; data gradient: channels of one gradient source
+  // data gradient only: destination / saved-activation windows of the two forward sources
+  HlView gdst[2], saved[2];
+  int csplit, gate[2];
 };
 
 __device__ __forceinline__ float hl_lo(uint32_t v) { return __uint_as_float(v << 16); }
@@ -98,7 +108,7 @@ struct TileIt {
   }
 };
 
-template <int NT, int KS, bool RESIDENT>
+template <int NT, int KS, bool RESIDENT, bool DGRAD>
 __global__ void __launch_bounds__(HL_THREADS, 1) conv_moments_halo_kernel(const __grid_constant__ HlMaps maps,
                                                                           const HlP p) {
   constexpr int B_PLANE = NT * HL_KC * 2;
@@ -129,12 +139,13 @@ __global__ void __launch_bounds__(HL_THREADS, 1) conv_moments_halo_kernel(const 
 
   const int warp = __shfl_sync(0xffffffffu, (int)(threadIdx.x >> 5), 0);   // provably warp-uniform
   const int lane = threadIdx.x & 31;
-  const int cblk = p.cblk0 + p.cblk1;
+  const int cblk = p.cblk_s[0] + p.cblk_s[1] + p.cblk_s[2] + p.cblk_s[3];
   constexpr int taps = KS * KS;
 
   if (warp == 0 && lane == 0) {
-    for (int s = 0; s < 2; ++s)
-      for (int pl = 0; pl < 3; ++pl) ptx::prefetch_tensormap(&maps.a[s][pl]);
+    for (int s = 0; s < 4; ++s)
+      if (p.cblk_s[s])
+        for (int pl = 0; pl < 3; ++pl) ptx::prefetch_tensormap(&maps.a[s][pl]);
     ptx::prefetch_tensormap(&maps.w);
     for (int s = 0; s < p.sa; ++s) {
       ptx::mbar_init(a_full(s), 1);
@@ -156,7 +167,7 @@ __global__ void __launch_bounds__(HL_THREADS, 1) conv_moments_halo_kernel(const 
     ptx::tmem_alloc(tmem_slot, TMEM_COLS);
     ptx::tmem_relinquish();
   }
-  for (int i = threadIdx.x; i < p.cout; i += HL_THREADS) s_sm[i] = p.s[i];
+  for (int i = threadIdx.x; i < p.s_len; i += HL_THREADS) s_sm[i] = p.s[i];
   ptx::tc_fence_before();
   __syncthreads();
   ptx::tc_fence_after();
@@ -173,16 +184,16 @@ __global__ void __launch_bounds__(HL_THREADS, 1) conv_moments_halo_kernel(const 
         const int ncol0 = nt_i * NT;
         const int group = ncol0 / p.cout;
         const int n0 = ncol0 - group * p.cout;
-        const int x0 = tx * p.TWo, y0 = ty * p.THo, b0 = tb * p.TN;
-        for (int cbt = 0; cbt < cblk; ++cbt) {
+        const int x0 = tx * p.TWo - p.pad, y0 = ty * p.THo - p.pad, b0 = tb * p.TN;
+        int src = 0, cb = 0;
+        for (int cbt = 0; cbt < cblk; ++cbt, ++cb) {
+          while (cb >= p.cblk_s[src]) { cb = 0; ++src; }
           {
             const int stage = ai % p.sa;
             const uint32_t parity = (uint32_t)(ai / p.sa) & 1u;
             ++ai;
             ptx::mbar_wait(a_empty(stage), parity ^ 1u);
             ptx::mbar_arrive_expect_tx(a_full(stage), (uint32_t)(3 * p.rows_box * 64));
-            const int src = cbt >= p.cblk0 ? 1 : 0;
-            const int cb = src ? cbt - p.cblk0 : cbt;
             const uint32_t sa_addr = smem_base + stage * a_stage;
 #pragma unroll
             for (int pl = 0; pl < 3; ++pl) {
@@ -306,26 +317,42 @@ __global__ void __launch_bounds__(HL_THREADS, 1) conv_moments_halo_kernel(const 
       uint32_t a_par = 0;
       for (int tile = blockIdx.x, titer = 0; tile < p.total_tiles; tile += gridDim.x, ++titer) {
         float qa = 0.f, qb = 0.f, qc = 0.f, qd = 0.f;         // four chains for ILP
-        for (int cbt = 0; cbt < cblk; ++cbt) {
+        int src = 0, cb = 0;
+        for (int cbt = 0; cbt < cblk; ++cbt, ++cb) {
+          if constexpr (DGRAD) {
+            while (cb >= p.cblk_s[src]) { cb = 0; ++src; }
+          }
           ptx::mbar_wait(a_full(a_stage_i), a_par);
           if (row < p.rows_box) {
             const uint8_t* ar = smem_gen + a_stage_i * a_stage + row * 64;
 #pragma unroll
             for (int j = 0; j < 4; ++j) {
               const int ch = ((j + (row >> 1)) & 3) * 16;   // chunk rotation: conflict-free, order-insensitive sum
-              const uint4 hh4 = *reinterpret_cast<const uint4*>(ar + ch);
-              const uint4 ll4 = *reinterpret_cast<const uint4*>(ar + p.a_plane + ch);
-              const uint4 vv4 = *reinterpret_cast<const uint4*>(ar + 2 * p.a_plane + ch);
-              const uint32_t hh[4] = {hh4.x, hh4.y, hh4.z, hh4.w}, ll[4] = {ll4.x, ll4.y, ll4.z, ll4.w},
-                             vv[4] = {vv4.x, vv4.y, vv4.z, vv4.w};
+              if constexpr (DGRAD) {
+                // t[pixel] = sum_n g_var[pixel, n] * s_n: only the variance-gradient plane
+                const uint4 vv4 = *reinterpret_cast<const uint4*>(ar + 2 * p.a_plane + ch);
+                // SWIZZLE_64B: physical 16-byte chunk c of smem row r holds logical chunk c ^ ((r >> 1) & 3)
+                const float* sp = s_sm + cb * HL_KC + (((ch >> 4) ^ ((row >> 1) & 3)) << 3);
+                const float4 s0 = *reinterpret_cast<const float4*>(sp), s1 = *reinterpret_cast<const float4*>(sp + 4);
+                qa = fmaf(hl_lo(vv4.x), s0.x, qa); qb = fmaf(hl_hi(vv4.x), s0.y, qb);
+                qc = fmaf(hl_lo(vv4.y), s0.z, qc); qd = fmaf(hl_hi(vv4.y), s0.w, qd);
+                qa = fmaf(hl_lo(vv4.z), s1.x, qa); qb = fmaf(hl_hi(vv4.z), s1.y, qb);
+                qc = fmaf(hl_lo(vv4.w), s1.z, qc); qd = fmaf(hl_hi(vv4.w), s1.w, qd);
+              } else {
+                const uint4 hh4 = *reinterpret_cast<const uint4*>(ar + ch);
+                const uint4 ll4 = *reinterpret_cast<const uint4*>(ar + p.a_plane + ch);
+                const uint4 vv4 = *reinterpret_cast<const uint4*>(ar + 2 * p.a_plane + ch);
+                const uint32_t hh[4] = {hh4.x, hh4.y, hh4.z, hh4.w}, ll[4] = {ll4.x, ll4.y, ll4.z, ll4.w},
+                               vv[4] = {vv4.x, vv4.y, vv4.z, vv4.w};
 #pragma unroll
-              for (int e = 0; e < 4; ++e) {
-                const float m_a = hl_lo(hh[e]) + hl_lo(ll[e]);
-                const float m_b = hl_hi(hh[e]) + hl_hi(ll[e]);
-                qa = fmaf(m_a, m_a, qa);
-                qb = fmaf(m_b, m_b, qb);
-                qc += hl_lo(vv[e]);
-                qd += hl_hi(vv[e]);
+                for (int e = 0; e < 4; ++e) {
+                  const float m_a = hl_lo(hh[e]) + hl_lo(ll[e]);
+                  const float m_b = hl_hi(hh[e]) + hl_hi(ll[e]);
+                  qa = fmaf(m_a, m_a, qa);
+                  qb = fmaf(m_b, m_b, qb);
+                  qc += hl_lo(vv[e]);
+                  qd += hl_hi(vv[e]);
+                }
               }
             }
           }
@@ -378,6 +405,70 @@ __global__ void __launch_bounds__(HL_THREADS, 1) conv_moments_halo_kernel(const 
         ptx::mbar_wait(acc_full(as), par);
         ptx::tc_fence_after();
         const uint32_t lane_base = tmem_base + ((uint32_t)(q * 32) << 16) + as * ACC_STAGE + half * NH;
+        if constexpr (DGRAD) {
+          // ---- data gradient: g_mu = acc_mu + 2 mu_saved T, g_var = acc_var + T, T = r; then the
+          // ReLU gate of the layer that produced the forward input (Brats.py:233-238: the gate is mu_saved > 0)
+#pragma unroll 1
+          for (int c0 = 0; c0 < NH; c0 += 16) {
+            const int gcol = gcol0 + c0;
+            const int seg = gcol >= p.csplit ? 1 : 0;
+            const int nch = gcol - (seg ? p.csplit : 0);
+            const HlView& dv = p.gdst[seg];
+            const HlView& sv = p.saved[seg];
+            uint4 sh0 = make_uint4(0, 0, 0, 0), sh1 = sh0, sl0 = sh0, sl1 = sh0;
+            if (valid) {
+              const __nv_bfloat16* sp =
+                  sv.base + ((((size_t)ob * sv.h + oy_i + sv.y0) * sv.w + ox_i + sv.x0) * 3) * sv.c + sv.c0 + nch;
+              sh0 = *reinterpret_cast<const uint4*>(sp);
+              sh1 = *reinterpret_cast<const uint4*>(sp + 8);
+              sl0 = *reinterpret_cast<const uint4*>(sp + sv.c);
+              sl1 = *reinterpret_cast<const uint4*>(sp + sv.c + 8);
+            }
+            uint32_t am[16], av[16];
+            ptx::tmem_ld16(lane_base + c0, am);
+            ptx::tmem_ld16(lane_base + (CONCAT ? 2 * NT : NT) + c0, av);
+            if constexpr (CONCAT) {
+              uint32_t am2[16];
+              ptx::tmem_ld16(lane_base + NT + c0, am2);
+              ptx::tmem_ld_wait();
+#pragma unroll
+              for (int j = 0; j < 16; ++j) am[j] = __float_as_uint(__uint_as_float(am[j]) + __uint_as_float(am2[j]));
+            } else {
+              ptx::tmem_ld_wait();
+            }
+            const uint32_t shw[8] = {sh0.x, sh0.y, sh0.z, sh0.w, sh1.x, sh1.y, sh1.z, sh1.w};
+            const uint32_t slw[8] = {sl0.x, sl0.y, sl0.z, sl0.w, sl1.x, sl1.y, sl1.z, sl1.w};
+            const bool gate = p.gate[seg] != 0;
+            const float r2 = 2.f * r;
+            uint32_t hi[8], lo[8], vr[8];
+#pragma unroll
+            for (int j = 0; j < 8; ++j) {
+              const float m0 = hl_lo(shw[j]) + hl_lo(slw[j]), m1 = hl_hi(shw[j]) + hl_hi(slw[j]);
+              float a0 = fmaf(m0, r2, __uint_as_float(am[2 * j])), a1 = fmaf(m1, r2, __uint_as_float(am[2 * j + 1]));
+              float v0 = __uint_as_float(av[2 * j]) + r, v1 = __uint_as_float(av[2 * j + 1]) + r;
+              if (gate) {
+                if (!(m0 > 0.f)) { a0 = 0.f; v0 = 0.f; }
+                if (!(m1 > 0.f)) { a1 = 0.f; v1 = 0.f; }
+              }
+              hi[j] = hl_pack2(a0, a1);
+              lo[j] = hl_pack2(a0 - hl_lo(hi[j]), a1 - hl_hi(hi[j]));
+              vr[j] = hl_pack2(v0, v1);
+            }
+            if (valid) {
+              __nv_bfloat16* d_hi =
+                  dv.base + ((((size_t)ob * dv.h + oy_i + dv.y0) * dv.w + ox_i + dv.x0) * 3) * dv.c + dv.c0 + nch;
+              uint4* ph = reinterpret_cast<uint4*>(d_hi);
+              uint4* pl = reinterpret_cast<uint4*>(d_hi + dv.c);
+              uint4* pv = reinterpret_cast<uint4*>(d_hi + 2 * dv.c);
+              ph[0] = make_uint4(hi[0], hi[1], hi[2], hi[3]);
+              ph[1] = make_uint4(hi[4], hi[5], hi[6], hi[7]);
+              pl[0] = make_uint4(lo[0], lo[1], lo[2], lo[3]);
+              pl[1] = make_uint4(lo[4], lo[5], lo[6], lo[7]);
+              pv[0] = make_uint4(vr[0], vr[1], vr[2], vr[3]);
+              pv[1] = make_uint4(vr[4], vr[5], vr[6], vr[7]);
+            }
+          }
+        } else {
 #pragma unroll 1
         for (int c0 = 0; c0 < NH; c0 += 16) {
           // destination of this 16-channel chunk (an up-conv tile may span several parity groups; cout % 32 == 0,
@@ -456,6 +547,7 @@ __global__ void __launch_bounds__(HL_THREADS, 1) conv_moments_halo_kernel(const 
             }
           }
         }
+        }
         ptx::tc_fence_before();
         __syncwarp();
         if (lane == 0) ptx::mbar_arrive(acc_empty(as));    // this warp's TMEM reads of stage `as` are done
@@ -527,13 +619,16 @@ static HaloTiling choose_tiling(int batch, int in_h, int in_w, int k) {
   return best;
 }
 
+// Tensor map of one plane of a packed window.  `step` = 2 with origin (oy, ox) addresses the pixels (2y+oy, 2x+ox):
+// the four parity views the data gradient of an up-conv reads.  Everything outside the window reads as zero
+// (TMA out-of-bounds fill), which is how the data gradient gets its (k-1)-wide zero border.
 static int hl_make_act_map(CUtensorMap* out, const sn_packed_view& v, int plane, int src_c, int batch, int in_h,
-                           int in_w, const HaloTiling& t) {
+                           int in_w, const HaloTiling& t, int step = 1, int oy = 0, int ox = 0) {
   const size_t pix = (size_t)3 * v.c;
   char* base = reinterpret_cast<char*>(v.base) +
-               ((((size_t)v.y0 * v.w + v.x0) * 3 + plane) * v.c + v.c0) * sizeof(__nv_bfloat16);
+               ((((size_t)(v.y0 + oy) * v.w + v.x0 + ox) * 3 + plane) * v.c + v.c0) * sizeof(__nv_bfloat16);
   cuuint64_t dims[4] = {(cuuint64_t)src_c, (cuuint64_t)in_w, (cuuint64_t)in_h, (cuuint64_t)batch};
-  cuuint64_t strides[3] = {pix * 2, (cuuint64_t)v.w * pix * 2, (cuuint64_t)v.h * v.w * pix * 2};
+  cuuint64_t strides[3] = {pix * 2 * step, (cuuint64_t)v.w * pix * 2 * step, (cuuint64_t)v.h * v.w * pix * 2};
   cuuint32_t box[4] = {HL_KC, (cuuint32_t)t.R, (cuuint32_t)t.THb, (cuuint32_t)t.TN};
   cuuint32_t estr[4] = {1, 1, 1, 1};
   CUresult r = hl_encode_tiled()(out, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 4, base, dims, strides, box, estr,
@@ -555,30 +650,79 @@ static int hl_make_weight_map(CUtensorMap* out, const void* w_packed, int taps, 
   return SN_OK;
 }
 
-template <int NT, int KS, bool RESIDENT>
+template <int NT, int KS, bool RESIDENT, bool DGRAD>
 static int hl_launch3(const HlMaps& maps, const HlP& p, cudaStream_t st) {
   static std::once_flag once;
   static cudaError_t attr_err = cudaSuccess;
   std::call_once(once, [] {
-    attr_err = cudaFuncSetAttribute(conv_moments_halo_kernel<NT, KS, RESIDENT>,
+    attr_err = cudaFuncSetAttribute(conv_moments_halo_kernel<NT, KS, RESIDENT, DGRAD>,
                                     cudaFuncAttributeMaxDynamicSharedMemorySize, HL_SMEM);
   });
   if (attr_err != cudaSuccess) return fail(SN_ERR_LAUNCH, "conv_halo: cannot reserve %d B of shared memory", HL_SMEM);
   int grid = p.total_tiles < num_sms() ? p.total_tiles : num_sms();
-  conv_moments_halo_kernel<NT, KS, RESIDENT><<<grid, HL_THREADS, HL_SMEM, st>>>(maps, p);
-  return check_launch("conv_moments_halo");
+  conv_moments_halo_kernel<NT, KS, RESIDENT, DGRAD><<<grid, HL_THREADS, HL_SMEM, st>>>(maps, p);
+  return check_launch(DGRAD ? "conv_moments_halo_dgrad" : "conv_moments_halo");
 }
 
 template <int NT>
 static int hl_launch(const HlMaps& maps, const HlP& p, cudaStream_t st) {
   switch (p.ksize * 2 + (p.b_resident ? 1 : 0)) {
-    case 2: return hl_launch3<NT, 1, false>(maps, p, st);
-    case 3: return hl_launch3<NT, 1, true>(maps, p, st);
-    case 4: return hl_launch3<NT, 2, false>(maps, p, st);
-    case 5: return hl_launch3<NT, 2, true>(maps, p, st);
-    case 6: return hl_launch3<NT, 3, false>(maps, p, st);
-    default: return hl_launch3<NT, 3, true>(maps, p, st);
+    case 2: return hl_launch3<NT, 1, false, false>(maps, p, st);
+    case 3: return hl_launch3<NT, 1, true, false>(maps, p, st);
+    case 4: return hl_launch3<NT, 2, false, false>(maps, p, st);
+    case 5: return hl_launch3<NT, 2, true, false>(maps, p, st);
+    case 6: return hl_launch3<NT, 3, false, false>(maps, p, st);
+    default: return hl_launch3<NT, 3, true, false>(maps, p, st);
   }
+}
+
+// The data gradient only ever needs k = 3 / 2 (regular convs) and k = 1 (1x1 convs and the up-conv, whose four
+// output parities become four K-concatenated sources).
+template <int NT>
+static int hl_launch_dgrad(const HlMaps& maps, const HlP& p, cudaStream_t st) {
+  switch (p.ksize * 2 + (p.b_resident ? 1 : 0)) {
+    case 2: return hl_launch3<NT, 1, false, true>(maps, p, st);
+    case 3: return hl_launch3<NT, 1, true, true>(maps, p, st);
+    case 4: return hl_launch3<NT, 2, false, true>(maps, p, st);
+    case 5: return hl_launch3<NT, 2, true, true>(maps, p, st);
+    case 6: return hl_launch3<NT, 3, false, true>(maps, p, st);
+    default: return hl_launch3<NT, 3, true, true>(maps, p, st);
+  }
+}
+
+// Tile geometry + shared-memory plan shared by the forward and the data-gradient dispatch.
+static int hl_plan(HlP& p, const HaloTiling& t, int keff, int ncols, int nt, int cblk) {
+  p.tiles_x = t.tiles_x; p.tiles_y = t.tiles_y; p.tiles_b = t.tiles_b;
+  p.tiles_n = ncols / nt;
+  const long long total = (long long)p.tiles_x * p.tiles_y * p.tiles_b * p.tiles_n;
+  SN_REQUIRE(total < (1ll << 30), SN_ERR_UNSUPPORTED, "conv_halo: too many tiles");
+  p.total_tiles = (int)total;
+  p.TWo = t.TWo; p.THo = t.THo; p.R = t.R; p.THb = t.THb; p.TN = t.TN;
+  p.rows_box = t.R * t.THb * t.TN;
+  const int rows_alloc = HL_BM + (keff - 1) * (t.R + 1);
+  const int rows_need = rows_alloc > p.rows_box ? rows_alloc : p.rows_box;
+  SN_REQUIRE(rows_need <= 256, SN_ERR_UNSUPPORTED, "conv_halo: halo tile of %d rows", rows_need);
+  p.a_plane = ((rows_need * 64 + 1023) / 1024) * 1024;
+  p.ksize = keff;
+  // shared-memory plan: [A stages][B slots][1 KB barriers][2 KB q buffers][2 KB s], 1 KB alignment slack
+  const int avail = HL_SMEM - 1024 - 1024 - 2048 - 2048;
+  const int a_stage = 3 * p.a_plane;
+  const int b_slot = 3 * nt * HL_KC * 2;
+  const int resident_slots = cblk * keff * keff;
+  if (p.tiles_n == 1 && resident_slots <= HL_MAX_BSLOTS && resident_slots * b_slot + 2 * a_stage <= avail) {
+    p.b_resident = 1;
+    p.sb = resident_slots;
+    p.sa = (avail - resident_slots * b_slot) / a_stage;
+  } else {
+    p.b_resident = 0;
+    p.sa = 3;
+    if (3 * a_stage + 3 * b_slot > avail) p.sa = 2;
+    p.sb = (avail - p.sa * a_stage) / b_slot;
+    if (p.sb > HL_MAX_BSLOTS) p.sb = HL_MAX_BSLOTS;
+    SN_REQUIRE(p.sb >= 2, SN_ERR_UNSUPPORTED, "conv_halo: shared memory plan failed");
+  }
+  if (p.sa > HL_MAX_ASTAGES) p.sa = HL_MAX_ASTAGES;
+  return SN_OK;
 }
 
 // Called by sn_conv_moments_fwd_tc (sn_tc_conv.cu) after argument validation.
@@ -595,61 +739,32 @@ int conv_moments_halo_dispatch(const sn_tc_conv_desc* d, cudaStream_t stream) {
   const int taps_w = upconv ? 4 : d->ksize * d->ksize;
   const int cin = d->src_c[0] + d->src_c[1];
   const int cblk = cin / HL_KC;
-  const int taps = keff * keff;
 
   const HaloTiling t = choose_tiling(d->batch, d->in_h, d->in_w, keff);
   SN_REQUIRE(t.eff > 0, SN_ERR_UNSUPPORTED, "conv_halo: no tiling for %dx%d k=%d", d->in_h, d->in_w, keff);
   SN_REQUIRE(d->cout <= 512, SN_ERR_UNSUPPORTED, "conv_halo: cout %d > 512", d->cout);
 
   HlP p{};
-  p.tiles_x = t.tiles_x; p.tiles_y = t.tiles_y; p.tiles_b = t.tiles_b;
-  p.tiles_n = ncols / nt;
-  const long long total = (long long)p.tiles_x * p.tiles_y * p.tiles_b * p.tiles_n;
-  SN_REQUIRE(total < (1ll << 30), SN_ERR_UNSUPPORTED, "conv_halo: too many tiles");
-  p.total_tiles = (int)total;
-  p.TWo = t.TWo; p.THo = t.THo; p.R = t.R; p.THb = t.THb; p.TN = t.TN;
-  p.rows_box = t.R * t.THb * t.TN;
-  const int rows_alloc = HL_BM + (keff - 1) * (t.R + 1);
-  const int rows_need = rows_alloc > p.rows_box ? rows_alloc : p.rows_box;
-  SN_REQUIRE(rows_need <= 256, SN_ERR_UNSUPPORTED, "conv_halo: halo tile of %d rows", rows_need);
-  p.a_plane = ((rows_need * 64 + 1023) / 1024) * 1024;
-  p.ksize = keff; p.taps_w = taps_w;
-  p.cblk0 = d->src_c[0] / HL_KC; p.cblk1 = d->src_c[1] / HL_KC;
+  int rc;
+  if ((rc = hl_plan(p, t, keff, ncols, nt, cblk))) return rc;
+  p.taps_w = taps_w;
+  p.cblk_s[0] = d->src_c[0] / HL_KC; p.cblk_s[1] = d->src_c[1] / HL_KC;
   p.Ho = Ho; p.Wo = Wo; p.B = d->batch;
   p.cout = d->cout;
   p.relu = (d->flags & SN_TC_RELU) ? 1 : 0; p.upconv = upconv ? 1 : 0; p.dst_f32 = dst_f32 ? 1 : 0;
   p.dst = reinterpret_cast<__nv_bfloat16*>(d->dst.base);
   p.dh = d->dst.h; p.dw = d->dst.w; p.dc = d->dst.c; p.dy0 = d->dst.y0; p.dx0 = d->dst.x0; p.dc0 = d->dst.c0;
   p.dst_mu = d->dst_mu; p.dst_var = d->dst_var; p.out_h = out_h; p.out_w = out_w;
-  p.s = d->s;
-
-  // shared-memory plan: [A stages][B slots][1 KB barriers][2 KB q buffers][2 KB s], 1 KB alignment slack
-  const int avail = HL_SMEM - 1024 - 1024 - 2048 - 2048;
-  const int a_stage = 3 * p.a_plane;
-  const int b_slot = 3 * nt * HL_KC * 2;
-  const int resident_slots = cblk * taps;
-  if (p.tiles_n == 1 && resident_slots <= HL_MAX_BSLOTS && resident_slots * b_slot + 2 * a_stage <= avail) {
-    p.b_resident = 1;
-    p.sb = resident_slots;
-    p.sa = (avail - resident_slots * b_slot) / a_stage;
-  } else {
-    p.b_resident = 0;
-    p.sa = 3;
-    if (3 * a_stage + 3 * b_slot > avail) p.sa = 2;
-    p.sb = (avail - p.sa * a_stage) / b_slot;
-    if (p.sb > HL_MAX_BSLOTS) p.sb = HL_MAX_BSLOTS;
-    SN_REQUIRE(p.sb >= 2, SN_ERR_UNSUPPORTED, "conv_halo: shared memory plan failed");
-  }
-  if (p.sa > HL_MAX_ASTAGES) p.sa = HL_MAX_ASTAGES;
+  p.s = d->s; p.s_len = d->cout;
 
   HlMaps maps;
-  int rc;
   for (int s = 0; s < 2; ++s) {
     const int srcs = d->src_c[s] ? s : 0;
     for (int pl = 0; pl < 3; ++pl)
       if ((rc = hl_make_act_map(&maps.a[s][pl], d->src[srcs], pl, d->src_c[srcs], d->batch, d->in_h, d->in_w, t)))
         return rc;
   }
+  for (int pl = 0; pl < 3; ++pl) maps.a[2][pl] = maps.a[3][pl] = maps.a[0][pl];     // unused
   // regular: [3*taps][cout][cin]; up-conv: [3][4*cout][cin] (same memory, parity and channel fused into one axis)
   if ((rc = hl_make_weight_map(&maps.w, d->w_packed, upconv ? 1 : taps_w, upconv ? ncols : d->cout, cin, nt)))
     return rc;
@@ -657,6 +772,65 @@ int conv_moments_halo_dispatch(const sn_tc_conv_desc* d, cudaStream_t stream) {
     case 128: return hl_launch<128>(maps, p, stream);
     case 64: return hl_launch<64>(maps, p, stream);
     default: return hl_launch<32>(maps, p, stream);
+  }
+}
+
+static HlView hl_view(const sn_packed_view& v) {
+  return HlView{reinterpret_cast<__nv_bfloat16*>(v.base), v.h, v.w, v.c, v.y0, v.x0, v.c0};
+}
+
+// Called by sn_conv_moments_bwd_data_tc (sn_tc_conv.cu) after argument validation.  The data gradient of a VALID
+// k x k moment conv is the same halo GEMM run over the gradient w.r.t. the conv's output, zero-extended by k-1
+// (TMA out-of-bounds fill), against the flipped / transposed weights (sn_prepare_weights_bwd):
+//   g_mu = g_mu' (*)^T W + 2 mu box^T(t),  g_var = g_var' (*)^T W^2 + box^T(t),  t = sum_n g_var'_n s_n.
+// The up-conv (unpool + 2x2 conv) is pointwise per 2x2 output block: a 1x1 GEMM whose K axis concatenates the four
+// parity views (2y+a, 2x+b) of the output gradient.
+int conv_moments_halo_dgrad_dispatch(const sn_tc_dgrad_desc* d, cudaStream_t stream) {
+  SN_REQUIRE(hl_encode_tiled() != nullptr, SN_ERR_DRIVER, "conv_halo: cuTensorMapEncodeTiled unavailable");
+  const bool upconv = (d->flags & SN_TC_UPCONV) != 0;
+  const int keff = upconv ? 1 : d->ksize;
+  const int pad = keff - 1;
+  const int Ho_f = d->in_h - keff + 1, Wo_f = d->in_w - keff + 1;     // grid of one gradient source
+  const int gh = Ho_f + 2 * pad, gw = Wo_f + 2 * pad;                  // zero-extended gradient = the GEMM's "input"
+  const int ncols = d->in_c[0] + d->in_c[1];                           // GEMM N = the forward's input channels
+  const int nt = ncols % 128 == 0 ? 128 : (ncols % 64 == 0 ? 64 : 32);
+  const int nsrc = upconv ? 4 : 1;
+  const int cblk = nsrc * d->cout / HL_KC;
+
+  const HaloTiling t = choose_tiling(d->batch, gh, gw, keff);
+  SN_REQUIRE(t.eff > 0, SN_ERR_UNSUPPORTED, "conv_halo dgrad: no tiling for %dx%d k=%d", gh, gw, keff);
+  SN_REQUIRE(d->cout <= 512, SN_ERR_UNSUPPORTED, "conv_halo dgrad: cout %d > 512", d->cout);
+
+  HlP p{};
+  int rc;
+  if ((rc = hl_plan(p, t, keff, ncols, nt, cblk))) return rc;
+  p.taps_w = keff * keff;
+  for (int s = 0; s < nsrc; ++s) p.cblk_s[s] = d->cout / HL_KC;
+  p.pad = pad;
+  p.Ho = d->in_h; p.Wo = d->in_w; p.B = d->batch;
+  p.cout = ncols;
+  p.s = d->s; p.s_len = d->cout;
+  p.csplit = d->in_c[1] ? d->in_c[0] : ncols;
+  for (int s = 0; s < 2; ++s) {
+    const int ss = d->in_c[s] ? s : 0;
+    p.gdst[s] = hl_view(d->g_in[ss]);
+    p.saved[s] = hl_view(d->in[ss]);
+    p.gate[s] = d->gate[ss];
+  }
+
+  HlMaps maps;
+  for (int s = 0; s < 4; ++s) {
+    const int oy = upconv ? (s >> 1) : 0, ox = upconv ? (s & 1) : 0;
+    for (int pl = 0; pl < 3; ++pl)
+      if ((rc = hl_make_act_map(&maps.a[s][pl], d->g_out, pl, d->cout, d->batch, Ho_f, Wo_f, t, upconv ? 2 : 1, oy, ox)))
+        return rc;
+  }
+  // transposed weights [3][taps][N = cin][K = nsrc * cout]
+  if ((rc = hl_make_weight_map(&maps.w, d->wt_packed, keff * keff, ncols, nsrc * d->cout, nt))) return rc;
+  switch (nt) {
+    case 128: return hl_launch_dgrad<128>(maps, p, stream);
+    case 64: return hl_launch_dgrad<64>(maps, p, stream);
+    default: return hl_launch_dgrad<32>(maps, p, stream);
   }
 }
 

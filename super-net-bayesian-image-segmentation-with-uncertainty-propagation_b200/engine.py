@@ -34,6 +34,7 @@ class InferenceEngine:
         self._graph: Optional[torch.cuda.CUDAGraph] = None
         self._steps: List[Callable[[], None]] = []
         self.step_names: List[str] = []
+        self.records: List[dict] = []        # one entry per forward launch (what GradientEngine walks backwards)
         self._weights_version = None
         self._build()
 
@@ -66,6 +67,7 @@ class InferenceEngine:
             m.build_with_input(Cin, dev)
         self._prepare_weights()
         steps = self._steps
+        self.skip_window = {}
         self.x_in = torch.empty(self.shape, device=dev, dtype=torch.float32)
 
         def new(h, w, c, prefill=None):
@@ -78,6 +80,8 @@ class InferenceEngine:
             wp, s = self.prepared[name]
             cout = getattr(m, name).kernel_num
             self.step_names.append(name)
+            self.records.append(dict(kind="conv", name=name, src0=src, c0=c0, src1=src1, c1=c1, h=h, w=w, k=k,
+                                     cout=cout, dst=dst, relu=relu, upconv=upconv))
             steps.append(lambda: F.conv_moments_tc(src, c0, B, h, w, k, cout, wp, s, dst=dst, relu=relu,
                                                    upconv=upconv, src1=src1, c1=c1))
 
@@ -86,6 +90,7 @@ class InferenceEngine:
         a0 = new(h, w, n)
         w_in, ws_in = m.conv_input.weights()
         self.step_names.append("conv_input")
+        self.records.append(dict(kind="first", dst=PackedView(a0)))
         steps.append(lambda: F.first_conv_packed(self.x_in, w_in, ws_in, PackedView(a0), relu=True))
         skip = new(h - 2, w - 2, n)
         conv("conv1", PackedView(a0), n, h, w, 3, PackedView(skip), True)
@@ -103,6 +108,7 @@ class InferenceEngine:
                 pooled = new(ph, pw, c)
                 pview = PackedView(pooled)
             self.step_names.append(f"pool{lvl}")
+            self.records.append(dict(kind="pool", src=PackedView(cur), h=h, w=w, c=c, dst=pview))
             steps.append(lambda s=PackedView(cur), hh=h, ww=w, cc=c, d=pview: F.maxpool2_packed(s, B, hh, ww, cc, d))
             h, w = ph, pw
             cur = pooled
@@ -130,6 +136,7 @@ class InferenceEngine:
             mid = new(h - 2 + 4, w - 2 + 4, c1n, prefill=fill)           # mypad [2,2] (Brats.py:420)
             conv(f"up{d}_conv1", PackedView(up), cu, h, w, 3, PackedView(mid, 2, 2, 0), True,
                  src1=PackedView(enc, oy, ox, 0), c1=ec)
+            self.skip_window[enc.data_ptr()] = (oy, ox, h, w)            # where the decoder reads the skip tensor
             h, w = h + 2, w + 2
             c2n = getattr(m, f"up{d}_conv2").kernel_num
             out = new(h - 2, w - 2, c2n)
@@ -145,6 +152,7 @@ class InferenceEngine:
         wf, wsf = m.conv_final.weights()
         last, lc = cur, c
         self.step_names.append("conv_final")
+        self.records.append(dict(kind="head", src=PackedView(last), h=h, w=w, c=lc))
         pre = (self.pre_m, self.pre_v) if self.keep_presoftmax else (None, None)
         steps.append(lambda: F.final_conv_softmax_packed(PackedView(last), B, h, w, lc, wf, wsf, self.p, self.v,
                                                          pre[0], pre[1]))
@@ -184,6 +192,151 @@ class InferenceEngine:
                 raise RuntimeError("engine was built with keep_presoftmax=False")
             return p.clone(), v.clone(), self.pre_m.clone(), self.pre_v.clone()
         return p.clone(), v.clone()
+
+
+class GradientEngine(InferenceEngine):
+    """FAST-mode forward + input-gradient chain: what create_adversarial_pattern (Brats.py:582-596) needs, on the
+    tensor cores.  The forward is InferenceEngine's launch sequence (every activation buffer is kept, nothing is
+    aliased); the backward walks its records in reverse:
+
+      head      sn_head_bwd_packed            NLL -> softmax Jacobian -> conv_final -> ReLU gate
+      conv      sn_conv_moments_bwd_data_tc   halo GEMM over the output gradient, flipped/transposed weights; the
+                                              adjoints of pad / crop / concat / unpool are the forward's windows
+      pool      sn_maxpool2_bwd_packed        arg-max routing recomputed from the saved pool input, summed with the
+                                              gradient the decoder's concat already left in the skip tensor
+      first     sn_first_conv_bwd_data_packed g_x (fp32 NHWC)
+
+    Gradient tensors use the packed layout of the activation they belong to (g_mean hi/lo, g_variance).  The whole
+    forward + loss + backward sequence is allocation-free and is captured in one CUDA graph."""
+
+    def __init__(self, model, batch: int, in_h: int, in_w: int, in_c: int, device, graph: bool = True):
+        super().__init__(model, batch, in_h, in_w, in_c, device, graph=False, keep_presoftmax=False)
+        self.use_graph_bwd = graph
+        self._graph_bwd: Optional[torch.cuda.CUDAGraph] = None
+        self._bwd_steps: List[Callable[[], None]] = []
+        self.bwd_step_names: List[str] = []
+        self._clip = (-1e4, 1e3)
+        self._loss_scale = 0.5
+        self._build_backward()
+
+    def _prepare_weights(self) -> None:
+        super()._prepare_weights()
+        m = self.model
+        self.prepared_bwd = {}
+        for name in m.conv_names:
+            if name in ("conv_input", "conv_final"):
+                continue
+            w, _ = getattr(m, name).weights()
+            self.prepared_bwd[name] = F.prepare_weights_bwd(w, upconv=name.endswith("conv2x2"))
+
+    def _build_backward(self) -> None:
+        m = self.model
+        B, H, W, Cin = self.shape
+        dev = self.device
+        C = m.n_labels
+        oh, ow = self.out_hw
+        self.y_in = torch.zeros((B, oh * ow, C), device=dev, dtype=torch.float32)
+        self.g_x = torch.empty(self.shape, device=dev, dtype=torch.float32)
+        self.nll_acc = torch.zeros(2, device=dev, dtype=torch.float64)
+        self.nll_loss = torch.zeros(1, device=dev, dtype=torch.float32)
+        gbuf = {}                 # activation buffer -> gradient buffer of the same shape
+        gated = {}                # activation buffer -> its producer applied the ReLU gate (or pooled such a tensor)
+
+        def g_of(view: PackedView) -> PackedView:
+            key = view.buf.data_ptr()
+            if key not in gbuf:
+                gbuf[key] = torch.empty_like(view.buf)
+            return PackedView(gbuf[key], view.y0, view.x0, view.c0)
+
+        for r in self.records:
+            if r["kind"] == "first":
+                gated[r["dst"].buf.data_ptr()] = True
+            elif r["kind"] == "conv":
+                gated[r["dst"].buf.data_ptr()] = bool(r["relu"])
+            elif r["kind"] == "pool":
+                gated[r["dst"].buf.data_ptr()] = gated[r["src"].buf.data_ptr()]
+        steps, names = self._bwd_steps, self.bwd_step_names
+        wf, wsf = m.conv_final.weights()
+        w_in, ws_in = m.conv_input.weights()
+        for r in reversed(self.records):
+            kind = r["kind"]
+            if kind == "head":
+                src = r["src"]
+                if not gated[src.buf.data_ptr()]:
+                    raise RuntimeError("conv_final must read a post-ReLU tensor")
+                names.append("head_bwd")
+                steps.append(lambda src=src, r=r: F.head_bwd_packed(src, B, r["h"], r["w"], r["c"], wf, wsf, self.y_in,
+                                                                    self._clip, self.nll_acc, self._loss_scale,
+                                                                    g_of(src)))
+                g_of(src)
+            elif kind == "conv":
+                name = r["name"]
+                wt = self.prepared_bwd[name]
+                s = self.prepared[name][1]
+                src0, src1 = r["src0"], r["src1"]
+                args = dict(g_out=g_of(r["dst"]), batch=B, in_h=r["h"], in_w=r["w"], ksize=r["k"], cout=r["cout"],
+                            wt_packed=wt, s=s, in0=src0, g_in0=g_of(src0), c0=r["c0"],
+                            gate0=gated[src0.buf.data_ptr()], upconv=r["upconv"])
+                if src1 is not None:
+                    args.update(in1=src1, g_in1=g_of(src1), c1=r["c1"], gate1=gated[src1.buf.data_ptr()])
+                names.append(name + "_dgrad")
+                steps.append(lambda a=args: F.conv_moments_bwd_data_tc(**a))
+            elif kind == "pool":
+                src, dst = r["src"], r["dst"]
+                keep = self.skip_window.get(src.buf.data_ptr(), (0, 0, 0, 0))
+                names.append("pool_bwd")
+                steps.append(lambda src=src, dst=dst, r=r, keep=keep: F.maxpool2_bwd_packed(
+                    src, B, r["h"], r["w"], r["c"], g_of(dst), g_of(src), keep))
+                g_of(dst), g_of(src)
+            elif kind == "first":
+                names.append("conv_input_dgrad")
+                steps.append(lambda r=r: F.first_conv_bwd_data_packed(self.x_in, w_in, ws_in, g_of(r["dst"]), self.g_x))
+                g_of(r["dst"])
+        self.grad_buffers = gbuf
+        self.n_launches_bwd = len(steps) + 2          # + the two NLL forward kernels
+
+    def refresh_weights(self) -> None:
+        super().refresh_weights()
+        self._graph_bwd = None
+
+    def _launch_fwd_bwd(self) -> None:
+        self._launch_all()
+        F.nll_gaussian_fwd(self.y_in, self.p, self.v, self._clip, self.nll_acc, self.nll_loss)
+        for s in self._bwd_steps:
+            s()
+
+    def loss_and_input_gradient_resident(self) -> Tuple[Tensor, Tensor]:
+        """Forward, loss_scale * NLL and d(loss)/dx on whatever is in self.x_in / self.y_in; returns engine-owned
+        (loss [1] = the un-scaled NLL, g_x)."""
+        if not self.use_graph_bwd:
+            self._launch_fwd_bwd()
+        else:
+            if self._graph_bwd is None:
+                side = torch.cuda.Stream(device=self.device)
+                side.wait_stream(torch.cuda.current_stream())
+                with torch.cuda.stream(side):
+                    self._launch_fwd_bwd()
+                torch.cuda.current_stream().wait_stream(side)
+                g = torch.cuda.CUDAGraph()
+                with torch.cuda.graph(g):
+                    self._launch_fwd_bwd()
+                self._graph_bwd = g
+            self._graph_bwd.replay()
+        return self.nll_loss, self.g_x
+
+    def input_gradient(self, x: Tensor, y_onehot: Tensor, loss_scale: float = 0.5,
+                       clip: Tuple[float, float] = (-1e4, 1e3)) -> Tuple[Tensor, Tensor]:
+        """(loss, d loss / d x) with loss = loss_scale * nll_gaussian(y, p, clip(var)): the defaults are
+        create_adversarial_pattern's loss (Brats.py:587-590)."""
+        if not self.matches(x):
+            raise RuntimeError(f"engine built for input {self.shape}, got {tuple(x.shape)}")
+        if (loss_scale, tuple(clip)) != (self._loss_scale, self._clip):
+            self._loss_scale, self._clip = float(loss_scale), (float(clip[0]), float(clip[1]))
+            self._graph_bwd = None                       # scalars are baked into the captured launches
+        self.x_in.copy_(x, non_blocking=True)
+        self.y_in.copy_(y_onehot.reshape(self.y_in.shape), non_blocking=True)
+        loss, g = self.loss_and_input_gradient_resident()
+        return loss_scale * loss.clone(), g.clone()
 
 
 class StreamingPipeline:

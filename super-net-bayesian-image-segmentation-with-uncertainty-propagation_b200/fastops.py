@@ -1,7 +1,8 @@
 """FAST-mode (tcgen05) entry points of the C-ABI as thin Python functions over torch tensors.
 
 A packed moment tensor is a torch.bfloat16 tensor of shape [n, h, w, 3, c] (planes mean_hi, mean_lo, variance
-per pixel; include/supernet.h).  `PackedView` names a window of one.  Inference only: no autograd.
+per pixel; include/supernet.h).  `PackedView` names a window of one.  No autograd tape: the backward entry points
+(data gradients on packed gradient tensors, same layout) are called explicitly by engine.GradientEngine.
 """
 from __future__ import annotations
 
@@ -12,7 +13,8 @@ from typing import Optional, Tuple
 import torch
 
 from . import _lib
-from ._lib import SN_TC_DST_F32, SN_TC_IM2COL, SN_TC_RELU, SN_TC_UPCONV, check, ptr, sn_packed_view, sn_tc_conv_desc, stream_ptr
+from ._lib import (SN_TC_DST_F32, SN_TC_IM2COL, SN_TC_RELU, SN_TC_UPCONV, check, ptr, sn_packed_view, sn_tc_conv_desc,
+                   sn_tc_dgrad_desc, stream_ptr)
 
 Tensor = torch.Tensor
 
@@ -111,3 +113,64 @@ def final_conv_softmax_packed(src: PackedView, batch: int, in_h: int, in_w: int,
     check(_lib.load().sn_final_conv_softmax_packed(C.byref(v), batch, in_h, in_w, cin, n_labels, ptr(w_mu),
                                                    ptr(w_sigma), ptr(p_out), ptr(var_out), ptr(pre_mu), ptr(pre_var),
                                                    stream_ptr()), "final_conv_softmax_packed")
+
+
+# ---- backward (data gradient) ----------------------------------------------------------------------------
+def prepare_weights_bwd(w_mu: Tensor, upconv: bool = False) -> Tensor:
+    """HWIO fp32 -> the data-gradient operands [3, taps, cin, K] bf16 (flipped / transposed filter; up-conv: K =
+    (parity, cout), taps = 1)."""
+    k, _, cin, cout = w_mu.shape
+    shape = (3, 1, cin, 4 * cout) if upconv else (3, k * k, cin, cout)
+    wt = torch.empty(shape, device=w_mu.device, dtype=torch.bfloat16)
+    check(_lib.load().sn_prepare_weights_bwd(ptr(w_mu.detach().contiguous()), k, cin, cout, 1 if upconv else 0,
+                                             ptr(wt), stream_ptr()), "prepare_weights_bwd")
+    return wt
+
+
+def conv_moments_bwd_data_tc(g_out: PackedView, batch: int, in_h: int, in_w: int, ksize: int, cout: int,
+                             wt_packed: Tensor, s: Tensor, in0: PackedView, g_in0: PackedView, c0: int, gate0: bool,
+                             in1: Optional[PackedView] = None, g_in1: Optional[PackedView] = None, c1: int = 0,
+                             gate1: bool = False, upconv: bool = False) -> None:
+    d = sn_tc_dgrad_desc()
+    d.g_out = g_out.c_view()
+    d.in_[0], d.g_in[0] = in0.c_view(), g_in0.c_view()
+    d.in_[1] = (in1 if in1 is not None else in0).c_view()
+    d.g_in[1] = (g_in1 if g_in1 is not None else g_in0).c_view()
+    d.in_c[0], d.in_c[1] = c0, c1
+    d.gate[0], d.gate[1] = int(gate0), int(gate1)
+    d.batch, d.in_h, d.in_w, d.ksize, d.cout = batch, in_h, in_w, ksize, cout
+    d.flags = SN_TC_UPCONV if upconv else 0
+    d.wt_packed = wt_packed.data_ptr()
+    d.s = s.data_ptr()
+    check(_lib.load().sn_conv_moments_bwd_data_tc(C.byref(d), stream_ptr()), "conv_moments_bwd_data_tc")
+
+
+def maxpool2_bwd_packed(inp: PackedView, batch: int, in_h: int, in_w: int, c: int, g_out: PackedView,
+                        g_in: PackedView, keep: Tuple[int, int, int, int] = (0, 0, 0, 0)) -> None:
+    a, b, g = inp.c_view(), g_out.c_view(), g_in.c_view()
+    check(_lib.load().sn_maxpool2_bwd_packed(C.byref(a), batch, in_h, in_w, c, C.byref(b), C.byref(g), keep[0],
+                                             keep[1], keep[2], keep[3], stream_ptr()), "maxpool2_bwd_packed")
+
+
+def head_bwd_packed(inp: PackedView, batch: int, in_h: int, in_w: int, cin: int, w_mu: Tensor, w_sigma: Tensor,
+                    y: Tensor, clip: Tuple[float, float], acc: Tensor, loss_scale: float, g_in: PackedView) -> None:
+    a, g = inp.c_view(), g_in.c_view()
+    n_labels = w_mu.shape[-1]
+    check(_lib.load().sn_head_bwd_packed(C.byref(a), batch, in_h, in_w, cin, n_labels, ptr(w_mu), ptr(w_sigma),
+                                         ptr(y), C.c_float(clip[0]), C.c_float(clip[1]), ptr(acc),
+                                         C.c_float(loss_scale), C.byref(g), stream_ptr()), "head_bwd_packed")
+
+
+def first_conv_bwd_data_packed(x: Tensor, w_mu: Tensor, w_sigma: Tensor, g_out: PackedView, g_x: Tensor) -> None:
+    B, H, W, cin = x.shape
+    k, _, _, cout = w_mu.shape
+    g = g_out.c_view()
+    check(_lib.load().sn_first_conv_bwd_data_packed(B, H, W, cin, cout, k, ptr(x), ptr(w_mu), ptr(w_sigma),
+                                                    C.byref(g), ptr(g_x), stream_ptr()), "first_conv_bwd_data_packed")
+
+
+def nll_gaussian_fwd(y: Tensor, p: Tensor, var: Tensor, clip: Tuple[float, float], acc: Tensor, loss: Tensor) -> None:
+    """sn_nll_gaussian_fwd on preallocated workspaces (acc: 2 doubles, loss: 1 float): graph-capturable."""
+    rows, c = p.numel() // p.shape[-1], p.shape[-1]
+    check(_lib.load().sn_nll_gaussian_fwd(C.c_size_t(rows), c, ptr(y), ptr(p), ptr(var), C.c_float(clip[0]),
+                                          C.c_float(clip[1]), ptr(acc), ptr(loss), stream_ptr()), "nll_gaussian_fwd")

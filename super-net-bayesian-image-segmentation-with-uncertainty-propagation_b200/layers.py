@@ -248,6 +248,7 @@ class Density_prop_with_pad_UNET(nn.Module):
             if not name_.endswith("conv2x2") and name_ != "conv_final":
                 getattr(self, name_).fuse_relu = True
         self._engine = None
+        self._grad_engine = None
 
     # -- Keras-like accessors ---------------------------------------------------------------------------
     def convs(self) -> List[_MomentConv]:
@@ -273,6 +274,7 @@ class Density_prop_with_pad_UNET(nn.Module):
                 w, s = w.to(device), s.to(device)
             getattr(self, n).set_weights(w, s)
         self._engine = None
+        self._grad_engine = None
         return self
 
     def build_with_input(self, in_channels: int, device) -> None:
@@ -346,6 +348,14 @@ class Density_prop_with_pad_UNET(nn.Module):
             self._engine = InferenceEngine(self, x.shape[0], x.shape[1], x.shape[2], x.shape[3], x.device)
         return self._engine.run(x, return_presoftmax)
 
+    def input_gradient_fast(self, x: Tensor, y_onehot: Tensor, loss_scale: float = 0.5,
+                            clip: Tuple[float, float] = (-1e4, 1e3)):
+        """(loss, d loss/dx), loss = loss_scale * NLL(clip(var)), through the FAST-mode gradient engine."""
+        from .engine import GradientEngine
+        if self._grad_engine is None or not self._grad_engine.matches(x):
+            self._grad_engine = GradientEngine(self, x.shape[0], x.shape[1], x.shape[2], x.shape[3], x.device)
+        return self._grad_engine.input_gradient(x, y_onehot, loss_scale, clip)
+
     # -- losses of the reference's step functions ---------------------------------------------------------
     def elbo_loss(self, x: Tensor, y_onehot: Tensor, kl_factor: float = 1e-5) -> Tensor:
         """train_on_batch loss (Brats.py:572-576): NLL(clip(var,1e-12,1e3)) + kl_factor * 0.5 * regularisers."""
@@ -360,6 +370,10 @@ class Density_prop_with_pad_UNET(nn.Module):
 
 def create_adversarial_pattern(model: Density_prop_with_pad_UNET, input_image: Tensor, input_label: Tensor):
     """create_adversarial_pattern (Brats.py:582-596): sign of d(0.5 NLL)/dx.  Returns (signed_grad, gradient)."""
+    if model.mode == "fast":
+        # tensor-core forward + data-gradient chain (engine.GradientEngine); no autograd tape involved
+        _, g = model.input_gradient_fast(input_image.detach(), input_label)
+        return torch.sign(g), g
     x = input_image.detach().clone().requires_grad_(True)
     loss = model.adversarial_loss(x, input_label)
     (g,) = torch.autograd.grad(loss, x)

@@ -1,0 +1,267 @@
+"""GPU parity tests of the FAST-mode (tcgen05) BACKWARD kernels against autograd on the CPU oracle.
+
+The reference obtains every gradient from tf.GradientTape (Brats.py:578,593); the oracle restates the forward in
+fp64 torch, so torch.autograd on it is the reference gradient.  Bars: data gradients within 1e-2
+relative L2, sign agreement >= 99 % (what FGSM consumes); per layer the kernels do much better, so the per-layer
+bars here are 2e-4 for the mean gradient of a pure GEMM and 5e-3 where the bf16 variance-gradient plane enters.
+"""
+import pytest
+import torch
+
+from oracle import supernet_oracle as O
+
+pytestmark = pytest.mark.gpu
+
+G_TOL = 5e-3
+
+
+@pytest.fixture(scope="module")
+def S():
+    import supernet_b200 as S_
+    lib = S_._lib.load()
+    assert lib.sn_device_check() == 0
+    from supernet_b200 import fastops  # noqa: F401
+    return S_
+
+
+def dev(t):
+    return t.to(torch.float32).cuda().contiguous()
+
+
+def rel(a, b):
+    return O.rel_l2(a.detach().cpu(), b.detach().cpu())
+
+
+def rnd(shape, seed, scale=1.0, positive=False):
+    g = torch.Generator().manual_seed(seed)
+    t = (torch.rand(shape, generator=g, dtype=torch.float64) if positive
+         else torch.randn(shape, generator=g, dtype=torch.float64)) * scale
+    return t.float().double()
+
+
+def layer(B, H, W, cin, cout, k, seed):
+    mu = rnd((B, H, W, cin), seed)
+    var = rnd((B, H, W, cin), seed + 1, positive=True)
+    w = rnd((k, k, cin, cout), seed + 2, 0.1)
+    ws = torch.empty(cout, dtype=torch.float64).uniform_(-6, -2, generator=torch.Generator().manual_seed(seed + 3))
+    return mu, var, w, ws.float().double()
+
+
+DGRAD_CASES = [
+    # B, H, W, cin, cout, k
+    (2, 10, 9, 32, 32, 3),
+    (3, 12, 14, 64, 32, 3),     # cin != cout
+    (1, 20, 20, 128, 128, 3),   # NT = 128
+    (2, 9, 9, 256, 64, 3),      # two N tiles of 128, K = 9 x 64
+    (2, 11, 13, 32, 64, 1),     # 1x1
+    (2, 7, 8, 64, 32, 2),       # plain k = 2
+    (9, 8, 8, 64, 64, 3),       # tiny images: several zero-extended gradients per 128-row tile
+    (2, 70, 150, 32, 32, 3),    # column tiles, resident weights
+    (40, 30, 30, 32, 64, 3),    # many tiles per persistent CTA
+    (20, 24, 24, 128, 128, 3),  # streamed weights, NT = 128
+]
+
+
+@pytest.mark.parametrize("case", DGRAD_CASES)
+@pytest.mark.parametrize("gate", [False, True])
+def test_conv_dgrad_tc(S, case, gate):
+    F = S.fastops
+    B, H, W, cin, cout, k = case
+    mu_pre, var_pre, w, ws = layer(B, H, W, cin, cout, k, seed=sum(case))
+    Ho, Wo = H - k + 1, W - k + 1
+    gm = rnd((B, Ho, Wo, cout), 77)
+    gv = rnd((B, Ho, Wo, cout), 78)
+    mu_pre.requires_grad_(True)
+    var_pre.requires_grad_(True)
+    mu, var = O.relu(mu_pre, var_pre) if gate else (mu_pre, var_pre)
+    m_out, v_out = O.conv_intermediate_conv_form(mu, var, w, ws)
+    ((m_out * gm).sum() + (v_out * gv).sum()).backward()
+    saved = F.PackedView(F.pack_moments(dev(mu), dev(var)))
+    g_out = F.PackedView(F.pack_moments(dev(gm), dev(gv)))
+    g_in = F.packed_empty(B, H, W, cin, "cuda")
+    g_in.fill_(float("nan"))
+    wt = F.prepare_weights_bwd(dev(w))
+    _, s = F.prepare_weights(dev(w), dev(ws))
+    F.conv_moments_bwd_data_tc(g_out, B, H, W, k, cout, wt, s, saved, F.PackedView(g_in), cin, gate)
+    a, b = F.unpack_moments(g_in)
+    torch.cuda.synchronize()
+    assert bool(torch.isfinite(a).all()) and bool(torch.isfinite(b).all())
+    e_m, e_v = rel(a, mu_pre.grad), rel(b, var_pre.grad)
+    print(case, gate, e_m, e_v)
+    assert e_m < G_TOL and e_v < G_TOL, (e_m, e_v)
+    if gate:
+        off = (mu_pre.detach() <= 0)
+        assert float(a.cpu()[off].abs().max()) == 0.0 and float(b.cpu()[off].abs().max()) == 0.0
+
+
+def test_conv_dgrad_tc_concat_windows(S):
+    """Two forward sources (padded decoder window: no gate; cropped encoder window: gated), gradient read from the
+    interior of a padded buffer -- the address arithmetic that replaces the adjoints of mypadding / crop / myConc."""
+    F = S.fastops
+    B, H, W, k, cout = 2, 10, 12, 3, 64
+    mu_d, var_d, _, _ = layer(B, H, W, 64, cout, k, seed=5)
+    mu_e_pre, var_e_pre, _, _ = layer(B, H + 4, W + 4, 32, cout, k, seed=6)
+    _, _, w, ws = layer(B, H, W, 96, cout, k, seed=7)
+    for t in (mu_d, var_d, mu_e_pre, var_e_pre):
+        t.requires_grad_(True)
+    mu_e, var_e = O.relu(mu_e_pre, var_e_pre)
+    m_in, v_in = O.conc(mu_d, var_d, mu_e, var_e)
+    m_out, v_out = O.conv_intermediate_conv_form(m_in, v_in, w, ws)
+    gm, gv = rnd(tuple(m_out.shape), 8), rnd(tuple(m_out.shape), 9)
+    ((m_out * gm).sum() + (v_out * gv).sum()).backward()
+    dbuf = F.packed_empty(B, H + 3, W + 5, 64, "cuda")
+    F.packed_fill(dbuf, 7.0)
+    dbuf[:, 1:1 + H, 2:2 + W] = F.pack_moments(dev(mu_d), dev(var_d))
+    ebuf = F.pack_moments(dev(mu_e), dev(var_e))
+    gbuf = F.packed_empty(B, H - 2 + 4, W - 2 + 4, cout, "cuda")      # the forward's padded destination
+    gbuf.fill_(3.0)                                                   # border content must not leak in
+    gbuf[:, 2:-2, 2:-2] = F.pack_moments(dev(gm), dev(gv))
+    gd = torch.zeros_like(dbuf)
+    ge = torch.zeros_like(ebuf)
+    wt = F.prepare_weights_bwd(dev(w))
+    _, s = F.prepare_weights(dev(w), dev(ws))
+    F.conv_moments_bwd_data_tc(F.PackedView(gbuf, 2, 2, 0), B, H, W, k, cout, wt, s,
+                               F.PackedView(dbuf, 1, 2, 0), F.PackedView(gd, 1, 2, 0), 64, False,
+                               in1=F.PackedView(ebuf, 2, 2, 0), g_in1=F.PackedView(ge, 2, 2, 0), c1=32, gate1=True)
+    a_d, b_d = F.unpack_moments(gd)
+    a_e, b_e = F.unpack_moments(ge)
+    assert rel(a_d[:, 1:1 + H, 2:2 + W], mu_d.grad) < G_TOL and rel(b_d[:, 1:1 + H, 2:2 + W], var_d.grad) < G_TOL
+    assert rel(a_e, mu_e_pre.grad) < G_TOL and rel(b_e, var_e_pre.grad) < G_TOL      # zero outside the crop window
+    assert float(a_d[:, 0].abs().max()) == 0.0                                        # untouched outside the window
+
+
+@pytest.mark.parametrize("case", [(2, 6, 6, 64, 32), (1, 9, 7, 128, 64), (2, 5, 5, 256, 128), (3, 30, 41, 64, 32)])
+def test_upconv_dgrad_tc(S, case):
+    """Adjoint of unpool + 2x2 VALID conv (Brats.py:178-203,414-415), gradient read from the interior of the
+    [3,3]-padded buffer the forward writes."""
+    F = S.fastops
+    B, H, W, cin, cout = case
+    mu_pre, var_pre, w, ws = layer(B, H, W, cin, cout, 2, seed=sum(case))
+    mu_pre.requires_grad_(True)
+    var_pre.requires_grad_(True)
+    mu, var = O.relu(mu_pre, var_pre)
+    m_out, v_out = O.conv_intermediate_conv_form(*O.upsampling(mu, var), w, ws)
+    gm, gv = rnd(tuple(m_out.shape), 11), rnd(tuple(m_out.shape), 12)
+    ((m_out * gm).sum() + (v_out * gv).sum()).backward()
+    gbuf = F.packed_empty(B, 2 * H + 6, 2 * W + 6, cout, "cuda")
+    gbuf.fill_(5.0)
+    gbuf[:, 3:-3, 3:-3] = F.pack_moments(dev(gm), dev(gv))
+    saved = F.PackedView(F.pack_moments(dev(mu), dev(var)))
+    g_in = F.packed_empty(B, H, W, cin, "cuda")
+    wt = F.prepare_weights_bwd(dev(w), upconv=True)
+    _, s = F.prepare_weights(dev(w), dev(ws), upconv=True)
+    F.conv_moments_bwd_data_tc(F.PackedView(gbuf, 3, 3, 0), B, H, W, 2, cout, wt, s, saved, F.PackedView(g_in), cin,
+                               True, upconv=True)
+    a, b = F.unpack_moments(g_in)
+    e_m, e_v = rel(a, mu_pre.grad), rel(b, var_pre.grad)
+    print(case, e_m, e_v)
+    assert e_m < G_TOL and e_v < G_TOL, (e_m, e_v)
+
+
+@pytest.mark.parametrize("shape", [(2, 10, 12, 32), (1, 9, 7, 64)])
+def test_maxpool_bwd_packed(S, shape):
+    F = S.fastops
+    B, H, W, c = shape
+    mu = rnd(shape, 21).clamp_min(0).float()
+    var = rnd(shape, 22, positive=True).float() * (mu > 0)
+    buf = F.pack_moments(dev(mu), dev(var))
+    m_s, v_s = [t.cpu().double().requires_grad_(True) for t in F.unpack_moments(buf)]   # the values the kernels see
+    pm, pv = O.maxpooling(m_s, v_s)
+    gm, gv = rnd(tuple(pm.shape), 23), rnd(tuple(pm.shape), 24)
+    ((pm * gm).sum() + (pv * gv).sum()).backward()
+    g_out = F.PackedView(F.pack_moments(dev(gm), dev(gv)))
+    # plain overwrite
+    g_in = F.packed_empty(B, H, W, c, "cuda")
+    g_in.fill_(float("nan"))
+    F.maxpool2_bwd_packed(F.PackedView(buf), B, H, W, c, g_out, F.PackedView(g_in))
+    a, b = F.unpack_moments(g_in)
+    assert rel(a, m_s.grad) < 2e-5 and rel(b, v_s.grad) < 4e-3
+    assert bool(((a.cpu() != 0) == (m_s.grad != 0)).all())          # routing is exact
+    # accumulate inside a keep window (the decoder's crop of the skip tensor)
+    prev_m, prev_v = rnd(shape, 25), rnd(shape, 26)
+    g_in2 = F.pack_moments(dev(prev_m), dev(prev_v))
+    keep = (1, 2, H - 3, W - 4)
+    F.maxpool2_bwd_packed(F.PackedView(buf), B, H, W, c, g_out, F.PackedView(g_in2), keep)
+    mask = torch.zeros(shape, dtype=torch.float64)
+    mask[:, keep[0]:keep[0] + keep[2], keep[1]:keep[1] + keep[3]] = 1
+    a2, b2 = F.unpack_moments(g_in2)
+    assert rel(a2, m_s.grad + mask * prev_m) < 1e-4 and rel(b2, v_s.grad + mask * prev_v) < 5e-3
+
+
+@pytest.mark.parametrize("C", [3, 4, 5])
+@pytest.mark.parametrize("clip", [(-1e4, 1e3), (1e-12, 1e3)])
+def test_head_bwd_packed(S, C, clip):
+    """NLL -> softmax Jacobian -> conv_final -> ReLU gate in one kernel vs autograd on the oracle."""
+    F = S.fastops
+    B, H, W, cin = 2, 9, 11, 32
+    mu_pre, var_pre, w, ws = layer(B, H, W, cin, C, 1, seed=40 + C)
+    mu_pre = mu_pre * 0.5
+    y = O.make_labels(B, H * W, C, dtype=torch.float64)
+    buf = F.pack_moments(dev(torch.relu(mu_pre)), dev(var_pre * (mu_pre > 0)))
+    m_s, v_s = [t.cpu().double() for t in F.unpack_moments(buf)]
+    m_pre = torch.where(mu_pre > 0, m_s, mu_pre).requires_grad_(True)   # pre-ReLU tensor whose ReLU is what is stored
+    v_pre = torch.where(mu_pre > 0, v_s, var_pre).requires_grad_(True)
+    mf, sf = O.conv_intermediate_conv_form(*O.relu(m_pre, v_pre), w, ws)
+    p, vo = O.softmax_as_written(mf, sf)
+    loss = 0.5 * O.nll_gaussian(y, p, torch.clamp(vo, clip[0], clip[1]))
+    loss.backward()
+    p32, vo32 = dev(p.detach()), dev(vo.detach())
+    acc = torch.zeros(2, device="cuda", dtype=torch.float64)
+    lossb = torch.zeros(1, device="cuda")
+    F.nll_gaussian_fwd(dev(y), p32, vo32, clip, acc, lossb)
+    assert abs(0.5 * float(lossb) - float(loss)) < 1e-4 * abs(float(loss))
+    g_in = F.packed_empty(B, H, W, cin, "cuda")
+    F.head_bwd_packed(F.PackedView(buf), B, H, W, cin, dev(w), dev(ws), dev(y), clip, acc, 0.5, F.PackedView(g_in))
+    a, b = F.unpack_moments(g_in)
+    e_m, e_v = rel(a, m_pre.grad), rel(b, v_pre.grad)
+    print(C, clip, e_m, e_v)
+    assert e_m < 1e-4 and e_v < G_TOL, (e_m, e_v)
+
+
+@pytest.mark.parametrize("cin", [4, 1])
+def test_first_conv_bwd_packed(S, cin):
+    F = S.fastops
+    B, H, W, cout = 2, 12, 14, 32
+    x = rnd((B, H, W, cin), 50, positive=True).requires_grad_(True)
+    _, _, w, ws = layer(B, H, W, cin, cout, 3, seed=51)
+    m_out, v_out = O.conv_input_conv_form(x, w, ws)
+    gm, gv = rnd(tuple(m_out.shape), 52), rnd(tuple(m_out.shape), 53)
+    ((m_out * gm).sum() + (v_out * gv).sum()).backward()
+    g_out = F.PackedView(F.pack_moments(dev(gm), dev(gv)))
+    gx = torch.empty(B, H, W, cin, device="cuda")
+    F.first_conv_bwd_data_packed(dev(x), dev(w), dev(ws), g_out, gx)
+    assert rel(gx, x.grad) < G_TOL, rel(gx, x.grad)
+
+
+# ------------------------------------------------------------------------------------------------------------
+# whole network: create_adversarial_pattern (Brats.py:582-596) through mode='fast'
+# ------------------------------------------------------------------------------------------------------------
+def _fgsm_fast_vs_oracle(S, variant, C, in_ch, B, alpha):
+    oracle = O.UNetOracle(variant, 32, C, in_ch, torch.float64)
+    w32 = O.make_weights(variant, 32, C, in_ch)
+    model = S.Density_prop_with_pad_UNET(32, C, variant=variant, mode="fast").load_weight_dict(w32, device="cuda")
+    x = O.make_input(variant, B, alpha=alpha)
+    hw = O.output_hw(variant)
+    y = O.make_labels(B, hw * hw, C, dtype=torch.float64)
+    g_ref, loss_ref = oracle.fgsm_gradient(x, y)
+    sign, g = S.create_adversarial_pattern(model, dev(x), dev(y))
+    sign2, g2 = S.create_adversarial_pattern(model, dev(x), dev(y))      # second call replays the CUDA graph
+    torch.cuda.synchronize()
+    assert torch.equal(g, g2)
+    loss, _ = model.input_gradient_fast(dev(x), dev(y))
+    big = g_ref.abs() > 1e-3 * g_ref.abs().max()
+    agree = float((torch.sign(g_ref)[big] == sign.cpu().double()[big]).double().mean())
+    err = rel(g, g_ref)
+    print(variant, "input-gradient rel", err, "sign agreement", agree, "loss", float(loss), float(loss_ref))
+    assert g.shape == x.shape and bool(torch.isfinite(g).all())
+    assert abs(float(loss) - float(loss_ref)) < 2e-3 * abs(float(loss_ref))
+    assert err < 1e-2, err
+    assert agree >= 0.99, agree
+
+
+def test_hippocampus_fgsm_fast(S):
+    _fgsm_fast_vs_oracle(S, "hippocampus", 3, 1, 4, 1.0)
+
+
+def test_brats_fgsm_fast(S):
+    _fgsm_fast_vs_oracle(S, "brats", 4, 4, 1, O.BRATS_ALPHA)
