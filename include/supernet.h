@@ -28,7 +28,7 @@
 extern "C" {
 #endif
 
-#define SN_ABI_VERSION 1
+#define SN_ABI_VERSION 2
 
 typedef void* sn_stream_t; /* cudaStream_t */
 
@@ -195,6 +195,8 @@ typedef struct sn_tc_conv_desc {
   sn_packed_view dst;
   float* dst_mu;
   float* dst_var;
+  float* rsum_out;        /* optional fp32 [batch, Ho, Wo] (SN_TC_UPCONV: [batch, in_h, in_w]): the rank-1 statistic
+                             box_k(sum_c mu^2 + var) per pixel, which sn_conv_moments_bwd_weight_tc needs; may be NULL */
 } sn_tc_conv_desc;
 int sn_conv_moments_fwd_tc(const sn_tc_conv_desc* d, sn_stream_t st);
 
@@ -246,6 +248,30 @@ typedef struct sn_tc_dgrad_desc {
   const float* s;                                /* softplus(w_sigma) [cout] */
 } sn_tc_dgrad_desc;
 int sn_conv_moments_bwd_data_tc(const sn_tc_dgrad_desc* d, sn_stream_t st);
+
+/* Weight gradient of sn_conv_moments_fwd_tc on the tensor cores (train_on_batch, Brats.py:569-580):
+ *   g_w_mu = corr(mu_in, g_mu_out) + 2 W . corr(var_in, g_var_out);  g_w_sigma[n] = sigmoid(w_sigma[n]) sum_p g_var_out[p,n] rsum[p].
+ * Two pixel-axis GEMMs (tcgen05, MN-major operands straight from the NHWC planes, split-K with fp32 atomics into
+ * `workspace`, sn_wgrad_workspace_bytes() bytes, zeroed by the call), then a finalize pass.  Outputs are overwritten.
+ * in[]/in_c[]/g_out/flags as in sn_tc_dgrad_desc; rsum = the forward's rsum_out; w_mu HWIO fp32, w_sigma raw. */
+typedef struct sn_tc_wgrad_desc {
+  sn_packed_view g_out;
+  sn_packed_view in[2];
+  int32_t in_c[2];
+  int32_t batch, in_h, in_w, ksize, cout, flags;
+  const float* rsum;
+  const float* w_mu;
+  const float* w_sigma;
+  void* workspace;
+  float* g_w_mu;
+  float* g_w_sigma;
+} sn_tc_wgrad_desc;
+size_t sn_wgrad_workspace_bytes(int32_t ksize, int32_t cin, int32_t cout);
+int sn_conv_moments_bwd_weight_tc(const sn_tc_wgrad_desc* d, sn_stream_t st);
+/* rsum[b,y,x] = sum over the k x k window and the channels of x^2: myConv_input's rank-1 statistic (Brats.py:69-73),
+ * the `rsum` argument of sn_conv_moments_bwd_weight for the first layer. */
+int sn_first_conv_rsum(int32_t batch, int32_t in_h, int32_t in_w, int32_t cin, int32_t ksize, const float* x,
+                       float* rsum, sn_stream_t st);
 
 /* Adjoint of sn_maxpool2_packed (Brats.py:171-174,206-216): routes g_out (ceil(in_h/2) x ceil(in_w/2) x c) to the
  * arg-max position recomputed from the saved pool input `in` (first maximum in row-major window order).  g_in

@@ -39,7 +39,7 @@ class sn_tc_conv_desc(C.Structure):
                 ("batch", C.c_int32), ("in_h", C.c_int32), ("in_w", C.c_int32), ("ksize", C.c_int32),
                 ("cout", C.c_int32), ("flags", C.c_int32),
                 ("w_packed", C.c_void_p), ("s", C.c_void_p),
-                ("dst", sn_packed_view), ("dst_mu", C.c_void_p), ("dst_var", C.c_void_p)]
+                ("dst", sn_packed_view), ("dst_mu", C.c_void_p), ("dst_var", C.c_void_p), ("rsum_out", C.c_void_p)]
 
 
 class sn_tc_dgrad_desc(C.Structure):
@@ -48,6 +48,14 @@ class sn_tc_dgrad_desc(C.Structure):
                 ("batch", C.c_int32), ("in_h", C.c_int32), ("in_w", C.c_int32), ("ksize", C.c_int32),
                 ("cout", C.c_int32), ("flags", C.c_int32),
                 ("wt_packed", C.c_void_p), ("s", C.c_void_p)]
+
+
+class sn_tc_wgrad_desc(C.Structure):
+    _fields_ = [("g_out", sn_packed_view), ("in_", sn_packed_view * 2), ("in_c", C.c_int32 * 2),
+                ("batch", C.c_int32), ("in_h", C.c_int32), ("in_w", C.c_int32), ("ksize", C.c_int32),
+                ("cout", C.c_int32), ("flags", C.c_int32),
+                ("rsum", C.c_void_p), ("w_mu", C.c_void_p), ("w_sigma", C.c_void_p), ("workspace", C.c_void_p),
+                ("g_w_mu", C.c_void_p), ("g_w_sigma", C.c_void_p)]
 
 
 SN_CONV_RELU = 1
@@ -84,9 +92,10 @@ def load(build_if_missing: bool = True) -> C.CDLL:
     lib.sn_version.restype = C.c_int
     for name in declared_symbols():
         fn = getattr(lib, name)  # AttributeError here == header/library mismatch
-        if name not in ("sn_last_error", "sn_packed_bytes", "sn_prepared_weight_bytes", "sn_conv_workspace_bytes"):
+        if name not in ("sn_last_error", "sn_packed_bytes", "sn_prepared_weight_bytes", "sn_conv_workspace_bytes",
+                        "sn_wgrad_workspace_bytes"):
             fn.restype = C.c_int
-    for name in ("sn_packed_bytes", "sn_prepared_weight_bytes"):
+    for name in ("sn_packed_bytes", "sn_prepared_weight_bytes", "sn_wgrad_workspace_bytes"):
         if hasattr(lib, name):
             getattr(lib, name).restype = C.c_size_t
     _LIB = lib

@@ -5,6 +5,8 @@
 // the saved forward activations.  Formulas: SURVEY.md A.3 (what tf.GradientTape derives at Brats.py:578,593).
 #include "sn_common.cuh"
 
+#include <mutex>
+
 namespace sn {
 
 __device__ __forceinline__ float b_lo(uint32_t v) { return __uint_as_float(v << 16); }
@@ -340,6 +342,142 @@ __global__ void __launch_bounds__(128) first_conv_bwd_kernel(int B, int H, int W
   }
 }
 
+// Specialisation for the shapes the two networks use (k = 3, 32 gradient channels, Cin = 4 or 1).  A block owns a
+// 32 x 8 tile of input pixels; the (32+2) x (8+2) gradient pixels it touches are read once with fully coalesced
+// 16-byte loads (one pixel = 192 contiguous bytes), combined to fp32 (g_mean = hi + lo; t = sum_n g_var_n s_n)
+// and staged in shared memory (rows padded to 36 floats: conflict-free 16-byte reads).  Each thread then
+// accumulates 2 pixels x 9 taps x 32 channels x CIN with the transposed weights broadcast from shared memory.
+constexpr int FB_TW = 32, FB_TH = 8, FB_THREADS = 128, FB_ROW = 36;
+constexpr int FB_GW = FB_TW + 2, FB_GH = FB_TH + 2;
+
+template <int CIN>
+__global__ void __launch_bounds__(FB_THREADS) first_conv_bwd_k3c32_kernel(int B, int H, int W,
+                                                                          const float* __restrict__ x,
+                                                                          const float* __restrict__ w,
+                                                                          const float* __restrict__ ws,
+                                                                          sn_packed_view gout, float* __restrict__ gx,
+                                                                          int tiles_x, int tiles_y) {
+  constexpr int COUT = 32;
+  extern __shared__ __align__(16) float bsm[];
+  float* sg = bsm;                                   // [FB_GH * FB_GW][FB_ROW] g_mean
+  float* st = sg + FB_GH * FB_GW * FB_ROW;           // [FB_GH * FB_GW] t
+  float* sw = st + ((FB_GH * FB_GW + 3) & ~3);       // [9][COUT][CIN]
+  float* ss = sw + 9 * COUT * CIN;                   // [COUT]
+  for (int i = threadIdx.x; i < 9 * COUT * CIN; i += FB_THREADS) {
+    const int ci = i % CIN;
+    const int n = (i / CIN) % COUT;
+    const int tap = i / (CIN * COUT);
+    sw[i] = w[((size_t)tap * CIN + ci) * COUT + n];
+  }
+  if (threadIdx.x < COUT) ss[threadIdx.x] = softplus_f(ws[threadIdx.x]);
+  __syncthreads();
+  const int Ho = H - 2, Wo = W - 2;
+  const __nv_bfloat16* go = reinterpret_cast<const __nv_bfloat16*>(gout.base);
+  const int total_tiles = B * tiles_y * tiles_x;
+  for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
+    const int tx = tile % tiles_x;
+    const int ty = (tile / tiles_x) % tiles_y;
+    const int b = tile / (tiles_x * tiles_y);
+    const int x0 = tx * FB_TW, y0 = ty * FB_TH;
+    // ---- stage the gradient tile: chunk = (pixel, 8 channels); gradient pixel (y0 - 2 + gy, x0 - 2 + gxx)
+    constexpr int CHUNKS = FB_GH * FB_GW * 4;
+    for (int c = threadIdx.x; c < ((CHUNKS + FB_THREADS - 1) / FB_THREADS) * FB_THREADS; c += FB_THREADS) {
+      const bool live = c < CHUNKS;                 // whole warps stay in the loop: the shuffles below need them
+      const int pix = live ? c >> 2 : 0, part = c & 3;
+      const int gy = pix / FB_GW, gxx = pix - gy * FB_GW;
+      const int oy = y0 - 2 + gy, ox = x0 - 2 + gxx;
+      float m[8], tpart = 0.f;
+      if (live && oy >= 0 && oy < Ho && ox >= 0 && ox < Wo) {
+        const __nv_bfloat16* gp = go + pv_off(gout, b, oy, ox) + part * 8;
+        float h[8], l[8], v[8];
+        b_unpack8(*reinterpret_cast<const uint4*>(gp), h);
+        b_unpack8(*reinterpret_cast<const uint4*>(gp + gout.c), l);
+        b_unpack8(*reinterpret_cast<const uint4*>(gp + 2 * gout.c), v);
+#pragma unroll
+        for (int e = 0; e < 8; ++e) {
+          m[e] = h[e] + l[e];
+          tpart = fmaf(v[e], ss[part * 8 + e], tpart);
+        }
+      } else {
+#pragma unroll
+        for (int e = 0; e < 8; ++e) m[e] = 0.f;
+      }
+      if (live) {
+        float* d = sg + pix * FB_ROW + part * 8;
+        *reinterpret_cast<float4*>(d) = make_float4(m[0], m[1], m[2], m[3]);
+        *reinterpret_cast<float4*>(d + 4) = make_float4(m[4], m[5], m[6], m[7]);
+      }
+      // the four parts of a pixel sit in four consecutive lanes
+      tpart += __shfl_xor_sync(0xffffffffu, tpart, 1);
+      tpart += __shfl_xor_sync(0xffffffffu, tpart, 2);
+      if (live && part == 0) st[pix] = tpart;
+    }
+    __syncthreads();
+    // ---- thread = 2 input pixels (rows ly and ly + 4 of the tile, column lx)
+    const int lx = threadIdx.x & 31, ly = threadIdx.x >> 5;
+    float acc[2][CIN];
+    float T[2] = {0.f, 0.f};
+#pragma unroll
+    for (int q = 0; q < 2; ++q)
+#pragma unroll
+      for (int c = 0; c < CIN; ++c) acc[q][c] = 0.f;
+#pragma unroll
+    for (int kh = 0; kh < 3; ++kh)
+#pragma unroll
+      for (int kw = 0; kw < 3; ++kw) {
+        // input pixel (y, x) reads gradient pixel (y - kh, x - kw) = staged (ly + 2 - kh, lx + 2 - kw)
+        const float* wt = sw + (kh * 3 + kw) * COUT * CIN;
+        const int p0 = (ly + 2 - kh) * FB_GW + lx + 2 - kw;
+        const int p1 = p0 + 4 * FB_GW;
+        T[0] += st[p0];
+        T[1] += st[p1];
+        const float* g0 = sg + p0 * FB_ROW;
+        const float* g1 = sg + p1 * FB_ROW;
+#pragma unroll
+        for (int n4 = 0; n4 < COUT; n4 += 4) {
+          const float4 a = *reinterpret_cast<const float4*>(g0 + n4);
+          const float4 bq = *reinterpret_cast<const float4*>(g1 + n4);
+          const float av[4] = {a.x, a.y, a.z, a.w}, bv[4] = {bq.x, bq.y, bq.z, bq.w};
+#pragma unroll
+          for (int e = 0; e < 4; ++e) {
+            if constexpr (CIN == 4) {
+              const float4 wv = *reinterpret_cast<const float4*>(wt + (n4 + e) * 4);
+              acc[0][0] = fmaf(av[e], wv.x, acc[0][0]); acc[0][1] = fmaf(av[e], wv.y, acc[0][1]);
+              acc[0][2] = fmaf(av[e], wv.z, acc[0][2]); acc[0][3] = fmaf(av[e], wv.w, acc[0][3]);
+              acc[1][0] = fmaf(bv[e], wv.x, acc[1][0]); acc[1][1] = fmaf(bv[e], wv.y, acc[1][1]);
+              acc[1][2] = fmaf(bv[e], wv.z, acc[1][2]); acc[1][3] = fmaf(bv[e], wv.w, acc[1][3]);
+            } else {
+#pragma unroll
+              for (int c = 0; c < CIN; ++c) {
+                const float wv = wt[(n4 + e) * CIN + c];
+                acc[0][c] = fmaf(av[e], wv, acc[0][c]);
+                acc[1][c] = fmaf(bv[e], wv, acc[1][c]);
+              }
+            }
+          }
+        }
+      }
+#pragma unroll
+    for (int q = 0; q < 2; ++q) {
+      const int yy = y0 + ly + 4 * q, xx = x0 + lx;
+      if (yy < H && xx < W) {
+        const size_t i = ((size_t)b * H + yy) * W + xx;
+        if constexpr (CIN == 4) {
+          const float4 xv = *reinterpret_cast<const float4*>(x + i * 4);
+          const float t2 = 2.f * T[q];
+          *reinterpret_cast<float4*>(gx + i * 4) =
+              make_float4(fmaf(xv.x, t2, acc[q][0]), fmaf(xv.y, t2, acc[q][1]), fmaf(xv.z, t2, acc[q][2]),
+                          fmaf(xv.w, t2, acc[q][3]));
+        } else {
+#pragma unroll
+          for (int c = 0; c < CIN; ++c) gx[i * CIN + c] = fmaf(2.f * x[i * CIN + c], T[q], acc[q][c]);
+        }
+      }
+    }
+    __syncthreads();
+  }
+}
+
 static int check_pv(const sn_packed_view* v, int batch, int h, int w, int c, const char* who) {
   SN_REQUIRE(v && v->base && aligned16(v->base), SN_ERR_BAD_ARG, "%s: null/misaligned packed view", who);
   SN_REQUIRE(v->n >= batch && v->c % 8 == 0 && v->c0 % 8 == 0 && c % 8 == 0, SN_ERR_MISALIGNED,
@@ -416,6 +554,24 @@ int sn_first_conv_bwd_data_packed(int32_t batch, int32_t in_h, int32_t in_w, int
   SN_REQUIRE(cout % 8 == 0 && cout <= 256, SN_ERR_UNSUPPORTED, "first_conv_bwd: cout %d", cout);
   int rc = check_pv(g_out, batch, in_h - ksize + 1, in_w - ksize + 1, cout, "first_conv_bwd g_out");
   if (rc) return rc;
+  if (ksize == 3 && cout == 32 && (cin == 4 || cin == 1) && aligned16(x) && aligned16(g_x)) {
+    const int tiles_x = (in_w + FB_TW - 1) / FB_TW, tiles_y = (in_h + FB_TH - 1) / FB_TH;
+    const size_t fb_smem = ((size_t)FB_GH * FB_GW * FB_ROW + ((FB_GH * FB_GW + 3) & ~3) + 9 * 32 * cin + 32) * sizeof(float);
+    static std::once_flag fb_once;
+    std::call_once(fb_once, [] {
+      cudaFuncSetAttribute(first_conv_bwd_k3c32_kernel<4>, cudaFuncAttributeMaxDynamicSharedMemorySize, 64 * 1024);
+      cudaFuncSetAttribute(first_conv_bwd_k3c32_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, 64 * 1024);
+    });
+    const long long tiles = (long long)batch * tiles_x * tiles_y;
+    const int grid = (int)(tiles < (long long)num_sms() * 3 ? tiles : (long long)num_sms() * 3);
+    if (cin == 4)
+      first_conv_bwd_k3c32_kernel<4><<<grid, FB_THREADS, fb_smem, as_stream(st)>>>(batch, in_h, in_w, x, w_mu, w_sigma,
+                                                                                   *g_out, g_x, tiles_x, tiles_y);
+    else
+      first_conv_bwd_k3c32_kernel<1><<<grid, FB_THREADS, fb_smem, as_stream(st)>>>(batch, in_h, in_w, x, w_mu, w_sigma,
+                                                                                   *g_out, g_x, tiles_x, tiles_y);
+    return check_launch("first_conv_bwd_k3c32");
+  }
   const size_t total = (size_t)batch * in_h * in_w;
   const size_t smem = ((size_t)ksize * ksize * cout * cin + cout) * sizeof(float);
   SN_REQUIRE(smem <= 48 * 1024, SN_ERR_UNSUPPORTED, "first_conv_bwd: weights do not fit shared memory");

@@ -425,6 +425,7 @@ extern "C" int sn_conv_moments_fwd_tc(const sn_tc_conv_desc* d, sn_stream_t st) 
   }
 
   if (!(d->flags & SN_TC_IM2COL)) return conv_moments_halo_dispatch(d, as_stream(st));
+  SN_REQUIRE(d->rsum_out == nullptr, SN_ERR_UNSUPPORTED, "conv_tc: rsum_out needs the halo kernel (no SN_TC_IM2COL)");
 
   const int nt = d->cout % 128 == 0 ? 128 : (d->cout % 64 == 0 ? 64 : 32);
   const int groups = upconv ? 4 : 1;

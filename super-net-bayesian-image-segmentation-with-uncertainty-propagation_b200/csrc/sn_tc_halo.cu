@@ -71,6 +71,7 @@ struct HlP {
   float* dst_var;
   int out_h, out_w;
   const float* s;
+  float* r_out;            // optional: box_k(sum_c mu^2 + var) per valid pixel, fp32 [B][Ho][Wo]
   int s_len;               // forward: cout; data gradient: channels of one gradient source
   // data gradient only: destination / saved-activation windows of the two forward sources
   HlView gdst[2], saved[2];
@@ -402,6 +403,8 @@ __global__ void __launch_bounds__(HL_THREADS, 1) conv_moments_halo_kernel(const 
         const int gcol0 = nt_i * NT + half * NH;               // first column (parity group, channel) of this warp
         const int ox_i = tx * p.TWo + x, oy_i = ty * p.THo + y, ob = tb * p.TN + n;
         const bool valid = x < p.TWo && y < p.THo && n < p.TN && ox_i < p.Wo && oy_i < p.Ho && ob < p.B;
+        if (!DGRAD && p.r_out != nullptr && half == 0 && nt_i == 0 && valid)
+          p.r_out[((size_t)ob * p.Ho + oy_i) * p.Wo + ox_i] = r;
         ptx::mbar_wait(acc_full(as), par);
         ptx::tc_fence_after();
         const uint32_t lane_base = tmem_base + ((uint32_t)(q * 32) << 16) + as * ACC_STAGE + half * NH;
@@ -756,6 +759,7 @@ int conv_moments_halo_dispatch(const sn_tc_conv_desc* d, cudaStream_t stream) {
   p.dh = d->dst.h; p.dw = d->dst.w; p.dc = d->dst.c; p.dy0 = d->dst.y0; p.dx0 = d->dst.x0; p.dc0 = d->dst.c0;
   p.dst_mu = d->dst_mu; p.dst_var = d->dst_var; p.out_h = out_h; p.out_w = out_w;
   p.s = d->s; p.s_len = d->cout;
+  p.r_out = d->rsum_out;
 
   HlMaps maps;
   for (int s = 0; s < 2; ++s) {

@@ -14,7 +14,7 @@ import torch
 
 from . import _lib
 from ._lib import (SN_TC_DST_F32, SN_TC_IM2COL, SN_TC_RELU, SN_TC_UPCONV, check, ptr, sn_packed_view, sn_tc_conv_desc,
-                   sn_tc_dgrad_desc, stream_ptr)
+                   sn_tc_dgrad_desc, sn_tc_wgrad_desc, stream_ptr)
 
 Tensor = torch.Tensor
 
@@ -74,7 +74,8 @@ def prepare_weights(w_mu: Tensor, w_sigma: Tensor, upconv: bool = False) -> Tupl
 def conv_moments_tc(src0: PackedView, c0: int, batch: int, in_h: int, in_w: int, ksize: int, cout: int,
                     w_packed: Tensor, s: Tensor, dst: Optional[PackedView] = None, relu: bool = False,
                     upconv: bool = False, src1: Optional[PackedView] = None, c1: int = 0,
-                    dst_f32: Optional[Tuple[Tensor, Tensor]] = None, im2col: bool = False) -> None:
+                    dst_f32: Optional[Tuple[Tensor, Tensor]] = None, im2col: bool = False,
+                    rsum_out: Optional[Tensor] = None) -> None:
     d = sn_tc_conv_desc()
     d.src[0] = src0.c_view()
     d.src[1] = (src1 if src1 is not None else src0).c_view()
@@ -84,6 +85,8 @@ def conv_moments_tc(src0: PackedView, c0: int, batch: int, in_h: int, in_w: int,
                (SN_TC_IM2COL if im2col else 0))
     d.w_packed = w_packed.data_ptr()
     d.s = s.data_ptr()
+    if rsum_out is not None:
+        d.rsum_out = rsum_out.data_ptr()
     if dst_f32 is not None:
         d.dst_mu, d.dst_var = dst_f32[0].data_ptr(), dst_f32[1].data_ptr()
     else:
@@ -174,3 +177,30 @@ def nll_gaussian_fwd(y: Tensor, p: Tensor, var: Tensor, clip: Tuple[float, float
     rows, c = p.numel() // p.shape[-1], p.shape[-1]
     check(_lib.load().sn_nll_gaussian_fwd(C.c_size_t(rows), c, ptr(y), ptr(p), ptr(var), C.c_float(clip[0]),
                                           C.c_float(clip[1]), ptr(acc), ptr(loss), stream_ptr()), "nll_gaussian_fwd")
+
+
+# ---- backward (weight gradient) ---------------------------------------------------------------------------
+def wgrad_workspace(ksize: int, cin: int, cout: int, device) -> Tensor:
+    n = _lib.load().sn_wgrad_workspace_bytes(ksize, cin, cout)
+    return torch.empty(n // 4, device=device, dtype=torch.float32)
+
+
+def conv_moments_bwd_weight_tc(g_out: PackedView, batch: int, in_h: int, in_w: int, ksize: int, cout: int,
+                               in0: PackedView, c0: int, rsum: Tensor, w_mu: Tensor, w_sigma: Tensor,
+                               workspace: Tensor, g_w_mu: Tensor, g_w_sigma: Tensor,
+                               in1: Optional[PackedView] = None, c1: int = 0, upconv: bool = False) -> None:
+    d = sn_tc_wgrad_desc()
+    d.g_out = g_out.c_view()
+    d.in_[0] = in0.c_view()
+    d.in_[1] = (in1 if in1 is not None else in0).c_view()
+    d.in_c[0], d.in_c[1] = c0, c1
+    d.batch, d.in_h, d.in_w, d.ksize, d.cout = batch, in_h, in_w, ksize, cout
+    d.flags = SN_TC_UPCONV if upconv else 0
+    d.rsum, d.w_mu, d.w_sigma = rsum.data_ptr(), w_mu.data_ptr(), w_sigma.data_ptr()
+    d.workspace, d.g_w_mu, d.g_w_sigma = workspace.data_ptr(), g_w_mu.data_ptr(), g_w_sigma.data_ptr()
+    check(_lib.load().sn_conv_moments_bwd_weight_tc(C.byref(d), stream_ptr()), "conv_moments_bwd_weight_tc")
+
+
+def first_conv_rsum(x: Tensor, ksize: int, rsum: Tensor) -> None:
+    B, H, W, cin = x.shape
+    check(_lib.load().sn_first_conv_rsum(B, H, W, cin, ksize, ptr(x), ptr(rsum), stream_ptr()), "first_conv_rsum")

@@ -265,3 +265,110 @@ def test_hippocampus_fgsm_fast(S):
 
 def test_brats_fgsm_fast(S):
     _fgsm_fast_vs_oracle(S, "brats", 4, 4, 1, O.BRATS_ALPHA)
+
+
+# ------------------------------------------------------------------------------------------------------------
+# weight gradient on the tensor cores (pixel-axis GEMMs, MN-major operands)
+# ------------------------------------------------------------------------------------------------------------
+W_TOL = 1e-2      # weight gradients within 1e-2 relative per tensor (single-bf16 operands)
+
+WGRAD_CASES = [
+    # B, H, W, cin, cout, k
+    (2, 10, 9, 32, 32, 3),      # 9 M blocks -> 3 M tiles (last with one valid block), 2 K tiles
+    (3, 12, 14, 64, 32, 3),
+    (1, 20, 20, 128, 128, 3),   # N tile of 128
+    (2, 9, 9, 256, 64, 3),
+    (2, 11, 13, 32, 64, 1),     # 1x1: a single valid M block
+    (2, 7, 8, 64, 32, 2),       # plain k = 2
+    (9, 8, 8, 64, 96, 3),       # cout = 96 -> N tiles of 32
+    (40, 30, 30, 32, 64, 3),    # split-K over every SM
+]
+
+
+@pytest.mark.parametrize("case", WGRAD_CASES)
+def test_conv_wgrad_tc(S, case):
+    F = S.fastops
+    B, H, W, cin, cout, k = case
+    mu, var, w, ws = layer(B, H, W, cin, cout, k, seed=sum(case))
+    Ho, Wo = H - k + 1, W - k + 1
+    gm, gv = rnd((B, Ho, Wo, cout), 87), rnd((B, Ho, Wo, cout), 88)
+    w.requires_grad_(True)
+    ws.requires_grad_(True)
+    m_out, v_out = O.conv_intermediate_conv_form(mu, var, w, ws)
+    ((m_out * gm).sum() + (v_out * gv).sum()).backward()
+    src = F.PackedView(F.pack_moments(dev(mu), dev(var)))
+    g_out = F.PackedView(F.pack_moments(dev(gm), dev(gv)))
+    wd, wsd = dev(w.detach()), dev(ws.detach())
+    wp, s = F.prepare_weights(wd, wsd)
+    rsum = torch.full((B, Ho, Wo), float("nan"), device="cuda")
+    out = F.packed_empty(B, Ho, Wo, cout, "cuda")
+    F.conv_moments_tc(src, cin, B, H, W, k, cout, wp, s, dst=F.PackedView(out), rsum_out=rsum)
+    r_ref = O._box_sum((mu.square() + var).sum(-1), k)
+    assert rel(rsum, r_ref) < 1e-3          # includes the bf16 rounding of the variance plane
+    gw = torch.full_like(wd, float("nan"))
+    gws = torch.full_like(wsd, float("nan"))
+    work = F.wgrad_workspace(k, cin, cout, "cuda")
+    F.conv_moments_bwd_weight_tc(g_out, B, H, W, k, cout, src, cin, rsum, wd, wsd, work, gw, gws)
+    torch.cuda.synchronize()
+    e_w, e_s = rel(gw, w.grad), rel(gws, ws.grad)
+    print(case, e_w, e_s)
+    assert e_w < W_TOL and e_s < W_TOL, (e_w, e_s)
+
+
+def test_conv_wgrad_tc_concat_windows(S):
+    F = S.fastops
+    B, H, W, k, cout = 2, 10, 12, 3, 64
+    mu_d, var_d, _, _ = layer(B, H, W, 64, cout, k, seed=5)
+    mu_e, var_e, _, _ = layer(B, H + 4, W + 4, 32, cout, k, seed=6)
+    _, _, w, ws = layer(B, H, W, 96, cout, k, seed=7)
+    w.requires_grad_(True)
+    ws.requires_grad_(True)
+    m_in, v_in = O.conc(mu_d, var_d, mu_e, var_e)
+    m_out, v_out = O.conv_intermediate_conv_form(m_in, v_in, w, ws)
+    gm, gv = rnd(tuple(m_out.shape), 8), rnd(tuple(m_out.shape), 9)
+    ((m_out * gm).sum() + (v_out * gv).sum()).backward()
+    dbuf = F.packed_empty(B, H + 3, W + 5, 64, "cuda")
+    F.packed_fill(dbuf, 7.0)
+    dbuf[:, 1:1 + H, 2:2 + W] = F.pack_moments(dev(mu_d), dev(var_d))
+    ebuf = F.pack_moments(dev(mu_e), dev(var_e))
+    gbuf = F.packed_empty(B, H - 2 + 4, W - 2 + 4, cout, "cuda")
+    gbuf.fill_(3.0)
+    gbuf[:, 2:-2, 2:-2] = F.pack_moments(dev(gm), dev(gv))
+    wd, wsd = dev(w.detach()), dev(ws.detach())
+    rsum = dev(O._box_sum((m_in.square() + v_in).sum(-1), k))
+    gw, gws = torch.empty_like(wd), torch.empty_like(wsd)
+    work = F.wgrad_workspace(k, 96, cout, "cuda")
+    F.conv_moments_bwd_weight_tc(F.PackedView(gbuf, 2, 2, 0), B, H, W, k, cout, F.PackedView(dbuf, 1, 2, 0), 64, rsum,
+                                 wd, wsd, work, gw, gws, in1=F.PackedView(ebuf, 2, 2, 0), c1=32)
+    e_w, e_s = rel(gw, w.grad), rel(gws, ws.grad)
+    print(e_w, e_s)
+    assert e_w < W_TOL and e_s < W_TOL, (e_w, e_s)
+
+
+@pytest.mark.parametrize("case", [(2, 6, 6, 64, 32), (1, 9, 7, 128, 64), (2, 5, 5, 256, 128), (3, 30, 41, 64, 32)])
+def test_upconv_wgrad_tc(S, case):
+    F = S.fastops
+    B, H, W, cin, cout = case
+    mu, var, w, ws = layer(B, H, W, cin, cout, 2, seed=sum(case))
+    w.requires_grad_(True)
+    ws.requires_grad_(True)
+    m_out, v_out = O.conv_intermediate_conv_form(*O.upsampling(mu, var), w, ws)
+    gm, gv = rnd(tuple(m_out.shape), 11), rnd(tuple(m_out.shape), 12)
+    ((m_out * gm).sum() + (v_out * gv).sum()).backward()
+    gbuf = F.packed_empty(B, 2 * H + 6, 2 * W + 6, cout, "cuda")
+    gbuf.fill_(5.0)
+    gbuf[:, 3:-3, 3:-3] = F.pack_moments(dev(gm), dev(gv))
+    src = F.PackedView(F.pack_moments(dev(mu), dev(var)))
+    wd, wsd = dev(w.detach()), dev(ws.detach())
+    wp, s = F.prepare_weights(wd, wsd, upconv=True)
+    rsum = torch.empty((B, H, W), device="cuda")
+    out = F.packed_empty(B, 2 * H, 2 * W, cout, "cuda")
+    F.conv_moments_tc(src, cin, B, H, W, 2, cout, wp, s, dst=F.PackedView(out), upconv=True, rsum_out=rsum)
+    assert rel(rsum, (mu.square() + var).sum(-1)) < 1e-3
+    gw, gws = torch.empty_like(wd), torch.empty_like(wsd)
+    work = F.wgrad_workspace(2, cin, cout, "cuda")
+    F.conv_moments_bwd_weight_tc(F.PackedView(gbuf, 3, 3, 0), B, H, W, 2, cout, src, cin, rsum, wd, wsd, work, gw, gws,
+                                 upconv=True)
+    e_w, e_s = rel(gw, w.grad), rel(gws, ws.grad)
+    print(case, e_w, e_s)
+    assert e_w < W_TOL and e_s < W_TOL, (e_w, e_s)
