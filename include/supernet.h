@@ -285,10 +285,13 @@ int sn_maxpool2_bwd_packed(const sn_packed_view* in, int32_t batch, int32_t in_h
 /* Backward of the fused head: loss_scale * nll_gaussian(y, p, clip(var)) (Brats.py:293-311; clips :573-574 / :588-589)
  * -> mysoftmax (Brats.py:269-283) -> conv_final (k = 1) -> ReLU gate of the tensor feeding conv_final, in one pass.
  * The forward quantities are recomputed from the saved packed input `in`; `acc` is the workspace sn_nll_gaussian_fwd
- * filled for this batch (NaN/Inf -> 0 rule of Brats.py:304-305).  Writes the packed gradient window g_in. */
+ * filled for this batch (NaN/Inf -> 0 rule of Brats.py:304-305).  Writes the packed gradient window g_in and,
+ * when the three optional fp32 outputs are given (all or none), what the weight gradient of conv_final needs:
+ * the gradients w.r.t. the pre-softmax mean / variance [rows, n_labels] and rsum [rows] = sum_c mu^2 + var. */
 int sn_head_bwd_packed(const sn_packed_view* in, int32_t batch, int32_t in_h, int32_t in_w, int32_t cin,
                        int32_t n_labels, const float* w_mu, const float* w_sigma, const float* y, float clip_lo,
-                       float clip_hi, const double* acc, float loss_scale, const sn_packed_view* g_in, sn_stream_t st);
+                       float clip_hi, const double* acc, float loss_scale, const sn_packed_view* g_in,
+                       float* g_logit_mu, float* g_logit_var, float* rsum_out, sn_stream_t st);
 
 /* Input gradient of myConv_input (Brats.py:65-76; what create_adversarial_pattern returns the sign of):
  *   g_x = g_mu_out (*)^T W + 2 x . box^T(t),  t = sum_n g_var_out s_n;  g_out: packed (in_h-k+1 x in_w-k+1 x cout)

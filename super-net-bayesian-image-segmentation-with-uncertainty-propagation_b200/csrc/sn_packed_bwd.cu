@@ -152,7 +152,8 @@ __global__ void __launch_bounds__(128) head_bwd_kernel(sn_packed_view in, int B,
                                                        const float* __restrict__ w, const float* __restrict__ ws,
                                                        const float* __restrict__ y, float clip_lo, float clip_hi,
                                                        const double* __restrict__ acc, float loss_scale,
-                                                       sn_packed_view gin) {
+                                                       sn_packed_view gin, float* __restrict__ g_logit_mu,
+                                                       float* __restrict__ g_logit_var, float* __restrict__ rsum_out) {
   extern __shared__ __align__(16) float hsm[];   // W [cin][C], W^2 [cin][C], s [C]
   float* sw = hsm;
   float* sw2 = hsm + cin * C;
@@ -252,6 +253,11 @@ __global__ void __launch_bounds__(128) head_bwd_kernel(sn_packed_view in, int B,
     for (int j = 0; j < C; ++j) {
       gm[j] = p[j] * (gpt[j] - dot);
       tt = fmaf(gv[j], ss[j], tt);
+    }
+    if (g_logit_mu) {               // what the weight gradient of conv_final needs
+#pragma unroll
+      for (int j = 0; j < C; ++j) { g_logit_mu[i * C + j] = gm[j]; g_logit_var[i * C + j] = gv[j]; }
+      rsum_out[i] = r;
     }
     // ---- conv_final data gradient + ReLU gate of its (post-ReLU) input
     __nv_bfloat16* o = dst + pv_off(gin, b, yy, xx);
@@ -523,8 +529,11 @@ int sn_maxpool2_bwd_packed(const sn_packed_view* in, int32_t batch, int32_t in_h
 
 int sn_head_bwd_packed(const sn_packed_view* in, int32_t batch, int32_t in_h, int32_t in_w, int32_t cin,
                        int32_t n_labels, const float* w_mu, const float* w_sigma, const float* y, float clip_lo,
-                       float clip_hi, const double* acc, float loss_scale, const sn_packed_view* g_in, sn_stream_t st) {
+                       float clip_hi, const double* acc, float loss_scale, const sn_packed_view* g_in,
+                       float* g_logit_mu, float* g_logit_var, float* rsum_out, sn_stream_t st) {
   SN_REQUIRE(w_mu && w_sigma && y && acc, SN_ERR_BAD_ARG, "head_bwd: null pointer");
+  SN_REQUIRE((g_logit_mu != nullptr) == (g_logit_var != nullptr) && (g_logit_mu != nullptr) == (rsum_out != nullptr),
+             SN_ERR_BAD_ARG, "head_bwd: pass all three optional outputs or none");
   SN_REQUIRE(n_labels >= 1 && n_labels <= 8, SN_ERR_UNSUPPORTED, "head_bwd: %d classes (max 8)", n_labels);
   SN_REQUIRE(cin > 0 && cin % 8 == 0 && cin <= 256, SN_ERR_UNSUPPORTED, "head_bwd: cin %d", cin);
   int rc = check_pv(in, batch, in_h, in_w, cin, "head_bwd in");
@@ -536,7 +545,8 @@ int sn_head_bwd_packed(const sn_packed_view* in, int32_t batch, int32_t in_h, in
 #define SN_HEAD(CC)                                                                                              \
   case CC:                                                                                                       \
     head_bwd_kernel<CC><<<grid, 128, smem, as_stream(st)>>>(*in, batch, in_h, in_w, cin, w_mu, w_sigma, y, clip_lo, \
-                                                             clip_hi, acc, loss_scale, *g_in);                   \
+                                                             clip_hi, acc, loss_scale, *g_in, g_logit_mu,        \
+                                                             g_logit_var, rsum_out);                             \
     break;
   switch (n_labels) {
     SN_HEAD(1) SN_HEAD(2) SN_HEAD(3) SN_HEAD(4) SN_HEAD(5) SN_HEAD(6) SN_HEAD(7) SN_HEAD(8)

@@ -103,7 +103,9 @@ class DataParallelTrainer:
     def step(self, x_local: Tensor, y_local: Tensor, global_batch: int) -> Tensor:
         params = [p for p in self.model.parameters() if p.requires_grad]
         self.opt.zero_grad(set_to_none=True)
-        if x_local.shape[0] > 0:
+        if x_local.shape[0] > 0 and getattr(self.model, "mode", "fp32") == "fast":
+            loss = self._fast_backward(x_local, y_local)
+        elif x_local.shape[0] > 0:
             loss = self.model.elbo_loss(x_local, y_local, self.kl_factor)
             loss.backward()
         else:                       # an empty shard still takes part in the collective
@@ -113,4 +115,32 @@ class DataParallelTrainer:
         allreduce_gradients(params, x_local.shape[0], global_batch, self.group)
         clip_by_norm_per_variable_(params, self.clipnorm)
         self.opt.step()
+        if self._engine is not None:
+            self._engine.refresh_weights()       # re-derive the bf16 tensor-core operands from the updated weights
         return loss.detach()
+
+    _engine = None
+
+    def _fast_backward(self, x: Tensor, y: Tensor) -> Tensor:
+        """FAST mode: tensor-core forward, data-gradient and weight-gradient chain (engine.GradientEngine), then the
+        regulariser terms of Brats.py:575-576, which depend on the weights only."""
+        import ctypes as C
+
+        from . import _lib, ops
+        from .engine import GradientEngine
+        m = self.model
+        if self._engine is None or not self._engine.matches(x):
+            self._engine = GradientEngine(m, x.shape[0], x.shape[1], x.shape[2], x.shape[3], x.device, train=True)
+        nll, grads = self._engine.loss_and_weight_gradients(x, y, clip=(1e-12, 1e3))
+        lib = _lib.load()
+        scale = self.kl_factor * 0.5
+        for name in m.conv_names:
+            w, ws = getattr(m, name).weights()
+            gw, gws = grads[name]
+            _lib.check(lib.sn_kl_regularizer_bwd(_lib.ptr(w), C.c_size_t(w.numel()), _lib.ptr(ws), ws.numel(),
+                                                 w.shape[0], C.c_float(scale), _lib.ptr(gw), _lib.ptr(gws),
+                                                 _lib.stream_ptr()), "kl_regularizer_bwd")
+            w.grad, ws.grad = gw, gws
+        with torch.no_grad():
+            reg = ops.kl_regularizer([c.weights() for c in m.convs()])
+        return nll[0] + scale * reg

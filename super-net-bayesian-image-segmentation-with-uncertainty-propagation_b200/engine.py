@@ -80,10 +80,13 @@ class InferenceEngine:
             wp, s = self.prepared[name]
             cout = getattr(m, name).kernel_num
             self.step_names.append(name)
+            rs = None
+            if getattr(self, "want_rsum", False):          # training: keep box_k(sum_c mu^2 + var) for d/d w_sigma
+                rs = torch.empty((B, h, w) if upconv else (B, h - k + 1, w - k + 1), device=dev, dtype=torch.float32)
             self.records.append(dict(kind="conv", name=name, src0=src, c0=c0, src1=src1, c1=c1, h=h, w=w, k=k,
-                                     cout=cout, dst=dst, relu=relu, upconv=upconv))
+                                     cout=cout, dst=dst, relu=relu, upconv=upconv, rsum=rs))
             steps.append(lambda: F.conv_moments_tc(src, c0, B, h, w, k, cout, wp, s, dst=dst, relu=relu,
-                                                   upconv=upconv, src1=src1, c1=c1))
+                                                   upconv=upconv, src1=src1, c1=c1, rsum_out=rs))
 
         # ---- encoder --------------------------------------------------------------------------------
         h, w = H - 2, W - 2
@@ -209,7 +212,10 @@ class GradientEngine(InferenceEngine):
     Gradient tensors use the packed layout of the activation they belong to (g_mean hi/lo, g_variance).  The whole
     forward + loss + backward sequence is allocation-free and is captured in one CUDA graph."""
 
-    def __init__(self, model, batch: int, in_h: int, in_w: int, in_c: int, device, graph: bool = True):
+    def __init__(self, model, batch: int, in_h: int, in_w: int, in_c: int, device, graph: bool = True,
+                 train: bool = False):
+        self.want_rsum = train
+        self.train = train
         super().__init__(model, batch, in_h, in_w, in_c, device, graph=False, keep_presoftmax=False)
         self.use_graph_bwd = graph
         self._graph_bwd: Optional[torch.cuda.CUDAGraph] = None
@@ -258,6 +264,17 @@ class GradientEngine(InferenceEngine):
         steps, names = self._bwd_steps, self.bwd_step_names
         wf, wsf = m.conv_final.weights()
         w_in, ws_in = m.conv_input.weights()
+        self.grads = {}           # training: layer name -> (g_w_mu, g_w_sigma), overwritten by every step
+        logit_grads = None
+        if self.train:
+            for name in m.conv_names:
+                w_, ws_ = getattr(m, name).weights()
+                self.grads[name] = (torch.zeros_like(w_), torch.zeros_like(ws_))
+            n_max = max(w_.numel() for w_, _ in (getattr(m, n).weights() for n in m.conv_names))
+            self._wg_work = torch.empty(2 * n_max + 1024, device=dev, dtype=torch.float32)
+            rows = B * oh * ow
+            logit_grads = (torch.empty((rows, C), device=dev), torch.empty((rows, C), device=dev),
+                           torch.empty(rows, device=dev))
         for r in reversed(self.records):
             kind = r["kind"]
             if kind == "head":
@@ -267,8 +284,17 @@ class GradientEngine(InferenceEngine):
                 names.append("head_bwd")
                 steps.append(lambda src=src, r=r: F.head_bwd_packed(src, B, r["h"], r["w"], r["c"], wf, wsf, self.y_in,
                                                                     self._clip, self.nll_acc, self._loss_scale,
-                                                                    g_of(src)))
+                                                                    g_of(src), logit_grads))
                 g_of(src)
+                if self.train:
+                    # conv_final (32 -> n_labels, k = 1) and conv_input (Cin <= 8) are too thin for the tensor
+                    # cores: their weight gradients run in the FP32-mode kernel on unpacked operands
+                    mu32 = torch.empty((B, r["h"], r["w"], r["c"]), device=dev)
+                    var32 = torch.empty_like(mu32)
+                    names.append("conv_final_wgrad")
+                    steps.append(lambda src=src, r=r, mu32=mu32, var32=var32: self._wgrad_f32(
+                        "conv_final", src.buf, mu32, var32, logit_grads[0], logit_grads[1], logit_grads[2], wf, wsf,
+                        r["h"], r["w"], r["c"], C, 1))
             elif kind == "conv":
                 name = r["name"]
                 wt = self.prepared_bwd[name]
@@ -279,6 +305,16 @@ class GradientEngine(InferenceEngine):
                             gate0=gated[src0.buf.data_ptr()], upconv=r["upconv"])
                 if src1 is not None:
                     args.update(in1=src1, g_in1=g_of(src1), c1=r["c1"], gate1=gated[src1.buf.data_ptr()])
+                if self.train:
+                    w_, ws_ = getattr(m, name).weights()
+                    gw, gws = self.grads[name]
+                    wargs = dict(g_out=g_of(r["dst"]), batch=B, in_h=r["h"], in_w=r["w"], ksize=r["k"],
+                                 cout=r["cout"], in0=src0, c0=r["c0"], rsum=r["rsum"], w_mu=w_, w_sigma=ws_,
+                                 workspace=self._wg_work, g_w_mu=gw, g_w_sigma=gws, upconv=r["upconv"])
+                    if src1 is not None:
+                        wargs.update(in1=src1, c1=r["c1"])
+                    names.append(name + "_wgrad")
+                    steps.append(lambda a=wargs: F.conv_moments_bwd_weight_tc(**a))
                 names.append(name + "_dgrad")
                 steps.append(lambda a=args: F.conv_moments_bwd_data_tc(**a))
             elif kind == "pool":
@@ -289,15 +325,65 @@ class GradientEngine(InferenceEngine):
                     src, B, r["h"], r["w"], r["c"], g_of(dst), g_of(src), keep))
                 g_of(dst), g_of(src)
             elif kind == "first":
-                names.append("conv_input_dgrad")
-                steps.append(lambda r=r: F.first_conv_bwd_data_packed(self.x_in, w_in, ws_in, g_of(r["dst"]), self.g_x))
+                if self.train:
+                    a0 = r["dst"].buf
+                    _, ah, aw, _, ac = a0.shape
+                    gm32 = torch.empty((B, ah, aw, ac), device=dev)
+                    gv32 = torch.empty_like(gm32)
+                    rs0 = torch.empty((B, ah, aw), device=dev)
+                    k0 = w_in.shape[0]
+                    names.append("conv_input_wgrad")
+                    steps.append(lambda r=r, gm32=gm32, gv32=gv32, rs0=rs0: self._first_wgrad(
+                        g_of(r["dst"]).buf, gm32, gv32, rs0, w_in, ws_in, k0))
+                else:                                    # the input gradient is what FGSM needs; training stops here
+                    names.append("conv_input_dgrad")
+                    steps.append(lambda r=r: F.first_conv_bwd_data_packed(self.x_in, w_in, ws_in, g_of(r["dst"]),
+                                                                          self.g_x))
                 g_of(r["dst"])
         self.grad_buffers = gbuf
         self.n_launches_bwd = len(steps) + 2          # + the two NLL forward kernels
 
     def refresh_weights(self) -> None:
-        super().refresh_weights()
-        self._graph_bwd = None
+        """After an optimiser step: re-derive the bf16 operands IN PLACE (the captured graph keeps its pointers)."""
+        m = self.model
+        for name in m.conv_names:
+            if name in ("conv_input", "conv_final"):
+                continue
+            w, ws = getattr(m, name).weights()
+            up = name.endswith("conv2x2")
+            F.prepare_weights(w, ws, upconv=up, out=self.prepared[name])
+            F.prepare_weights_bwd(w, upconv=up, out=self.prepared_bwd[name])
+
+    # FP32-mode weight gradient on unpacked operands (thin layers only)
+    def _wgrad_f32(self, name, packed_in, mu32, var32, g_mu, g_var, rsum, w, ws, h, wd, cin, cout, k) -> None:
+        from . import ops
+        F.unpack_moments(packed_in, out=(mu32, var32))
+        gw, gws = self.grads[name]
+        ops.conv_bwd_weight_raw(self.shape[0], h, wd, cin, cout, k, mu32, var32, g_mu, g_var, rsum, w, ws, gw, gws)
+
+    def _first_wgrad(self, g_packed, gm32, gv32, rs0, w, ws, k) -> None:
+        from . import ops
+        F.unpack_moments(g_packed, out=(gm32, gv32))
+        F.first_conv_rsum(self.x_in, k, rs0)
+        B, H, W, cin = self.shape
+        gw, gws = self.grads["conv_input"]
+        ops.conv_bwd_weight_raw(B, H, W, cin, w.shape[-1], k, self.x_in, None, gm32, gv32, rs0, w, ws, gw, gws)
+
+    def loss_and_weight_gradients(self, x: Tensor, y_onehot: Tensor, clip: Tuple[float, float] = (1e-12, 1e3)):
+        """train_on_batch's data term (Brats.py:572-574,578): returns (NLL, {layer: (dNLL/dw_mu, dNLL/dw_sigma)});
+        the tensors are engine-owned and overwritten by the next call.  The regulariser terms (Brats.py:575-576) depend
+        on the weights only and are added by the caller (dp.DataParallelTrainer)."""
+        if not self.train:
+            raise RuntimeError("engine was built with train=False")
+        if not self.matches(x):
+            raise RuntimeError(f"engine built for input {self.shape}, got {tuple(x.shape)}")
+        if (1.0, tuple(clip)) != (self._loss_scale, self._clip):
+            self._loss_scale, self._clip = 1.0, (float(clip[0]), float(clip[1]))
+            self._graph_bwd = None
+        self.x_in.copy_(x, non_blocking=True)
+        self.y_in.copy_(y_onehot.reshape(self.y_in.shape), non_blocking=True)
+        loss, _ = self.loss_and_input_gradient_resident()
+        return loss, self.grads
 
     def _launch_fwd_bwd(self) -> None:
         self._launch_all()

@@ -52,20 +52,27 @@ def pack_moments(mu: Tensor, var: Optional[Tensor]) -> Tensor:
     return out
 
 
-def unpack_moments(buf: Tensor) -> Tuple[Tensor, Tensor]:
+def unpack_moments(buf: Tensor, out: Optional[Tuple[Tensor, Tensor]] = None) -> Tuple[Tensor, Tensor]:
     n, h, w, _, c = buf.shape
-    mu = torch.empty((n, h, w, c), device=buf.device, dtype=torch.float32)
-    var = torch.empty_like(mu)
+    if out is not None:
+        mu, var = out
+    else:
+        mu = torch.empty((n, h, w, c), device=buf.device, dtype=torch.float32)
+        var = torch.empty_like(mu)
     check(_lib.load().sn_unpack_moments(C.c_size_t(n * h * w), c, ptr(buf), ptr(mu), ptr(var), stream_ptr()),
           "unpack_moments")
     return mu, var
 
 
-def prepare_weights(w_mu: Tensor, w_sigma: Tensor, upconv: bool = False) -> Tuple[Tensor, Tensor]:
+def prepare_weights(w_mu: Tensor, w_sigma: Tensor, upconv: bool = False,
+                    out: Optional[Tuple[Tensor, Tensor]] = None) -> Tuple[Tensor, Tensor]:
     """HWIO fp32 -> ([3, taps, cout, cin] bf16 operands, softplus(w_sigma) [cout])."""
     k, _, cin, cout = w_mu.shape
-    wp = torch.empty((3, k * k, cout, cin), device=w_mu.device, dtype=torch.bfloat16)
-    s = torch.empty(cout, device=w_mu.device, dtype=torch.float32)
+    if out is not None:
+        wp, s = out
+    else:
+        wp = torch.empty((3, k * k, cout, cin), device=w_mu.device, dtype=torch.bfloat16)
+        s = torch.empty(cout, device=w_mu.device, dtype=torch.float32)
     check(_lib.load().sn_prepare_weights(ptr(w_mu.detach().contiguous()), ptr(w_sigma.detach().contiguous()), k, cin,
                                          cout, 1 if upconv else 0, ptr(wp), ptr(s), stream_ptr()), "prepare_weights")
     return wp, s
@@ -119,12 +126,12 @@ def final_conv_softmax_packed(src: PackedView, batch: int, in_h: int, in_w: int,
 
 
 # ---- backward (data gradient) ----------------------------------------------------------------------------
-def prepare_weights_bwd(w_mu: Tensor, upconv: bool = False) -> Tensor:
+def prepare_weights_bwd(w_mu: Tensor, upconv: bool = False, out: Optional[Tensor] = None) -> Tensor:
     """HWIO fp32 -> the data-gradient operands [3, taps, cin, K] bf16 (flipped / transposed filter; up-conv: K =
     (parity, cout), taps = 1)."""
     k, _, cin, cout = w_mu.shape
     shape = (3, 1, cin, 4 * cout) if upconv else (3, k * k, cin, cout)
-    wt = torch.empty(shape, device=w_mu.device, dtype=torch.bfloat16)
+    wt = out if out is not None else torch.empty(shape, device=w_mu.device, dtype=torch.bfloat16)
     check(_lib.load().sn_prepare_weights_bwd(ptr(w_mu.detach().contiguous()), k, cin, cout, 1 if upconv else 0,
                                              ptr(wt), stream_ptr()), "prepare_weights_bwd")
     return wt
@@ -156,12 +163,15 @@ def maxpool2_bwd_packed(inp: PackedView, batch: int, in_h: int, in_w: int, c: in
 
 
 def head_bwd_packed(inp: PackedView, batch: int, in_h: int, in_w: int, cin: int, w_mu: Tensor, w_sigma: Tensor,
-                    y: Tensor, clip: Tuple[float, float], acc: Tensor, loss_scale: float, g_in: PackedView) -> None:
+                    y: Tensor, clip: Tuple[float, float], acc: Tensor, loss_scale: float, g_in: PackedView,
+                    logit_grads: Optional[Tuple[Tensor, Tensor, Tensor]] = None) -> None:
     a, g = inp.c_view(), g_in.c_view()
     n_labels = w_mu.shape[-1]
+    lg = logit_grads if logit_grads is not None else (None, None, None)
     check(_lib.load().sn_head_bwd_packed(C.byref(a), batch, in_h, in_w, cin, n_labels, ptr(w_mu), ptr(w_sigma),
                                          ptr(y), C.c_float(clip[0]), C.c_float(clip[1]), ptr(acc),
-                                         C.c_float(loss_scale), C.byref(g), stream_ptr()), "head_bwd_packed")
+                                         C.c_float(loss_scale), C.byref(g), ptr(lg[0]), ptr(lg[1]), ptr(lg[2]),
+                                         stream_ptr()), "head_bwd_packed")
 
 
 def first_conv_bwd_data_packed(x: Tensor, w_mu: Tensor, w_sigma: Tensor, g_out: PackedView, g_x: Tensor) -> None:

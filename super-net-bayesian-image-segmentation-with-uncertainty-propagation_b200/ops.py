@@ -92,6 +92,15 @@ class _ConvMoments(torch.autograd.Function):
         return g_mu, g_var, g_w, g_ws, None
 
 
+def conv_bwd_weight_raw(B, H, W, cin, cout, k, mu, var, g_mu_out, g_var_out, rsum, w_mu, w_sigma, g_w, g_ws) -> None:
+    """sn_conv_moments_bwd_weight on caller-owned tensors (no autograd, no allocation): used by the FAST-mode
+    training engine for the two layers too thin for the tensor cores."""
+    d = _conv_desc(B, H, W, cin, cout, k, 0)
+    check(_lib.load().sn_conv_moments_bwd_weight(C.byref(d), ptr(mu), ptr(var), ptr(g_mu_out), ptr(g_var_out),
+                                                 ptr(rsum), ptr(w_mu), ptr(w_sigma), ptr(g_w), ptr(g_ws),
+                                                 stream_ptr()), "conv_moments_bwd_weight")
+
+
 def conv_moments(mu: Tensor, var: Optional[Tensor], w_mu: Tensor, w_sigma: Tensor, relu: bool = False):
     """myConv_input.call (var=None, Brats.py:65-76) / myConv_intermediate.call (Brats.py:118-137), optionally
     fused with myReLU (Brats.py:233-238)."""

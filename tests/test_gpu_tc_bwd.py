@@ -372,3 +372,59 @@ def test_upconv_wgrad_tc(S, case):
     e_w, e_s = rel(gw, w.grad), rel(gws, ws.grad)
     print(case, e_w, e_s)
     assert e_w < W_TOL and e_s < W_TOL, (e_w, e_s)
+
+
+# ------------------------------------------------------------------------------------------------------------
+# whole network: train_on_batch gradients (Brats.py:569-580) through mode='fast'
+# ------------------------------------------------------------------------------------------------------------
+def _elbo_grads_fast_vs_oracle(S, variant, C, in_ch, B, alpha, kl):
+    from supernet_b200 import dp
+    oracle = O.UNetOracle(variant, 32, C, in_ch, torch.float64)
+    oracle.requires_grad_(True)
+    w32 = O.make_weights(variant, 32, C, in_ch)
+    model = S.Density_prop_with_pad_UNET(32, C, variant=variant, mode="fast").load_weight_dict(w32, device="cuda")
+    x = O.make_input(variant, B, alpha=alpha)
+    hw = O.output_hw(variant)
+    y = O.make_labels(B, hw * hw, C, dtype=torch.float64)
+    ref = oracle.elbo_loss(x, y, kl_factor=kl)
+    rg = torch.autograd.grad(ref, oracle.parameters())
+    trainer = dp.DataParallelTrainer(model, lr=0.0, kl_factor=kl)      # lr 0: gradients only
+    loss = trainer._fast_backward(dev(x), dev(y))
+    params = [p for c in model.convs() for p in c.weights()]
+    errs = {}
+    for (name, kind), a, b in zip([(n, k) for n in model.conv_names for k in ("w_mu", "w_sigma")], params, rg):
+        errs[f"{name}.{kind}"] = rel(a.grad, b)
+    worst = max(errs, key=errs.get)
+    print(variant, "loss", float(loss), float(ref), "worst", worst, errs[worst])
+    print({k: round(v, 5) for k, v in errs.items()})
+    assert abs(float(loss) - float(ref)) < 2e-3 * abs(float(ref))
+    return errs
+
+
+def test_hippocampus_elbo_gradients_fast(S):
+    errs = _elbo_grads_fast_vs_oracle(S, "hippocampus", 3, 1, 4, 1.0, 1e-3)
+    assert max(errs.values()) < 1e-2, errs
+
+
+def test_brats_elbo_gradients_fast(S):
+    errs = _elbo_grads_fast_vs_oracle(S, "brats", 4, 4, 1, O.BRATS_ALPHA, 1e-5)
+    # 23 layers deep the bf16 variance-gradient plane and the gate / arg-max flips of the bf16x3 forward compound
+    # (the input gradient of the same network sits at 9e-3): 2e-2 per tensor at BraTS depth
+    assert max(errs.values()) < 2e-2, errs
+
+
+def test_fast_training_step_runs_and_learns(S):
+    """Three Adam steps through the FAST-mode trainer: the loss goes down and the tensor-core operands follow the
+    updated weights (refresh after every step)."""
+    from supernet_b200 import dp
+    w32 = O.make_weights("hippocampus", 32, 3, 1)
+    model = S.Density_prop_with_pad_UNET(32, 3, variant="hippocampus", mode="fast").load_weight_dict(w32, device="cuda")
+    x = dev(O.make_input("hippocampus", 4))
+    y = dev(O.make_labels(4, 54 * 54, 3))
+    trainer = dp.DataParallelTrainer(model, lr=1e-3, kl_factor=1e-5)
+    losses = [float(trainer.step(x, y, global_batch=4)) for _ in range(4)]
+    print(losses)
+    assert all(torch.isfinite(torch.tensor(losses))) and losses[-1] < losses[0]
+    with torch.no_grad():
+        p, _ = model(x)                       # inference engine built from the updated weights
+    assert bool(torch.isfinite(p).all())
