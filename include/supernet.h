@@ -273,6 +273,18 @@ int sn_conv_moments_bwd_weight_tc(const sn_tc_wgrad_desc* d, sn_stream_t st);
 int sn_first_conv_rsum(int32_t batch, int32_t in_h, int32_t in_w, int32_t cin, int32_t ksize, const float* x,
                        float* rsum, sn_stream_t st);
 
+/* Weight gradients of the two layers too thin for the tensor cores, on CUDA cores (same formulas):
+ *   myConv_input (k = 3, cout = 32, cin 1 or 4): x fp32 NHWC, g_out = packed gradient w.r.t. its (pre-ReLU) output;
+ *   conv_final (k = 1, cin = 32): in = its packed input, g_logit_* / rsum = the optional outputs of sn_head_bwd_packed.
+ * workspace: at least sn_wgrad_workspace_bytes(ksize, cin, cout) bytes.  Outputs are overwritten. */
+int sn_first_conv_bwd_weight_packed(int32_t batch, int32_t in_h, int32_t in_w, int32_t cin, int32_t cout,
+                                    int32_t ksize, const float* x, const float* w_sigma, const sn_packed_view* g_out,
+                                    void* workspace, float* g_w_mu, float* g_w_sigma, sn_stream_t st);
+int sn_final_conv_bwd_weight_packed(const sn_packed_view* in, int32_t batch, int32_t in_h, int32_t in_w, int32_t cin,
+                                    int32_t n_labels, const float* w_mu, const float* w_sigma, const float* g_logit_mu,
+                                    const float* g_logit_var, const float* rsum, void* workspace, float* g_w_mu,
+                                    float* g_w_sigma, sn_stream_t st);
+
 /* Adjoint of sn_maxpool2_packed (Brats.py:171-174,206-216): routes g_out (ceil(in_h/2) x ceil(in_w/2) x c) to the
  * arg-max position recomputed from the saved pool input `in` (first maximum in row-major window order).  g_in
  * (in_h x in_w x c window) is overwritten, EXCEPT inside the sub-window (keep_y0, keep_x0, keep_h, keep_w), where

@@ -484,6 +484,205 @@ __global__ void __launch_bounds__(FB_THREADS) first_conv_bwd_k3c32_kernel(int B,
   }
 }
 
+// ---------------------------------------------------------------------------------------------------------
+// weight gradients of the two layers too thin for the tensor cores
+// ---------------------------------------------------------------------------------------------------------
+// myConv_input (k = 3, 32 output channels, Cin = 4 or 1):  g_w[tap,c,n] = sum_p x[p+tap,c] g_mu'[p,n];
+// ds[n] = sum_p g_var'[p,n] r[p], r = box_3(sum_c x^2).  A block owns 32 x 4 output pixels per step; warp w < 9 is
+// filter tap w (lane = output channel n, CIN accumulators), warp 9 accumulates ds.  Operands are staged in shared
+// memory as fp32 (x tile with its halo; g_mean = hi + lo; g_var); every lane reads its own bank, x is a broadcast.
+constexpr int FW_TW = 32, FW_TH = 4, FW_PIX = FW_TW * FW_TH, FW_THREADS = 320;
+
+template <int CIN>
+__global__ void __launch_bounds__(FW_THREADS) first_conv_wgrad_k3c32_kernel(int B, int H, int W,
+                                                                            const float* __restrict__ x,
+                                                                            sn_packed_view gout, float* __restrict__ g_w,
+                                                                            float* __restrict__ ds, int tiles_x,
+                                                                            int tiles_y) {
+  constexpr int COUT = 32, XW = FW_TW + 2, XH = FW_TH + 2;
+  __shared__ __align__(16) float xs[XH * XW * CIN];
+  __shared__ __align__(16) float gm[FW_PIX * COUT];
+  __shared__ __align__(16) float gv[FW_PIX * COUT];
+  __shared__ float rr[FW_PIX];
+  const int Ho = H - 2, Wo = W - 2;
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const __nv_bfloat16* go = reinterpret_cast<const __nv_bfloat16*>(gout.base);
+  float acc[CIN];
+#pragma unroll
+  for (int c = 0; c < CIN; ++c) acc[c] = 0.f;
+  const int total_tiles = B * tiles_y * tiles_x;
+  for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
+    const int tx = tile % tiles_x;
+    const int ty = (tile / tiles_x) % tiles_y;
+    const int b = tile / (tiles_x * tiles_y);
+    const int x0 = tx * FW_TW, y0 = ty * FW_TH;
+    for (int i = threadIdx.x; i < XH * XW; i += FW_THREADS) {
+      const int yy = y0 + i / XW, xx = x0 + i % XW;
+      const bool in = yy < H && xx < W;
+#pragma unroll
+      for (int c = 0; c < CIN; ++c) xs[i * CIN + c] = in ? x[(((size_t)b * H + yy) * W + xx) * CIN + c] : 0.f;
+    }
+    for (int i = threadIdx.x; i < FW_PIX * 4; i += FW_THREADS) {
+      const int pix = i >> 2, part = i & 3;
+      const int oy = y0 + pix / FW_TW, ox = x0 + pix % FW_TW;
+      float m[8], v[8];
+      if (oy < Ho && ox < Wo) {
+        const __nv_bfloat16* gp = go + pv_off(gout, b, oy, ox) + part * 8;
+        float h[8], l[8];
+        b_unpack8(*reinterpret_cast<const uint4*>(gp), h);
+        b_unpack8(*reinterpret_cast<const uint4*>(gp + gout.c), l);
+        b_unpack8(*reinterpret_cast<const uint4*>(gp + 2 * gout.c), v);
+#pragma unroll
+        for (int e = 0; e < 8; ++e) m[e] = h[e] + l[e];
+      } else {
+#pragma unroll
+        for (int e = 0; e < 8; ++e) m[e] = v[e] = 0.f;
+      }
+      float* dm = gm + pix * COUT + part * 8;
+      float* dv = gv + pix * COUT + part * 8;
+      *reinterpret_cast<float4*>(dm) = make_float4(m[0], m[1], m[2], m[3]);
+      *reinterpret_cast<float4*>(dm + 4) = make_float4(m[4], m[5], m[6], m[7]);
+      *reinterpret_cast<float4*>(dv) = make_float4(v[0], v[1], v[2], v[3]);
+      *reinterpret_cast<float4*>(dv + 4) = make_float4(v[4], v[5], v[6], v[7]);
+    }
+    __syncthreads();
+    if (threadIdx.x < FW_PIX) {
+      const int py = threadIdx.x / FW_TW, px = threadIdx.x % FW_TW;
+      float r = 0.f;
+#pragma unroll
+      for (int kh = 0; kh < 3; ++kh)
+#pragma unroll
+        for (int kw = 0; kw < 3; ++kw)
+#pragma unroll
+          for (int c = 0; c < CIN; ++c) {
+            const float xv = xs[((py + kh) * XW + px + kw) * CIN + c];
+            r = fmaf(xv, xv, r);
+          }
+      rr[threadIdx.x] = r;
+    }
+    __syncthreads();
+    if (warp < 9) {
+      const int kh = warp / 3, kw = warp - kh * 3;
+#pragma unroll 4
+      for (int pix = 0; pix < FW_PIX; ++pix) {
+        const int py = pix / FW_TW, px = pix % FW_TW;
+        const float g = gm[pix * COUT + lane];
+        const float* xp = xs + ((py + kh) * XW + px + kw) * CIN;
+        if constexpr (CIN == 4) {
+          const float4 xv = *reinterpret_cast<const float4*>(xp);
+          acc[0] = fmaf(xv.x, g, acc[0]); acc[1] = fmaf(xv.y, g, acc[1]);
+          acc[2] = fmaf(xv.z, g, acc[2]); acc[3] = fmaf(xv.w, g, acc[3]);
+        } else {
+#pragma unroll
+          for (int c = 0; c < CIN; ++c) acc[c] = fmaf(xp[c], g, acc[c]);
+        }
+      }
+    } else {
+#pragma unroll 4
+      for (int pix = 0; pix < FW_PIX; ++pix) acc[0] = fmaf(gv[pix * COUT + lane], rr[pix], acc[0]);
+    }
+    __syncthreads();
+  }
+  if (warp < 9) {
+#pragma unroll
+    for (int c = 0; c < CIN; ++c) atomicAdd(g_w + ((size_t)warp * CIN + c) * COUT + lane, acc[c]);
+  } else {
+    atomicAdd(ds + lane, acc[0]);
+  }
+}
+
+// conv_final (k = 1, cin = 32, C <= 8 classes): P_mu[ci,j] = sum_p mu[p,ci] g_mu[p,j], P_var likewise, ds[j] =
+// sum_p g_var[p,j] r[p].  lane = (pixel sub-index 0..7) x (8-channel chunk 0..3): 16-byte loads of the packed input,
+// 2*8*C accumulators per thread, reduced over the pixel lanes with shuffles and over warps through atomics.
+template <int C>
+__global__ void __launch_bounds__(256) final_conv_wgrad_kernel(sn_packed_view in, int B, int H, int W,
+                                                               const float* __restrict__ g_mu,
+                                                               const float* __restrict__ g_var,
+                                                               const float* __restrict__ rsum, float* __restrict__ p_mu,
+                                                               float* __restrict__ p_var, float* __restrict__ ds) {
+  const int lane = threadIdx.x & 31;
+  const int chunk = lane & 3, psub = lane >> 2;
+  const size_t total = (size_t)B * H * W;
+  const size_t warp_id = (size_t)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+  const size_t n_warps = (size_t)gridDim.x * (blockDim.x >> 5);
+  const __nv_bfloat16* src = reinterpret_cast<const __nv_bfloat16*>(in.base);
+  float am[8][C], av[8][C], ad[C];
+#pragma unroll
+  for (int e = 0; e < 8; ++e)
+#pragma unroll
+    for (int j = 0; j < C; ++j) am[e][j] = av[e][j] = 0.f;
+#pragma unroll
+  for (int j = 0; j < C; ++j) ad[j] = 0.f;
+  for (size_t p0 = warp_id * 8; p0 < total; p0 += n_warps * 8) {
+    const size_t i = p0 + psub;
+    if (i < total) {
+      const int xx = (int)(i % W);
+      size_t t = i / W;
+      const int yy = (int)(t % H);
+      const int b = (int)(t / H);
+      const __nv_bfloat16* s = src + pv_off(in, b, yy, xx) + chunk * 8;
+      float h[8], l[8], v[8];
+      b_unpack8(*reinterpret_cast<const uint4*>(s), h);
+      b_unpack8(*reinterpret_cast<const uint4*>(s + in.c), l);
+      b_unpack8(*reinterpret_cast<const uint4*>(s + 2 * in.c), v);
+      float gmj[C], gvj[C];
+#pragma unroll
+      for (int j = 0; j < C; ++j) { gmj[j] = g_mu[i * C + j]; gvj[j] = g_var[i * C + j]; }
+#pragma unroll
+      for (int e = 0; e < 8; ++e) {
+        const float mu = h[e] + l[e];
+#pragma unroll
+        for (int j = 0; j < C; ++j) {
+          am[e][j] = fmaf(mu, gmj[j], am[e][j]);
+          av[e][j] = fmaf(v[e], gvj[j], av[e][j]);
+        }
+      }
+      if (chunk == 0) {
+        const float r = rsum[i];
+#pragma unroll
+        for (int j = 0; j < C; ++j) ad[j] = fmaf(gvj[j], r, ad[j]);
+      }
+    }
+  }
+  // reduce over the 8 pixel lanes (lane bits 2..4)
+#pragma unroll
+  for (int o = 4; o < 32; o <<= 1) {
+#pragma unroll
+    for (int e = 0; e < 8; ++e)
+#pragma unroll
+      for (int j = 0; j < C; ++j) {
+        am[e][j] += __shfl_xor_sync(0xffffffffu, am[e][j], o);
+        av[e][j] += __shfl_xor_sync(0xffffffffu, av[e][j], o);
+      }
+#pragma unroll
+    for (int j = 0; j < C; ++j) ad[j] += __shfl_xor_sync(0xffffffffu, ad[j], o);
+  }
+  if (psub == 0) {
+#pragma unroll
+    for (int e = 0; e < 8; ++e)
+#pragma unroll
+      for (int j = 0; j < C; ++j) {
+        atomicAdd(p_mu + (size_t)(chunk * 8 + e) * C + j, am[e][j]);
+        atomicAdd(p_var + (size_t)(chunk * 8 + e) * C + j, av[e][j]);
+      }
+    if (chunk == 0) {
+#pragma unroll
+      for (int j = 0; j < C; ++j) atomicAdd(ds + j, ad[j]);
+    }
+  }
+}
+
+// g_w = P_mu + 2 W P_var (p_var may be NULL: first layer) ; g_w_sigma[n] = sigmoid(w_sigma[n]) ds[n]
+__global__ void thin_wgrad_finalize_kernel(size_t n_w, int cout, const float* __restrict__ w,
+                                           const float* __restrict__ ws, const float* __restrict__ p_mu,
+                                           const float* __restrict__ p_var, const float* __restrict__ ds,
+                                           float* __restrict__ g_w, float* __restrict__ g_ws) {
+  const size_t stride = (size_t)gridDim.x * blockDim.x;
+  const size_t t0 = blockIdx.x * (size_t)blockDim.x + threadIdx.x;
+  for (size_t i = t0; i < n_w; i += stride) g_w[i] = p_var ? fmaf(2.f * w[i], p_var[i], p_mu[i]) : p_mu[i];
+  for (size_t i = t0; i < (size_t)cout; i += stride) g_ws[i] = sigmoid_f(ws[i]) * ds[i];
+}
+
 static int check_pv(const sn_packed_view* v, int batch, int h, int w, int c, const char* who) {
   SN_REQUIRE(v && v->base && aligned16(v->base), SN_ERR_BAD_ARG, "%s: null/misaligned packed view", who);
   SN_REQUIRE(v->n >= batch && v->c % 8 == 0 && v->c0 % 8 == 0 && c % 8 == 0, SN_ERR_MISALIGNED,
@@ -596,6 +795,67 @@ int sn_first_conv_bwd_data_packed(int32_t batch, int32_t in_h, int32_t in_w, int
   }
 #undef SN_FCB
   return check_launch("first_conv_bwd");
+}
+
+int sn_first_conv_bwd_weight_packed(int32_t batch, int32_t in_h, int32_t in_w, int32_t cin, int32_t cout,
+                                    int32_t ksize, const float* x, const float* w_sigma, const sn_packed_view* g_out,
+                                    void* workspace, float* g_w_mu, float* g_w_sigma, sn_stream_t st) {
+  SN_REQUIRE(x && w_sigma && workspace && g_w_mu && g_w_sigma, SN_ERR_BAD_ARG, "first_conv_wgrad: null pointer");
+  SN_REQUIRE(batch > 0 && ksize == 3 && cout == 32 && (cin == 4 || cin == 1) && in_h >= 3 && in_w >= 3,
+             SN_ERR_UNSUPPORTED, "first_conv_wgrad: supports k = 3, 32 output channels, cin 1 or 4 (got k %d, cout %d, cin %d)",
+             ksize, cout, cin);
+  int rc = check_pv(g_out, batch, in_h - 2, in_w - 2, cout, "first_conv_wgrad g_out");
+  if (rc) return rc;
+  cudaStream_t s = as_stream(st);
+  const size_t n_w = (size_t)9 * cin * cout;
+  float* wsf = reinterpret_cast<float*>(workspace);      // [n_w] P_mu, then [cout] ds
+  if (cudaMemsetAsync(wsf, 0, (n_w + cout) * sizeof(float), s) != cudaSuccess)
+    return fail(SN_ERR_LAUNCH, "first_conv_wgrad: memset failed");
+  const int tiles_x = (in_w - 2 + FW_TW - 1) / FW_TW, tiles_y = (in_h - 2 + FW_TH - 1) / FW_TH;
+  const long long tiles = (long long)batch * tiles_x * tiles_y;
+  const int grid = (int)(tiles < (long long)num_sms() * 2 ? tiles : (long long)num_sms() * 2);
+  if (cin == 4)
+    first_conv_wgrad_k3c32_kernel<4><<<grid, FW_THREADS, 0, s>>>(batch, in_h, in_w, x, *g_out, wsf, wsf + n_w, tiles_x,
+                                                                 tiles_y);
+  else
+    first_conv_wgrad_k3c32_kernel<1><<<grid, FW_THREADS, 0, s>>>(batch, in_h, in_w, x, *g_out, wsf, wsf + n_w, tiles_x,
+                                                                 tiles_y);
+  if ((rc = check_launch("first_conv_wgrad"))) return rc;
+  thin_wgrad_finalize_kernel<<<ew_grid(n_w, 256), 256, 0, s>>>(n_w, cout, nullptr, w_sigma, wsf, nullptr, wsf + n_w,
+                                                              g_w_mu, g_w_sigma);
+  return check_launch("first_conv_wgrad_finalize");
+}
+
+int sn_final_conv_bwd_weight_packed(const sn_packed_view* in, int32_t batch, int32_t in_h, int32_t in_w, int32_t cin,
+                                    int32_t n_labels, const float* w_mu, const float* w_sigma, const float* g_logit_mu,
+                                    const float* g_logit_var, const float* rsum, void* workspace, float* g_w_mu,
+                                    float* g_w_sigma, sn_stream_t st) {
+  SN_REQUIRE(w_mu && w_sigma && g_logit_mu && g_logit_var && rsum && workspace && g_w_mu && g_w_sigma, SN_ERR_BAD_ARG,
+             "final_conv_wgrad: null pointer");
+  SN_REQUIRE(cin == 32, SN_ERR_UNSUPPORTED, "final_conv_wgrad: cin %d (the networks feed conv_final 32 channels)", cin);
+  SN_REQUIRE(n_labels >= 1 && n_labels <= 8, SN_ERR_UNSUPPORTED, "final_conv_wgrad: %d classes (max 8)", n_labels);
+  int rc = check_pv(in, batch, in_h, in_w, cin, "final_conv_wgrad in");
+  if (rc) return rc;
+  cudaStream_t s = as_stream(st);
+  const size_t n_w = (size_t)cin * n_labels;
+  float* wsf = reinterpret_cast<float*>(workspace);      // P_mu [n_w], P_var [n_w], ds [n_labels]
+  if (cudaMemsetAsync(wsf, 0, (2 * n_w + n_labels) * sizeof(float), s) != cudaSuccess)
+    return fail(SN_ERR_LAUNCH, "final_conv_wgrad: memset failed");
+  const size_t total = (size_t)batch * in_h * in_w;
+  const int grid = ew_grid((total + 7) / 8 * 32, 256, 4);
+#define SN_FCW(CC)                                                                                                  \
+  case CC:                                                                                                          \
+    final_conv_wgrad_kernel<CC><<<grid, 256, 0, s>>>(*in, batch, in_h, in_w, g_logit_mu, g_logit_var, rsum, wsf,    \
+                                                     wsf + n_w, wsf + 2 * n_w);                                     \
+    break;
+  switch (n_labels) {
+    SN_FCW(1) SN_FCW(2) SN_FCW(3) SN_FCW(4) SN_FCW(5) SN_FCW(6) SN_FCW(7) SN_FCW(8)
+  }
+#undef SN_FCW
+  if ((rc = check_launch("final_conv_wgrad"))) return rc;
+  thin_wgrad_finalize_kernel<<<1, 256, 0, s>>>(n_w, n_labels, w_mu, w_sigma, wsf, wsf + n_w, wsf + 2 * n_w, g_w_mu,
+                                               g_w_sigma);
+  return check_launch("final_conv_wgrad_finalize");
 }
 
 }  // extern "C"

@@ -289,12 +289,17 @@ class GradientEngine(InferenceEngine):
                 if self.train:
                     # conv_final (32 -> n_labels, k = 1) and conv_input (Cin <= 8) are too thin for the tensor
                     # cores: their weight gradients run in the FP32-mode kernel on unpacked operands
-                    mu32 = torch.empty((B, r["h"], r["w"], r["c"]), device=dev)
-                    var32 = torch.empty_like(mu32)
                     names.append("conv_final_wgrad")
-                    steps.append(lambda src=src, r=r, mu32=mu32, var32=var32: self._wgrad_f32(
-                        "conv_final", src.buf, mu32, var32, logit_grads[0], logit_grads[1], logit_grads[2], wf, wsf,
-                        r["h"], r["w"], r["c"], C, 1))
+                    if r["c"] == 32:
+                        gwf, gwsf = self.grads["conv_final"]
+                        steps.append(lambda src=src, r=r: F.final_conv_bwd_weight_packed(
+                            src, B, r["h"], r["w"], r["c"], wf, wsf, logit_grads, self._wg_work, gwf, gwsf))
+                    else:                               # other widths: the general FP32-mode kernel on unpacked operands
+                        mu32 = torch.empty((B, r["h"], r["w"], r["c"]), device=dev)
+                        var32 = torch.empty_like(mu32)
+                        steps.append(lambda src=src, r=r, mu32=mu32, var32=var32: self._wgrad_f32(
+                            "conv_final", src.buf, mu32, var32, logit_grads[0], logit_grads[1], logit_grads[2], wf,
+                            wsf, r["h"], r["w"], r["c"], C, 1))
             elif kind == "conv":
                 name = r["name"]
                 wt = self.prepared_bwd[name]
@@ -328,13 +333,18 @@ class GradientEngine(InferenceEngine):
                 if self.train:
                     a0 = r["dst"].buf
                     _, ah, aw, _, ac = a0.shape
-                    gm32 = torch.empty((B, ah, aw, ac), device=dev)
-                    gv32 = torch.empty_like(gm32)
-                    rs0 = torch.empty((B, ah, aw), device=dev)
                     k0 = w_in.shape[0]
                     names.append("conv_input_wgrad")
-                    steps.append(lambda r=r, gm32=gm32, gv32=gv32, rs0=rs0: self._first_wgrad(
-                        g_of(r["dst"]).buf, gm32, gv32, rs0, w_in, ws_in, k0))
+                    if k0 == 3 and ac == 32 and Cin in (1, 4):
+                        gw0, gws0 = self.grads["conv_input"]
+                        steps.append(lambda r=r: F.first_conv_bwd_weight_packed(
+                            self.x_in, w_in, ws_in, g_of(r["dst"]), self._wg_work, gw0, gws0))
+                    else:
+                        gm32 = torch.empty((B, ah, aw, ac), device=dev)
+                        gv32 = torch.empty_like(gm32)
+                        rs0 = torch.empty((B, ah, aw), device=dev)
+                        steps.append(lambda r=r, gm32=gm32, gv32=gv32, rs0=rs0: self._first_wgrad(
+                            g_of(r["dst"]).buf, gm32, gv32, rs0, w_in, ws_in, k0))
                 else:                                    # the input gradient is what FGSM needs; training stops here
                     names.append("conv_input_dgrad")
                     steps.append(lambda r=r: F.first_conv_bwd_data_packed(self.x_in, w_in, ws_in, g_of(r["dst"]),

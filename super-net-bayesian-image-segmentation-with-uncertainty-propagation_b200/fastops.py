@@ -214,3 +214,23 @@ def conv_moments_bwd_weight_tc(g_out: PackedView, batch: int, in_h: int, in_w: i
 def first_conv_rsum(x: Tensor, ksize: int, rsum: Tensor) -> None:
     B, H, W, cin = x.shape
     check(_lib.load().sn_first_conv_rsum(B, H, W, cin, ksize, ptr(x), ptr(rsum), stream_ptr()), "first_conv_rsum")
+
+
+def first_conv_bwd_weight_packed(x: Tensor, w_mu: Tensor, w_sigma: Tensor, g_out: PackedView, workspace: Tensor,
+                                 g_w_mu: Tensor, g_w_sigma: Tensor) -> None:
+    B, H, W, cin = x.shape
+    k, _, _, cout = w_mu.shape
+    g = g_out.c_view()
+    check(_lib.load().sn_first_conv_bwd_weight_packed(B, H, W, cin, cout, k, ptr(x), ptr(w_sigma), C.byref(g),
+                                                      ptr(workspace), ptr(g_w_mu), ptr(g_w_sigma), stream_ptr()),
+          "first_conv_bwd_weight_packed")
+
+
+def final_conv_bwd_weight_packed(inp: PackedView, batch: int, in_h: int, in_w: int, cin: int, w_mu: Tensor,
+                                 w_sigma: Tensor, logit_grads: Tuple[Tensor, Tensor, Tensor], workspace: Tensor,
+                                 g_w_mu: Tensor, g_w_sigma: Tensor) -> None:
+    a = inp.c_view()
+    check(_lib.load().sn_final_conv_bwd_weight_packed(C.byref(a), batch, in_h, in_w, cin, w_mu.shape[-1], ptr(w_mu),
+                                                      ptr(w_sigma), ptr(logit_grads[0]), ptr(logit_grads[1]),
+                                                      ptr(logit_grads[2]), ptr(workspace), ptr(g_w_mu),
+                                                      ptr(g_w_sigma), stream_ptr()), "final_conv_bwd_weight_packed")

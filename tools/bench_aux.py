@@ -1,6 +1,6 @@
 """Secondary measurements (BASELINE.json configs 3 and 4; not the bench.py headline): FGSM input-gradient steps/s and
-ELBO training steps/s in FP32 mode, single GPU or batch-sharded under torchrun with the NCCL gradient all-reduce.
-usage: [torchrun ...] python tools/bench_aux.py [--variant brats|hippocampus] [--batch B] [--steps K]"""
+ELBO training steps/s in FP32 mode (CUDA-core kernels + autograd) or FAST mode (tcgen05 forward / dgrad / wgrad), single GPU or batch-sharded under torchrun with the NCCL gradient all-reduce.
+usage: [torchrun ...] python tools/bench_aux.py [--variant brats|hippocampus] [--batch B] [--steps K] [--mode fp32|fast]"""
 import argparse
 import json
 import os
@@ -18,6 +18,7 @@ ap = argparse.ArgumentParser()
 ap.add_argument("--variant", default="brats")
 ap.add_argument("--batch", type=int, default=8, help="slices per GPU")
 ap.add_argument("--steps", type=int, default=5)
+ap.add_argument("--mode", default="fp32", choices=["fp32", "fast"])
 args = ap.parse_args()
 world = int(os.environ.get("WORLD_SIZE", "1"))
 rank = int(os.environ.get("RANK", "0"))
@@ -29,7 +30,7 @@ if world > 1:
 C, in_ch = (4, 4) if args.variant == "brats" else (3, 1)
 hw = O.output_hw(args.variant)
 w = O.make_weights(args.variant, 32, C, in_ch)
-model = S.Density_prop_with_pad_UNET(32, C, variant=args.variant).load_weight_dict(w, device=dev)
+model = S.Density_prop_with_pad_UNET(32, C, variant=args.variant, mode=args.mode).load_weight_dict(w, device=dev)
 B = args.batch
 alpha = O.BRATS_ALPHA if args.variant == "brats" else 1.0
 x = O.make_input(args.variant, B, seed=2025 + rank, alpha=alpha).to(dev)
@@ -68,7 +69,7 @@ if world > 1:
 else:
     in_sync = True
 if rank == 0:
-    print(json.dumps({"variant": args.variant, "n_gpus": world, "batch_per_gpu": B, "mode": "fp32",
+    print(json.dumps({"variant": args.variant, "n_gpus": world, "batch_per_gpu": B, "mode": args.mode,
                       "fgsm_ms_per_step": round(fgsm_ms, 3), "fgsm_slices_per_s": round(B * world / fgsm_ms * 1e3, 1),
                       "train_ms_per_step": round(train_ms, 3),
                       "train_slices_per_s": round(B * world / train_ms * 1e3, 1), "replicas_in_sync": in_sync}))

@@ -18,6 +18,7 @@ ap.add_argument("--variant", default="brats")
 ap.add_argument("--batch", type=int, default=64)
 ap.add_argument("--steps", type=int, default=20)
 ap.add_argument("--study", action="store_true")
+ap.add_argument("--train", action="store_true", help="time the training chain (weight gradients) instead")
 args = ap.parse_args()
 C, in_ch, hw_in = (4, 4, 204) if args.variant == "brats" else (3, 1, 64)
 hw = O.output_hw(args.variant)
@@ -25,7 +26,9 @@ alpha = O.BRATS_ALPHA if args.variant == "brats" else 1.0
 w = O.make_weights(args.variant, 32, C, in_ch)
 model = S.Density_prop_with_pad_UNET(32, C, variant=args.variant, mode="fast").load_weight_dict(w, device="cuda")
 B = args.batch
-eng = GradientEngine(model, B, hw_in, hw_in, in_ch, "cuda", graph=True)
+eng = GradientEngine(model, B, hw_in, hw_in, in_ch, "cuda", graph=True, train=args.train)
+if args.train:
+    eng._loss_scale, eng._clip = 1.0, (1e-12, 1e3)
 eng.x_in.copy_(O.make_input(args.variant, B, alpha=alpha))
 eng.y_in.copy_(O.make_labels(B, hw * hw, C))
 for _ in range(3):
@@ -54,7 +57,7 @@ for name, fn in zip(names, fns):
     torch.cuda.synchronize()
     rows.append({"name": name, "ms": round(e0.elapsed_time(e1) / 5, 4)})
 fwd_ms = sum(r["ms"] for r in rows[:len(eng.step_names)])
-out = {"variant": args.variant, "batch": B, "fgsm_ms_per_step": round(ms, 4),
+out = {"variant": args.variant, "batch": B, "chain": "train (fwd + dgrad + wgrad)" if args.train else "fgsm (fwd + dgrad)", "fgsm_ms_per_step": round(ms, 4),
        "fgsm_slices_per_s": round(B / ms * 1e3, 1), "launches": len(names) + 1,
        "forward_ms_sum": round(fwd_ms, 4), "backward_ms_sum": round(sum(r["ms"] for r in rows) - fwd_ms, 4),
        "kernels": rows}
