@@ -253,7 +253,9 @@ int sn_conv_moments_bwd_data_tc(const sn_tc_dgrad_desc* d, sn_stream_t st);
  *   g_w_mu = corr(mu_in, g_mu_out) + 2 W . corr(var_in, g_var_out);  g_w_sigma[n] = sigmoid(w_sigma[n]) sum_p g_var_out[p,n] rsum[p].
  * Two pixel-axis GEMMs (tcgen05, MN-major operands straight from the NHWC planes, split-K with fp32 atomics into
  * `workspace`, sn_wgrad_workspace_bytes() bytes, zeroed by the call), then a finalize pass.  Outputs are overwritten.
- * in[]/in_c[]/g_out/flags as in sn_tc_dgrad_desc; rsum = the forward's rsum_out; w_mu HWIO fp32, w_sigma raw. */
+ * in[]/in_c[]/g_out/flags as in sn_tc_dgrad_desc; rsum = the forward's rsum_out; w_mu HWIO fp32, w_sigma raw.
+ * k = 3 layers run the row-halo kernel (one tiled TMA band of full-width rows, taps as K-row shifts of the MN-major
+ * tile); SN_TC_IM2COL forces the general kernel (TMA im2col per tap) that k = 1 / 2 and the up-conv always use. */
 typedef struct sn_tc_wgrad_desc {
   sn_packed_view g_out;
   sn_packed_view in[2];

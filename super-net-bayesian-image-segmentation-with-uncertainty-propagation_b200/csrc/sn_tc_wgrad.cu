@@ -236,6 +236,212 @@ __global__ void __launch_bounds__(WG_THREADS, 1) conv_moments_wgrad_kernel(const
 }
 
 // ---------------------------------------------------------------------------------------------------------
+// Row-halo form for k = 3 (the forward's tap-as-row-shift trick on the pixel axis).
+//
+// TMA im2col re-fetches every activation block once per tap and, with 64-byte rows, tops out near 16 B/clk per SM
+// (measured: the kernel above runs at 4-15 % tensor pipe on every layer).  Here ONE tiled TMA box brings a band of
+// full-width input rows {32 ch, R = in_w, THb rows, TN images} (row = pixel, 64-byte swizzled) and all nine taps
+// read it in place: in an MN-major operand the pixel is the K index, so tap (kh, kw) is the same tile with the
+// descriptor start advanced by (kh*R + kw) rows.  The three kw shifts of one kh even share one UMMA: M = 128 =
+// 4 blocks of 32 channels with LBO = 64 B, i.e. block i is the tile shifted by i pixels (block 3 is junk and never
+// stored).  The gradient tile uses the same row pitch: its box is {32 ch, R, rows, TN} over a tensor map whose
+// extents are the OUTPUT grid (Wo x Ho), so the k-1 junk columns (and, for whole-image tiles, junk rows) arrive as
+// TMA out-of-bounds zeros and contribute nothing.  Rows past the box (K padding to a multiple of 16) are zeroed once.
+//   job = (32-channel input block, N tile of 32/64 output channels, split of the row bands); TMEM holds the
+//   3 (kh) x 2 (mean, var) accumulators of 128 x NT.
+constexpr int WR_STAGES = 2;
+constexpr int WR_STAGE_MAX = 110 * 1024;
+constexpr int WR_SMEM = WR_STAGES * WR_STAGE_MAX + 1024 + 256;
+
+struct WrMaps {
+  CUtensorMap a[2][2];     // [forward source][plane: mean_hi, variance] tiled boxes {32, R, THb, TN}
+  CUtensorMap g[2];        // [plane: g_mean_hi, g_variance] tiled boxes {32, R, THg, TN}
+};
+
+struct WrP {
+  int cblk0, cblk1, nb_n, n_tiles, splits, total_jobs;
+  int R, THo, THb, THg, TN, tiles_y, tiles_b, tiles_total, tiles_per_split;
+  int rows_a, rows_g, ksteps;      // box rows of A / G, K steps of 16 pixels per tile
+  int a_plane, g_blk, stage;       // bytes: one A plane, one 32-channel G block, one pipeline stage
+  int cin, cout;
+  float* p_mu;
+  float* p_var;
+};
+
+__device__ __forceinline__ uint64_t wr_desc(uint32_t smem_addr, uint32_t lbo_bytes) {
+  return (uint64_t)((smem_addr >> 4) & 0x3FFF) | ((uint64_t)(lbo_bytes >> 4) << 16) | ((uint64_t)(512 >> 4) << 32) |
+         ((uint64_t)1 << 46) | ((uint64_t)4 << 61);
+}
+
+template <int NT>
+__global__ void __launch_bounds__(WG_THREADS, 1) conv_moments_wgrad_rows_kernel(const __grid_constant__ WrMaps maps,
+                                                                                const WrP p) {
+  constexpr int TMEM_COLS = NT == 32 ? 256 : 512;      // 6 * NT accumulator columns, rounded up to a power of two
+  extern __shared__ uint8_t smem_raw[];
+  const uint32_t smem_base = (ptx::smem_u32(smem_raw) + 1023u) & ~1023u;
+  uint8_t* smem_gen = smem_raw + (smem_base - ptx::smem_u32(smem_raw));
+  const uint32_t bar_base = smem_base + WR_STAGES * p.stage;
+  auto full_bar = [&](int s) { return bar_base + 8u * s; };
+  auto empty_bar = [&](int s) { return bar_base + 8u * (WR_STAGES + s); };
+  const uint32_t acc_full = bar_base + 8u * (2 * WR_STAGES);
+  const uint32_t acc_empty = bar_base + 8u * (2 * WR_STAGES + 1);
+  const uint32_t tmem_slot = bar_base + 8u * (2 * WR_STAGES + 2);
+  volatile uint32_t* tmem_slot_gen =
+      reinterpret_cast<volatile uint32_t*>(smem_gen + WR_STAGES * p.stage + 8 * (2 * WR_STAGES + 2));
+
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int cblk = p.cblk0 + p.cblk1;
+
+  // rows the TMA boxes never write are read by the UMMAs as K padding / shifted tails: zero everything once
+  for (int i = threadIdx.x; i < WR_STAGES * p.stage / 16; i += WG_THREADS)
+    reinterpret_cast<uint4*>(smem_gen)[i] = make_uint4(0, 0, 0, 0);
+  ptx::fence_proxy_async();
+  if (warp == 0 && lane == 0) {
+    for (int s = 0; s < 2; ++s)
+      for (int pl = 0; pl < 2; ++pl) ptx::prefetch_tensormap(&maps.a[s][pl]);
+    for (int pl = 0; pl < 2; ++pl) ptx::prefetch_tensormap(&maps.g[pl]);
+    for (int s = 0; s < WR_STAGES; ++s) {
+      ptx::mbar_init(full_bar(s), 1);
+      ptx::mbar_init(empty_bar(s), 1);
+    }
+    ptx::mbar_init(acc_full, 1);
+    ptx::mbar_init(acc_empty, 4);
+    ptx::fence_barrier_init();
+  }
+  if (warp == 1) {
+    ptx::tmem_alloc(tmem_slot, TMEM_COLS);
+    ptx::tmem_relinquish();
+  }
+  ptx::tc_fence_before();
+  __syncthreads();
+  ptx::tc_fence_after();
+  const uint32_t tmem_base = *tmem_slot_gen;
+  const int jobs_cn = cblk * p.n_tiles;
+
+  if (warp == 0) {
+    // ===================== TMA producer =====================
+    if (lane == 0) {
+      const uint32_t bytes = (uint32_t)((2 * p.rows_a + 2 * p.nb_n * p.rows_g) * 64);
+      int it = 0;
+      for (int job = blockIdx.x; job < p.total_jobs; job += gridDim.x) {
+        const int cbt = job % cblk;
+        const int nt = (job / cblk) % p.n_tiles;
+        const int sp = job / jobs_cn;
+        const int src = cbt >= p.cblk0 ? 1 : 0;
+        const int cb = src ? cbt - p.cblk0 : cbt;
+        const int t0 = sp * p.tiles_per_split;
+        int t1 = t0 + p.tiles_per_split;
+        if (t1 > p.tiles_total) t1 = p.tiles_total;
+        for (int t = t0; t < t1; ++t, ++it) {
+          const int stage = it % WR_STAGES;
+          const uint32_t parity = (uint32_t)(it / WR_STAGES) & 1u;
+          ptx::mbar_wait(empty_bar(stage), parity ^ 1u);
+          ptx::mbar_arrive_expect_tx(full_bar(stage), bytes);
+          const int ty = t % p.tiles_y, tb = t / p.tiles_y;
+          const int y0 = ty * p.THo, b0 = tb * p.TN;
+          const uint32_t sa = smem_base + stage * p.stage;
+          const uint32_t sg = sa + 2 * p.a_plane;
+#pragma unroll
+          for (int pl = 0; pl < 2; ++pl)
+            asm volatile(
+                "cp.async.bulk.tensor.4d.shared::cluster.global.mbarrier::complete_tx::bytes"
+                " [%0], [%1, {%3, %4, %5, %6}], [%2];"
+                :
+                : "r"(sa + pl * p.a_plane), "l"(reinterpret_cast<uint64_t>(&maps.a[src][pl])), "r"(full_bar(stage)),
+                  "r"(cb * 32), "r"(0), "r"(y0), "r"(b0)
+                : "memory");
+          for (int j = 0; j < p.nb_n; ++j)
+#pragma unroll
+            for (int pl = 0; pl < 2; ++pl)
+              asm volatile(
+                  "cp.async.bulk.tensor.4d.shared::cluster.global.mbarrier::complete_tx::bytes"
+                  " [%0], [%1, {%3, %4, %5, %6}], [%2];"
+                  :
+                  : "r"(sg + (pl * p.nb_n + j) * p.g_blk), "l"(reinterpret_cast<uint64_t>(&maps.g[pl])),
+                    "r"(full_bar(stage)), "r"((nt * p.nb_n + j) * 32), "r"(0), "r"(y0), "r"(b0)
+                  : "memory");
+        }
+      }
+    }
+  } else if (warp == 1) {
+    // ===================== UMMA issuer =====================
+    if (lane == 0) {
+      constexpr uint32_t idesc = wg_idesc(128, NT);
+      int it = 0, jobi = 0;
+      for (int job = blockIdx.x; job < p.total_jobs; job += gridDim.x, ++jobi) {
+        const int sp = job / jobs_cn;
+        const int t0 = sp * p.tiles_per_split;
+        int t1 = t0 + p.tiles_per_split;
+        if (t1 > p.tiles_total) t1 = p.tiles_total;
+        ptx::mbar_wait(acc_empty, ((uint32_t)jobi & 1u) ^ 1u);
+        ptx::tc_fence_after();
+        for (int t = t0; t < t1; ++t, ++it) {
+          const int stage = it % WR_STAGES;
+          const uint32_t parity = (uint32_t)(it / WR_STAGES) & 1u;
+          ptx::mbar_wait(full_bar(stage), parity);
+          ptx::tc_fence_after();
+          const uint32_t sa = smem_base + stage * p.stage;
+          const uint32_t sg = sa + 2 * p.a_plane;
+          const uint32_t gv_off = (uint32_t)(p.nb_n * p.g_blk);
+#pragma unroll 1
+          for (int kh = 0; kh < 3; ++kh) {
+            const uint32_t acc_mu = tmem_base + (uint32_t)(kh * 2 * NT), acc_var = acc_mu + NT;
+            const uint32_t a_kh = sa + (uint32_t)(kh * p.R) * 64u;
+#pragma unroll 1
+            for (int ks = 0; ks < p.ksteps; ++ks) {
+              const uint32_t koff = (uint32_t)ks * 1024u;       // 16 pixels = 16 rows of 64 B
+              const uint32_t acc = (t > t0 || ks > 0) ? 1u : 0u;
+              ptx::umma_bf16(acc_mu, wr_desc(a_kh + koff, 64u), wr_desc(sg + koff, (uint32_t)p.g_blk), idesc, acc);
+              ptx::umma_bf16(acc_var, wr_desc(a_kh + p.a_plane + koff, 64u),
+                             wr_desc(sg + gv_off + koff, (uint32_t)p.g_blk), idesc, acc);
+            }
+          }
+          ptx::umma_commit(empty_bar(stage));
+        }
+        ptx::umma_commit(acc_full);
+      }
+    }
+  } else {
+    // ===================== epilogue =====================
+    const int q = warp & 3;                   // TMEM lane quarter == kw shift block (3 = junk)
+    int jobi = 0;
+    for (int job = blockIdx.x; job < p.total_jobs; job += gridDim.x, ++jobi) {
+      const int cbt = job % cblk;
+      const int nt = (job / cblk) % p.n_tiles;
+      ptx::mbar_wait(acc_full, (uint32_t)jobi & 1u);
+      ptx::tc_fence_after();
+      if (q < 3) {
+        const int ci = cbt * 32 + lane;
+        const uint32_t lane_base = tmem_base + ((uint32_t)(q * 32) << 16);
+#pragma unroll 1
+        for (int kh = 0; kh < 3; ++kh) {
+#pragma unroll 1
+          for (int c0 = 0; c0 < NT; c0 += 16) {
+            uint32_t am[16], av[16];
+            ptx::tmem_ld16(lane_base + kh * 2 * NT + c0, am);
+            ptx::tmem_ld16(lane_base + kh * 2 * NT + NT + c0, av);
+            ptx::tmem_ld_wait();
+            const size_t o = ((size_t)(kh * 3 + q) * p.cin + ci) * p.cout + nt * NT + c0;
+#pragma unroll
+            for (int j = 0; j < 16; ++j) {
+              atomicAdd(p.p_mu + o + j, __uint_as_float(am[j]));
+              atomicAdd(p.p_var + o + j, __uint_as_float(av[j]));
+            }
+          }
+        }
+      }
+      ptx::tc_fence_before();
+      __syncwarp();
+      if (lane == 0) ptx::mbar_arrive(acc_empty);
+    }
+  }
+
+  ptx::tc_fence_before();
+  __syncthreads();
+  if (warp == 1) ptx::tmem_dealloc(tmem_base, TMEM_COLS);
+}
+
+// ---------------------------------------------------------------------------------------------------------
 // finalize: g_w = P_mu + 2 W P_var ;  g_w_sigma[n] = sigmoid(w_sigma[n]) * dsig[n]
 // ---------------------------------------------------------------------------------------------------------
 __global__ void wgrad_finalize_kernel(size_t n_w, int cout, const float* __restrict__ w, const float* __restrict__ ws,
@@ -381,6 +587,106 @@ static int wg_launch(const WgMaps& maps, const WgP& p, cudaStream_t st) {
   return check_launch("conv_moments_wgrad");
 }
 
+typedef CUresult (*WrEncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*,
+                                    const cuuint64_t*, const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave,
+                                    CUtensorMapSwizzle, CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+static WrEncodeTiledFn wr_encode_tiled() {
+  static WrEncodeTiledFn fn = nullptr;
+  static std::once_flag once;
+  std::call_once(once, [] {
+    void* f = nullptr;
+    cudaDriverEntryPointQueryResult q;
+    if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &f, cudaEnableDefault, &q) == cudaSuccess &&
+        q == cudaDriverEntryPointSuccess)
+      fn = reinterpret_cast<WrEncodeTiledFn>(f);
+  });
+  return fn;
+}
+
+// Tiled map over one plane of a packed window with extents (w x h): a box may overhang them (zero fill).
+static int wr_make_map(CUtensorMap* out, const sn_packed_view& v, int plane, int c, int batch, int h, int w, int box_w,
+                       int box_h, int box_n) {
+  const size_t pix = (size_t)3 * v.c;
+  char* base = reinterpret_cast<char*>(v.base) +
+               ((((size_t)v.y0 * v.w + v.x0) * 3 + plane) * v.c + v.c0) * sizeof(__nv_bfloat16);
+  cuuint64_t dims[4] = {(cuuint64_t)c, (cuuint64_t)w, (cuuint64_t)h, (cuuint64_t)batch};
+  cuuint64_t strides[3] = {pix * 2, (cuuint64_t)v.w * pix * 2, (cuuint64_t)v.h * v.w * pix * 2};
+  cuuint32_t box[4] = {32, (cuuint32_t)box_w, (cuuint32_t)box_h, (cuuint32_t)box_n};
+  cuuint32_t estr[4] = {1, 1, 1, 1};
+  CUresult r = wr_encode_tiled()(out, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 4, base, dims, strides, box, estr,
+                                 CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_64B,
+                                 CU_TENSOR_MAP_L2_PROMOTION_L2_128B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  if (r != CUDA_SUCCESS) return fail(SN_ERR_DRIVER, "cuTensorMapEncodeTiled(wgrad rows) failed (%d)", (int)r);
+  return SN_OK;
+}
+
+// Tile plan of the row-halo kernel; returns false when the layer does not fit (the im2col kernel takes it).
+static bool wr_plan(WrP& p, int batch, int in_h, int in_w, int cin0, int cin1, int cout) {
+  if (in_w > 256 || wr_encode_tiled() == nullptr) return false;
+  const int R = in_w, Ho = in_h - 2;
+  p.R = R;
+  p.cblk0 = cin0 / 32; p.cblk1 = cin1 / 32;
+  p.cin = cin0 + cin1; p.cout = cout;
+  p.nb_n = (cout / 32) % 2 == 0 ? 2 : 1;
+  p.n_tiles = cout / 32 / p.nb_n;
+  auto fits = [&](int rows_a, int rows_g) {
+    const int ks = (rows_g + 15) / 16;
+    const int need_a = 16 * ks + 2 * R + 3 > rows_a ? 16 * ks + 2 * R + 3 : rows_a;
+    p.ksteps = ks;
+    p.a_plane = ((need_a * 64 + 1023) / 1024) * 1024;
+    p.g_blk = ((16 * ks * 64 + 1023) / 1024) * 1024;
+    p.stage = 2 * p.a_plane + 2 * p.nb_n * p.g_blk;
+    // UMMA descriptor fields: LBO (g_blk) and every start address must stay below the 14-bit x 16 B range
+    return p.stage <= WR_STAGE_MAX && p.g_blk < (1 << 18);
+  };
+  // whole (small) images, several per tile: gradient box = input box, junk rows/columns are out-of-bounds zeros
+  int tn = 0;
+  for (int t = 1; t <= batch && t <= 256 && in_h <= 256; ++t) {
+    if (!fits(t * in_h * R, t * in_h * R)) break;
+    tn = t;
+  }
+  if (tn >= 1) {
+    fits(tn * in_h * R, tn * in_h * R);
+    p.TN = tn; p.THo = Ho; p.THb = in_h; p.THg = in_h;
+    p.tiles_y = 1; p.tiles_b = (batch + tn - 1) / tn;
+  } else {
+    int th = 0;
+    for (int t = 1; t <= Ho && t + 2 <= 256; ++t) {
+      if (!fits((t + 2) * R, t * R)) break;
+      th = t;
+    }
+    if (th < 1) return false;
+    fits((th + 2) * R, th * R);
+    p.TN = 1; p.THo = th; p.THb = th + 2; p.THg = th;
+    p.tiles_y = (Ho + th - 1) / th; p.tiles_b = batch;
+  }
+  p.rows_a = p.TN * p.THb * R;
+  p.rows_g = p.TN * p.THg * R;
+  p.tiles_total = p.tiles_y * p.tiles_b;
+  const int jobs_cn = (p.cblk0 + p.cblk1) * p.n_tiles;
+  int splits = (2 * num_sms() + jobs_cn - 1) / jobs_cn;
+  if (splits > p.tiles_total) splits = p.tiles_total;
+  if (splits < 1) splits = 1;
+  p.tiles_per_split = (p.tiles_total + splits - 1) / splits;
+  p.splits = (p.tiles_total + p.tiles_per_split - 1) / p.tiles_per_split;
+  p.total_jobs = jobs_cn * p.splits;
+  return true;
+}
+
+template <int NT>
+static int wr_launch(const WrMaps& maps, const WrP& p, cudaStream_t st) {
+  static std::once_flag once;
+  static cudaError_t attr_err = cudaSuccess;
+  std::call_once(once, [] {
+    attr_err = cudaFuncSetAttribute(conv_moments_wgrad_rows_kernel<NT>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                    WR_SMEM);
+  });
+  if (attr_err != cudaSuccess) return fail(SN_ERR_LAUNCH, "wgrad rows: cannot reserve %d B of shared memory", WR_SMEM);
+  const int grid = p.total_jobs < num_sms() ? p.total_jobs : num_sms();
+  conv_moments_wgrad_rows_kernel<NT><<<grid, WG_THREADS, WR_STAGES * p.stage + 1024 + 256, st>>>(maps, p);
+  return check_launch("conv_moments_wgrad_rows");
+}
+
 }  // namespace sn
 
 using namespace sn;
@@ -394,7 +700,8 @@ size_t sn_wgrad_workspace_bytes(int32_t ksize, int32_t cin, int32_t cout) {
 int sn_conv_moments_bwd_weight_tc(const sn_tc_wgrad_desc* d, sn_stream_t st) {
   SN_REQUIRE(d, SN_ERR_BAD_ARG, "wgrad_tc: null descriptor");
   const bool upconv = (d->flags & SN_TC_UPCONV) != 0;
-  SN_REQUIRE((d->flags & ~SN_TC_UPCONV) == 0, SN_ERR_BAD_ARG, "wgrad_tc: only SN_TC_UPCONV is a valid flag");
+  SN_REQUIRE((d->flags & ~(SN_TC_UPCONV | SN_TC_IM2COL)) == 0, SN_ERR_BAD_ARG,
+             "wgrad_tc: valid flags are SN_TC_UPCONV and SN_TC_IM2COL");
   SN_REQUIRE(d->batch > 0 && d->in_h > 0 && d->in_w > 0 && d->cout > 0, SN_ERR_BAD_ARG, "wgrad_tc: bad geometry");
   SN_REQUIRE(d->ksize >= 1 && d->ksize <= 3, SN_ERR_UNSUPPORTED, "wgrad_tc: kernel size %d", d->ksize);
   SN_REQUIRE(!upconv || d->ksize == 2, SN_ERR_BAD_ARG, "wgrad_tc: SN_TC_UPCONV needs ksize == 2");
@@ -443,8 +750,25 @@ int sn_conv_moments_bwd_weight_tc(const sn_tc_wgrad_desc* d, sn_stream_t st) {
   cudaError_t e = cudaMemsetAsync(d->workspace, 0, (2 * n_w + d->cout) * sizeof(float), stream);
   if (e != cudaSuccess) return fail(SN_ERR_LAUNCH, "wgrad_tc memset: %s", cudaGetErrorString(e));
 
-  WgMaps maps;
   const int planes[2] = {0, 2};
+  WrP rp{};
+  if (!upconv && d->ksize == 3 && !(d->flags & SN_TC_IM2COL) && wr_plan(rp, d->batch, d->in_h, d->in_w, d->in_c[0], d->in_c[1], d->cout)) {
+    rp.p_mu = p.p_mu; rp.p_var = p.p_var;
+    WrMaps rmaps;
+    for (int s = 0; s < 2; ++s) {
+      const int ss = d->in_c[s] ? s : 0;
+      for (int pl = 0; pl < 2; ++pl)
+        if ((rc = wr_make_map(&rmaps.a[s][pl], d->in[ss], planes[pl], d->in_c[ss], d->batch, d->in_h, d->in_w, rp.R,
+                              rp.THb, rp.TN)))
+          return rc;
+    }
+    for (int pl = 0; pl < 2; ++pl)
+      if ((rc = wr_make_map(&rmaps.g[pl], d->g_out, planes[pl], d->cout, d->batch, Ho, Wo, rp.R, rp.THg, rp.TN)))
+        return rc;
+    rc = rp.nb_n == 2 ? wr_launch<64>(rmaps, rp, stream) : wr_launch<32>(rmaps, rp, stream);
+    if (rc) return rc;
+  } else {
+  WgMaps maps;
   for (int s = 0; s < 2; ++s) {
     const int ss = d->in_c[s] ? s : 0;
     for (int pl = 0; pl < 2; ++pl)
@@ -463,6 +787,7 @@ int sn_conv_moments_bwd_weight_tc(const sn_tc_wgrad_desc* d, sn_stream_t st) {
     default: rc = wg_launch<32>(maps, p, stream); break;
   }
   if (rc) return rc;
+  }
   const size_t pixels = (size_t)d->batch * out_h * out_w;
   const int lanes = 256 / (d->cout / 8);
   size_t need = (pixels + lanes - 1) / lanes;

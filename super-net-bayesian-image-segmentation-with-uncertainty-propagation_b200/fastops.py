@@ -198,14 +198,15 @@ def wgrad_workspace(ksize: int, cin: int, cout: int, device) -> Tensor:
 def conv_moments_bwd_weight_tc(g_out: PackedView, batch: int, in_h: int, in_w: int, ksize: int, cout: int,
                                in0: PackedView, c0: int, rsum: Tensor, w_mu: Tensor, w_sigma: Tensor,
                                workspace: Tensor, g_w_mu: Tensor, g_w_sigma: Tensor,
-                               in1: Optional[PackedView] = None, c1: int = 0, upconv: bool = False) -> None:
+                               in1: Optional[PackedView] = None, c1: int = 0, upconv: bool = False,
+                               im2col: bool = False) -> None:
     d = sn_tc_wgrad_desc()
     d.g_out = g_out.c_view()
     d.in_[0] = in0.c_view()
     d.in_[1] = (in1 if in1 is not None else in0).c_view()
     d.in_c[0], d.in_c[1] = c0, c1
     d.batch, d.in_h, d.in_w, d.ksize, d.cout = batch, in_h, in_w, ksize, cout
-    d.flags = SN_TC_UPCONV if upconv else 0
+    d.flags = (SN_TC_UPCONV if upconv else 0) | (SN_TC_IM2COL if im2col else 0)
     d.rsum, d.w_mu, d.w_sigma = rsum.data_ptr(), w_mu.data_ptr(), w_sigma.data_ptr()
     d.workspace, d.g_w_mu, d.g_w_sigma = workspace.data_ptr(), g_w_mu.data_ptr(), g_w_sigma.data_ptr()
     check(_lib.load().sn_conv_moments_bwd_weight_tc(C.byref(d), stream_ptr()), "conv_moments_bwd_weight_tc")

@@ -285,8 +285,9 @@ WGRAD_CASES = [
 ]
 
 
-@pytest.mark.parametrize("case", WGRAD_CASES)
-def test_conv_wgrad_tc(S, case):
+@pytest.mark.parametrize("case", WGRAD_CASES + [(2, 70, 150, 32, 32, 3), (64, 24, 24, 128, 128, 3)])
+@pytest.mark.parametrize("im2col", [False, True], ids=["rows", "im2col"])
+def test_conv_wgrad_tc(S, case, im2col):
     F = S.fastops
     B, H, W, cin, cout, k = case
     mu, var, w, ws = layer(B, H, W, cin, cout, k, seed=sum(case))
@@ -308,10 +309,10 @@ def test_conv_wgrad_tc(S, case):
     gw = torch.full_like(wd, float("nan"))
     gws = torch.full_like(wsd, float("nan"))
     work = F.wgrad_workspace(k, cin, cout, "cuda")
-    F.conv_moments_bwd_weight_tc(g_out, B, H, W, k, cout, src, cin, rsum, wd, wsd, work, gw, gws)
+    F.conv_moments_bwd_weight_tc(g_out, B, H, W, k, cout, src, cin, rsum, wd, wsd, work, gw, gws, im2col=im2col)
     torch.cuda.synchronize()
     e_w, e_s = rel(gw, w.grad), rel(gws, ws.grad)
-    print(case, e_w, e_s)
+    print(case, im2col, e_w, e_s)
     assert e_w < W_TOL and e_s < W_TOL, (e_w, e_s)
 
 

@@ -51,6 +51,9 @@ with open(out, "w") as f:
     # launch list
     f.write("\n## launch list (`--metrics gpu__time_duration.sum`)\n\n| # | layer | kernel | us |\n|---|---|---|---|\n")
     lr = [r for r in csv.reader(l for l in open(launches) if l.startswith('"'))]
+    if not lr:          # metric-only capture: the table above already carries the per-launch times
+        print("wrote", out)
+        sys.exit(0)
     lh = lr[0]
     ik, iv, iu = lh.index("Kernel Name"), lh.index("Metric Value"), lh.index("Metric Unit")
     t2 = 0.0
