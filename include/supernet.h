@@ -174,7 +174,7 @@ size_t sn_prepared_weight_bytes(int32_t ksize, int32_t cin, int32_t cout);
 int sn_prepare_weights(const float* w_mu, const float* w_sigma, int32_t ksize, int32_t cin, int32_t cout,
                        int32_t upconv, void* w_packed, float* s_out, sn_stream_t st);
 
-enum { SN_TC_RELU = 1, SN_TC_UPCONV = 2, SN_TC_DST_F32 = 4, SN_TC_IM2COL = 8 };
+enum { SN_TC_RELU = 1, SN_TC_UPCONV = 2, SN_TC_DST_F32 = 4, SN_TC_IM2COL = 8, SN_TC_ROWS = 16 };
 
 /* One fused moment convolution on the tensor cores: myConv_intermediate.call (Brats.py:118-137), optionally
  * with the ReLU gate of Brats.py:233-238 (SN_TC_RELU), reading the channel-concat of up to two packed windows
@@ -255,7 +255,8 @@ int sn_conv_moments_bwd_data_tc(const sn_tc_dgrad_desc* d, sn_stream_t st);
  * `workspace`, sn_wgrad_workspace_bytes() bytes, zeroed by the call), then a finalize pass.  Outputs are overwritten.
  * in[]/in_c[]/g_out/flags as in sn_tc_dgrad_desc; rsum = the forward's rsum_out; w_mu HWIO fp32, w_sigma raw.
  * k = 3 layers run the row-halo kernel (one tiled TMA band of full-width rows, taps as K-row shifts of the MN-major
- * tile); SN_TC_IM2COL forces the general kernel (TMA im2col per tap) that k = 1 / 2 and the up-conv always use. */
+ * tile) unless both channel counts are >= 256 (few pixels: the general kernel is faster); SN_TC_IM2COL forces the
+ * general kernel (TMA im2col per tap) that k = 1 / 2 and the up-conv always use, SN_TC_ROWS forces the row-halo one. */
 typedef struct sn_tc_wgrad_desc {
   sn_packed_view g_out;
   sn_packed_view in[2];
@@ -306,6 +307,12 @@ int sn_head_bwd_packed(const sn_packed_view* in, int32_t batch, int32_t in_h, in
                        int32_t n_labels, const float* w_mu, const float* w_sigma, const float* y, float clip_lo,
                        float clip_hi, const double* acc, float loss_scale, const sn_packed_view* g_in,
                        float* g_logit_mu, float* g_logit_var, float* rsum_out, sn_stream_t st);
+
+/* Same chain for GIVEN upstream gradients w.r.t. the two outputs of mysoftmax (g_var_out may be NULL = 0): what
+ * create_saliency_map needs (Brats.py:598-609: d sum(masked p) / d x, no loss involved). */
+int sn_head_bwd_upstream_packed(const sn_packed_view* in, int32_t batch, int32_t in_h, int32_t in_w, int32_t cin,
+                                int32_t n_labels, const float* w_mu, const float* w_sigma, const float* g_p,
+                                const float* g_var_out, const sn_packed_view* g_in, sn_stream_t st);
 
 /* Input gradient of myConv_input (Brats.py:65-76; what create_adversarial_pattern returns the sign of):
  *   g_x = g_mu_out (*)^T W + 2 x . box^T(t),  t = sum_n g_var_out s_n;  g_out: packed (in_h-k+1 x in_w-k+1 x cout)

@@ -153,7 +153,11 @@ __global__ void __launch_bounds__(128) head_bwd_kernel(sn_packed_view in, int B,
                                                        const float* __restrict__ y, float clip_lo, float clip_hi,
                                                        const double* __restrict__ acc, float loss_scale,
                                                        sn_packed_view gin, float* __restrict__ g_logit_mu,
-                                                       float* __restrict__ g_logit_var, float* __restrict__ rsum_out) {
+                                                       float* __restrict__ g_logit_var, float* __restrict__ rsum_out,
+                                                       const float* __restrict__ up_gp,
+                                                       const float* __restrict__ up_gv) {
+  // up_gp != nullptr: the upstream gradients w.r.t. (p, var_out) are given (saliency, Brats.py:598-609) instead of
+  // being derived from the NLL; `y` and `acc` are then unused.
   extern __shared__ __align__(16) float hsm[];   // W [cin][C], W^2 [cin][C], s [C]
   float* sw = hsm;
   float* sw2 = hsm + cin * C;
@@ -166,7 +170,7 @@ __global__ void __launch_bounds__(128) head_bwd_kernel(sn_packed_view in, int B,
   for (int i = threadIdx.x; i < C; i += blockDim.x) ss[i] = softplus_f(ws[i]);
   __syncthreads();
   const size_t total = (size_t)B * H * W;
-  const float qmean = (float)(acc[0] / (double)total);
+  const float qmean = up_gp ? 0.f : (float)(acc[0] / (double)total);
   const float qon = (isnan(qmean) || isinf(qmean)) ? 0.f : 1.f;      // Brats.py:304-305
   const float g = 0.5f * loss_scale / (float)total;
   const __nv_bfloat16* src = reinterpret_cast<const __nv_bfloat16*>(in.base);
@@ -219,6 +223,11 @@ __global__ void __launch_bounds__(128) head_bwd_kernel(sn_packed_view in, int B,
       for (int j = 0; j < C; ++j) {
         const float J = p[a] * ((a == j ? 1.f : 0.f) - p[j]);
         vo = fmaf(J * J, v[j], vo);
+      }
+      if (up_gp) {
+        gp[a] = up_gp[i * C + a];
+        gvo[a] = up_gv ? up_gv[i * C + a] : 0.f;
+        continue;
       }
       const float vc = fminf(fmaxf(vo, clip_lo), clip_hi) + kHeadEps;
       const float iv = 1.f / vc;
@@ -696,6 +705,14 @@ static int check_pv(const sn_packed_view* v, int batch, int h, int w, int c, con
 
 using namespace sn;
 
+namespace sn {
+int sn_head_bwd_general(const sn_packed_view* in, int32_t batch, int32_t in_h, int32_t in_w, int32_t cin,
+                        int32_t n_labels, const float* w_mu, const float* w_sigma, const float* y, float clip_lo,
+                        float clip_hi, const double* acc, float loss_scale, const sn_packed_view* g_in,
+                        float* g_logit_mu, float* g_logit_var, float* rsum_out, const float* up_gp, const float* up_gv,
+                        sn_stream_t st);
+}
+
 extern "C" {
 
 int sn_prepare_weights_bwd(const float* w_mu, int32_t ksize, int32_t cin, int32_t cout, int32_t upconv,
@@ -730,7 +747,27 @@ int sn_head_bwd_packed(const sn_packed_view* in, int32_t batch, int32_t in_h, in
                        int32_t n_labels, const float* w_mu, const float* w_sigma, const float* y, float clip_lo,
                        float clip_hi, const double* acc, float loss_scale, const sn_packed_view* g_in,
                        float* g_logit_mu, float* g_logit_var, float* rsum_out, sn_stream_t st) {
-  SN_REQUIRE(w_mu && w_sigma && y && acc, SN_ERR_BAD_ARG, "head_bwd: null pointer");
+  return sn_head_bwd_general(in, batch, in_h, in_w, cin, n_labels, w_mu, w_sigma, y, clip_lo, clip_hi, acc, loss_scale,
+                             g_in, g_logit_mu, g_logit_var, rsum_out, nullptr, nullptr, st);
+}
+
+int sn_head_bwd_upstream_packed(const sn_packed_view* in, int32_t batch, int32_t in_h, int32_t in_w, int32_t cin,
+                                int32_t n_labels, const float* w_mu, const float* w_sigma, const float* g_p,
+                                const float* g_var_out, const sn_packed_view* g_in, sn_stream_t st) {
+  SN_REQUIRE(g_p, SN_ERR_BAD_ARG, "head_bwd_upstream: null upstream gradient");
+  return sn_head_bwd_general(in, batch, in_h, in_w, cin, n_labels, w_mu, w_sigma, nullptr, 0.f, 0.f, nullptr, 1.f, g_in,
+                             nullptr, nullptr, nullptr, g_p, g_var_out, st);
+}
+
+}  // extern "C"
+
+namespace sn {
+int sn_head_bwd_general(const sn_packed_view* in, int32_t batch, int32_t in_h, int32_t in_w, int32_t cin,
+                        int32_t n_labels, const float* w_mu, const float* w_sigma, const float* y, float clip_lo,
+                        float clip_hi, const double* acc, float loss_scale, const sn_packed_view* g_in,
+                        float* g_logit_mu, float* g_logit_var, float* rsum_out, const float* up_gp, const float* up_gv,
+                        sn_stream_t st) {
+  SN_REQUIRE(w_mu && w_sigma && (up_gp || (y && acc)), SN_ERR_BAD_ARG, "head_bwd: null pointer");
   SN_REQUIRE((g_logit_mu != nullptr) == (g_logit_var != nullptr) && (g_logit_mu != nullptr) == (rsum_out != nullptr),
              SN_ERR_BAD_ARG, "head_bwd: pass all three optional outputs or none");
   SN_REQUIRE(n_labels >= 1 && n_labels <= 8, SN_ERR_UNSUPPORTED, "head_bwd: %d classes (max 8)", n_labels);
@@ -745,7 +782,7 @@ int sn_head_bwd_packed(const sn_packed_view* in, int32_t batch, int32_t in_h, in
   case CC:                                                                                                       \
     head_bwd_kernel<CC><<<grid, 128, smem, as_stream(st)>>>(*in, batch, in_h, in_w, cin, w_mu, w_sigma, y, clip_lo, \
                                                              clip_hi, acc, loss_scale, *g_in, g_logit_mu,        \
-                                                             g_logit_var, rsum_out);                             \
+                                                             g_logit_var, rsum_out, up_gp, up_gv);               \
     break;
   switch (n_labels) {
     SN_HEAD(1) SN_HEAD(2) SN_HEAD(3) SN_HEAD(4) SN_HEAD(5) SN_HEAD(6) SN_HEAD(7) SN_HEAD(8)
@@ -753,6 +790,9 @@ int sn_head_bwd_packed(const sn_packed_view* in, int32_t batch, int32_t in_h, in
 #undef SN_HEAD
   return check_launch("head_bwd");
 }
+}  // namespace sn
+
+extern "C" {
 
 int sn_first_conv_bwd_data_packed(int32_t batch, int32_t in_h, int32_t in_w, int32_t cin, int32_t cout, int32_t ksize,
                                   const float* x, const float* w_mu, const float* w_sigma,

@@ -279,6 +279,7 @@ class GradientEngine(InferenceEngine):
             kind = r["kind"]
             if kind == "head":
                 src = r["src"]
+                self._head_record = r
                 if not gated[src.buf.data_ptr()]:
                     raise RuntimeError("conv_final must read a post-ReLU tensor")
                 names.append("head_bwd")
@@ -419,6 +420,31 @@ class GradientEngine(InferenceEngine):
                 self._graph_bwd = g
             self._graph_bwd.replay()
         return self.nll_loss, self.g_x
+
+    def forward_then_input_gradient(self, x: Tensor, upstream) -> Tuple[Tensor, Tensor, Tensor]:
+        """Forward, then d <g_p, p> + <g_v, v> / dx for upstream gradients chosen AFTER looking at the outputs:
+        `upstream(p, v) -> (g_p, g_v or None)`, both [B, HW, C] device tensors.  This is create_saliency_map's shape
+        (Brats.py:598-609): the mask depends on the prediction.  Eager launches (the callback sits in the middle).
+        Returns (g_x, p, v), engine-owned."""
+        if self.train:
+            raise RuntimeError("build the engine with train=False for input gradients")
+        if not self.matches(x):
+            raise RuntimeError(f"engine built for input {self.shape}, got {tuple(x.shape)}")
+        self.x_in.copy_(x, non_blocking=True)
+        self._launch_all()
+        g_p, g_v = upstream(self.p, self.v)
+        g_p = g_p.to(torch.float32).contiguous()
+        g_v = g_v.to(torch.float32).contiguous() if g_v is not None else None
+        head = self._head_record
+        src = head["src"]
+        gkey = src.buf.data_ptr()
+        B = self.shape[0]
+        wf, wsf = self.model.conv_final.weights()
+        F.head_bwd_upstream_packed(src, B, head["h"], head["w"], head["c"], wf, wsf, g_p, g_v,
+                                   PackedView(self.grad_buffers[gkey], src.y0, src.x0, src.c0))
+        for s_ in self._bwd_steps[1:]:
+            s_()
+        return self.g_x, self.p, self.v
 
     def input_gradient(self, x: Tensor, y_onehot: Tensor, loss_scale: float = 0.5,
                        clip: Tuple[float, float] = (-1e4, 1e3)) -> Tuple[Tensor, Tensor]:

@@ -13,7 +13,7 @@ from typing import Optional, Tuple
 import torch
 
 from . import _lib
-from ._lib import (SN_TC_DST_F32, SN_TC_IM2COL, SN_TC_RELU, SN_TC_UPCONV, check, ptr, sn_packed_view, sn_tc_conv_desc,
+from ._lib import (SN_TC_DST_F32, SN_TC_IM2COL, SN_TC_RELU, SN_TC_ROWS, SN_TC_UPCONV, check, ptr, sn_packed_view, sn_tc_conv_desc,
                    sn_tc_dgrad_desc, sn_tc_wgrad_desc, stream_ptr)
 
 Tensor = torch.Tensor
@@ -199,14 +199,15 @@ def conv_moments_bwd_weight_tc(g_out: PackedView, batch: int, in_h: int, in_w: i
                                in0: PackedView, c0: int, rsum: Tensor, w_mu: Tensor, w_sigma: Tensor,
                                workspace: Tensor, g_w_mu: Tensor, g_w_sigma: Tensor,
                                in1: Optional[PackedView] = None, c1: int = 0, upconv: bool = False,
-                               im2col: bool = False) -> None:
+                               im2col: Optional[bool] = None) -> None:
+    """im2col: None = the library's choice, True / False force the general / the row-halo kernel."""
     d = sn_tc_wgrad_desc()
     d.g_out = g_out.c_view()
     d.in_[0] = in0.c_view()
     d.in_[1] = (in1 if in1 is not None else in0).c_view()
     d.in_c[0], d.in_c[1] = c0, c1
     d.batch, d.in_h, d.in_w, d.ksize, d.cout = batch, in_h, in_w, ksize, cout
-    d.flags = (SN_TC_UPCONV if upconv else 0) | (SN_TC_IM2COL if im2col else 0)
+    d.flags = (SN_TC_UPCONV if upconv else 0) | (SN_TC_IM2COL if im2col else (SN_TC_ROWS if im2col is False else 0))
     d.rsum, d.w_mu, d.w_sigma = rsum.data_ptr(), w_mu.data_ptr(), w_sigma.data_ptr()
     d.workspace, d.g_w_mu, d.g_w_sigma = workspace.data_ptr(), g_w_mu.data_ptr(), g_w_sigma.data_ptr()
     check(_lib.load().sn_conv_moments_bwd_weight_tc(C.byref(d), stream_ptr()), "conv_moments_bwd_weight_tc")
@@ -235,3 +236,11 @@ def final_conv_bwd_weight_packed(inp: PackedView, batch: int, in_h: int, in_w: i
                                                       ptr(w_sigma), ptr(logit_grads[0]), ptr(logit_grads[1]),
                                                       ptr(logit_grads[2]), ptr(workspace), ptr(g_w_mu),
                                                       ptr(g_w_sigma), stream_ptr()), "final_conv_bwd_weight_packed")
+
+
+def head_bwd_upstream_packed(inp: PackedView, batch: int, in_h: int, in_w: int, cin: int, w_mu: Tensor,
+                             w_sigma: Tensor, g_p: Tensor, g_var_out: Optional[Tensor], g_in: PackedView) -> None:
+    a, g = inp.c_view(), g_in.c_view()
+    check(_lib.load().sn_head_bwd_upstream_packed(C.byref(a), batch, in_h, in_w, cin, w_mu.shape[-1], ptr(w_mu),
+                                                  ptr(w_sigma), ptr(g_p), ptr(g_var_out), C.byref(g), stream_ptr()),
+          "head_bwd_upstream_packed")

@@ -348,13 +348,17 @@ class Density_prop_with_pad_UNET(nn.Module):
             self._engine = InferenceEngine(self, x.shape[0], x.shape[1], x.shape[2], x.shape[3], x.device)
         return self._engine.run(x, return_presoftmax)
 
-    def input_gradient_fast(self, x: Tensor, y_onehot: Tensor, loss_scale: float = 0.5,
-                            clip: Tuple[float, float] = (-1e4, 1e3)):
-        """(loss, d loss/dx), loss = loss_scale * NLL(clip(var)), through the FAST-mode gradient engine."""
+    def grad_engine_for(self, x: Tensor):
+        """The FAST-mode gradient engine (engine.GradientEngine) for inputs shaped like x, built on first use."""
         from .engine import GradientEngine
         if self._grad_engine is None or not self._grad_engine.matches(x):
             self._grad_engine = GradientEngine(self, x.shape[0], x.shape[1], x.shape[2], x.shape[3], x.device)
-        return self._grad_engine.input_gradient(x, y_onehot, loss_scale, clip)
+        return self._grad_engine
+
+    def input_gradient_fast(self, x: Tensor, y_onehot: Tensor, loss_scale: float = 0.5,
+                            clip: Tuple[float, float] = (-1e4, 1e3)):
+        """(loss, d loss/dx), loss = loss_scale * NLL(clip(var)), through the FAST-mode gradient engine."""
+        return self.grad_engine_for(x).input_gradient(x, y_onehot, loss_scale, clip)
 
     # -- losses of the reference's step functions ---------------------------------------------------------
     def elbo_loss(self, x: Tensor, y_onehot: Tensor, kl_factor: float = 1e-5) -> Tensor:

@@ -108,6 +108,20 @@ def create_saliency_map(model, x: Tensor, target_class: int, tumor_structure: bo
     class vectors), i.e. the number of selected pixels: its saliency is zero up to rounding.  `class_only=True`
     sums only the target class' probability, the quantity the name suggests; the default keeps the reference's
     formula."""
+    if getattr(model, "mode", "fp32") == "fast":
+        # tensor-core forward + data-gradient chain; the mask is built on the device from the engine's own prediction
+        def upstream(p, v):
+            label = p.argmax(-1)
+            mask = (label > 0) if tumor_structure else (label == target_class)
+            g_p = torch.zeros_like(p)
+            if class_only:
+                g_p[..., target_class] = mask.to(p.dtype)
+            else:
+                g_p += mask.unsqueeze(-1).to(p.dtype)
+            return g_p, None
+        g, p, _ = model.grad_engine_for(x).forward_then_input_gradient(x.detach(), upstream)
+        g = g.clone()
+        return g, torch.relu(g), p.clone()
     xi = x.detach().clone().requires_grad_(True)
     p, _ = model._forward_fp32(xi)
     label = p.argmax(-1)

@@ -429,3 +429,22 @@ def test_fast_training_step_runs_and_learns(S):
     with torch.no_grad():
         p, _ = model(x)                       # inference engine built from the updated weights
     assert bool(torch.isfinite(p).all())
+
+
+def test_saliency_map_fast(S):
+    """create_saliency_map (Brats.py:598-609) through mode='fast': the mask is chosen from the engine's own
+    prediction, then d sum(masked p_target) / dx runs through the tensor-core data-gradient chain."""
+    from supernet_b200 import robustness as R
+    oracle = O.UNetOracle("hippocampus", 32, 3, 1, torch.float64)
+    w32 = O.make_weights("hippocampus", 32, 3, 1)
+    model = S.Density_prop_with_pad_UNET(32, 3, variant="hippocampus", mode="fast").load_weight_dict(w32, device="cuda")
+    x = O.make_input("hippocampus", 2)
+    grad, relu_grad, pred = R.create_saliency_map(model, dev(x), target_class=1, class_only=True)
+    xr = x.double().requires_grad_(True)
+    p, _ = oracle(xr)
+    mask = (p.argmax(-1) == 1).double()
+    (g_ref,) = torch.autograd.grad((p[..., 1] * mask).sum(), xr)
+    err = rel(grad, g_ref)
+    print("saliency rel", err)
+    assert err < 1e-2, err
+    assert torch.equal(relu_grad, torch.relu(grad)) and rel(pred, p) < 1e-3
