@@ -158,6 +158,38 @@ def cpu_baseline(seconds_budget: float = 15.0, form: str = "as_written"):
                       f"conv2d + extract_patches + 3 matmuls per layer)"}
 
 
+def aux_backward(model, B, dev, steps=10):
+    """Side measurements, not the headline (BASELINE.json configs[2] and [3]): the FAST-mode FGSM chain
+    (create_adversarial_pattern, Brats.py:582-596: forward + 0.5 NLL + input gradient) and the training chain
+    (train_on_batch, Brats.py:569-580: forward + NLL + data and weight gradients; optimiser excluded) on the tensor
+    cores, batch resident, CUDA-graph replay, CUDA events."""
+    from oracle import supernet_oracle as O
+    from supernet_b200.engine import GradientEngine
+    res = {"batch": B, "note": "resident batch, one CUDA graph per chain, single GPU"}
+    for key, train in (("fgsm", False), ("train", True)):
+        eng = GradientEngine(model, B, IN_HW, IN_HW, IN_CH, dev, graph=True, train=train)
+        if train:
+            eng._loss_scale, eng._clip = 1.0, (1e-12, 1e3)
+        eng.x_in.copy_(O.make_input("brats", B, alpha=O.BRATS_ALPHA))
+        eng.y_in.copy_(O.make_labels(B, OUT_HW * OUT_HW, N_LABELS))
+        for _ in range(3):
+            eng.loss_and_input_gradient_resident()
+        torch.cuda.synchronize()
+        a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        a.record()
+        for _ in range(steps):
+            eng.loss_and_input_gradient_resident()
+        b.record()
+        torch.cuda.synchronize()
+        ms = a.elapsed_time(b) / steps
+        res[key] = {"ms_per_step": round(ms, 3), "slices_per_s": round(B / ms * 1e3, 1),
+                    "launches_per_step": len(eng.step_names) + 2 + len(eng._bwd_steps),
+                    "algorithmic_gflop_per_slice": round((2 if not train else 3) * 20.19, 1)}
+        del eng
+        torch.cuda.empty_cache()
+    return res
+
+
 def run_reference(args):
     """--impl reference: the CPU restatement of the reference path (TensorFlow itself is not installable in this
     image), one slice per step, all host threads."""
@@ -201,6 +233,7 @@ def main():
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
     ap.add_argument("--mode", default="fast", choices=["fast", "fp32"])
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-aux", action="store_true", help="skip the FGSM / training-chain side measurements")
     args = ap.parse_args()
     args.warmup = max(args.warmup, 3)
 
@@ -371,6 +404,8 @@ def main():
         if roofline:
             out["roofline"] = roofline
             out["kernels"] = kernels
+        if args.mode == "fast" and world == 1 and not args.no_aux:
+            out["aux"] = aux_backward(model, B, dev)
         if not args.no_cpu_baseline and world == 1:
             out["cpu_baseline"] = cpu_baseline()
         print(json.dumps(out))

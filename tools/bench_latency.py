@@ -1,4 +1,4 @@
-"""Latency / small-batch view (BASELINE.json configs[0] and the low end of configs[4]): one CUDA-graph forward of
+"""Batch sweep 1-512 (BASELINE.json configs[0] and configs[4]): one CUDA-graph forward of
 FAST mode at small batches for both networks, next to the CPU oracle (conv form = best-case CPU, as-written form =
 the reference's op sequence) on the host cores."""
 import json
@@ -13,7 +13,8 @@ from supernet_b200.engine import InferenceEngine
 from oracle import supernet_oracle as O
 
 out = []
-for variant, C, in_ch, hw, batches in (("hippocampus", 3, 1, 64, (1, 8, 64)), ("brats", 4, 4, 204, (1, 2, 4, 8))):
+for variant, C, in_ch, hw, batches in (("hippocampus", 3, 1, 64, (1, 8, 64, 512)),
+                                       ("brats", 4, 4, 204, (1, 2, 4, 8, 16, 32, 64, 128, 256, 512))):
     w = O.make_weights(variant, 32, C, in_ch)
     model = S.Density_prop_with_pad_UNET(32, C, variant=variant, mode="fast").load_weight_dict(w, device="cuda")
     for B in batches:
@@ -46,4 +47,6 @@ for variant, C, in_ch, hw, batches in (("hippocampus", 3, 1, 64, (1, 8, 64)), ("
                     row[f"cpu_{form}_ms"] = round((time.perf_counter() - t0) / n * 1e3, 2)
             row["cpu_cores"] = os.cpu_count()
         out.append(row)
-        print(json.dumps(row))
+        print(json.dumps(row), flush=True)
+        del eng
+        torch.cuda.empty_cache()
