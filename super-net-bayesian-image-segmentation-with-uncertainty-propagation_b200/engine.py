@@ -30,6 +30,8 @@ class InferenceEngine:
         self.keep_presoftmax = keep_presoftmax
         self.shape = (batch, in_h, in_w, in_c)
         self.device = torch.device(device)
+        if self.device.type == "cuda" and self.device.index is None:      # "cuda" -> the current device, so that
+            self.device = torch.device("cuda", torch.cuda.current_device())   # matches() can compare with x.device
         self.use_graph = graph
         self._graph: Optional[torch.cuda.CUDAGraph] = None
         self._steps: List[Callable[[], None]] = []
