@@ -26,7 +26,7 @@ def test_library_exports_every_declared_symbol():
     assert len(names) >= 28 and "sn_conv_moments_fwd_tc" in names and "sn_nll_gaussian_bwd" in names
     for n in names:
         assert hasattr(lib, n), n
-    assert lib.sn_version() == 1
+    assert lib.sn_version() == 2          # SN_ABI_VERSION: 2 added the FAST-mode backward entry points
 
 
 def test_struct_layouts_match_header():
