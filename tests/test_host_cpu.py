@@ -34,7 +34,10 @@ def test_struct_layouts_match_header():
     L = S._lib
     assert C.sizeof(L.sn_conv_desc) == 32 and C.sizeof(L.sn_window) == 72
     assert C.sizeof(L.sn_packed_view) == 40
-    assert C.sizeof(L.sn_tc_conv_desc) == 2 * 40 + 8 + 24 + 8 + 8 + 40 + 8 + 8
+    assert C.sizeof(L.sn_tc_conv_desc) == 2 * 40 + 8 + 24 + 8 + 8 + 40 + 8 + 8 + 8          # + rsum_out (ABI v2)
+    # backward descriptors (ABI v2): g_out + in[2] + g_in[2] views, 4 + 6 ints, 2 pointers / g_out + in[2], 2 + 6 ints, 6 pointers
+    assert C.sizeof(L.sn_tc_dgrad_desc) == 5 * 40 + 4 * 4 + 6 * 4 + 2 * 8
+    assert C.sizeof(L.sn_tc_wgrad_desc) == 3 * 40 + 2 * 4 + 6 * 4 + 6 * 8
 
 
 def test_argument_validation_needs_no_device():
@@ -53,6 +56,15 @@ def test_argument_validation_needs_no_device():
     t.batch, t.in_h, t.in_w, t.ksize, t.cout = 1, 8, 8, 3, 32
     t.src_c[0] = 16                                                                          # not a multiple of 32
     assert lib.sn_conv_moments_fwd_tc(C.byref(t), None) == -2
+    g = S._lib.sn_tc_dgrad_desc()
+    g.batch, g.in_h, g.in_w, g.ksize, g.cout = 1, 8, 8, 3, 32
+    g.in_c[0] = 48                                                                           # not a multiple of 32
+    assert lib.sn_conv_moments_bwd_data_tc(C.byref(g), None) == -2
+    wg = S._lib.sn_tc_wgrad_desc()
+    wg.batch, wg.in_h, wg.in_w, wg.ksize, wg.cout = 1, 8, 8, 4, 32                            # kernel size 4
+    assert lib.sn_conv_moments_bwd_weight_tc(C.byref(wg), None) == -2
+    assert lib.sn_conv_moments_bwd_weight_tc(None, None) == -1
+    assert lib.sn_wgrad_workspace_bytes(3, 64, 32) == (2 * 9 * 64 * 32 + 32) * 4
     assert lib.sn_packed_bytes(2, 3, 4, 32) == 2 * 3 * 4 * 3 * 32 * 2
     assert lib.sn_prepared_weight_bytes(3, 64, 32) == 3 * 9 * 64 * 32 * 2
 
