@@ -75,17 +75,37 @@ def allreduce_gradients(params: Sequence[Tensor], local_count: int, global_count
 
 def clip_by_norm_per_variable_(params: Iterable[Tensor], clipnorm: float = 1.0) -> None:
     """Keras optimizer `clipnorm`: every variable's gradient is rescaled to L2 norm <= clipnorm on its own
-    (Brats.py:566), unlike torch's clip_grad_norm_ which uses the global norm."""
-    for p in params:
-        if p.grad is None:
-            continue
-        n = p.grad.norm()
-        p.grad.mul_(torch.clamp(clipnorm / (n + 1e-12), max=1.0))
+    (Brats.py:566), unlike torch's clip_grad_norm_ which uses the global norm.  Multi-tensor kernels: a handful of
+    launches for all variables instead of three per variable."""
+    grads = [p.grad for p in params if p.grad is not None]
+    if not grads:
+        return
+    norms = torch.stack(torch._foreach_norm(grads))
+    coef = torch.clamp(clipnorm / (norms + 1e-12), max=1.0)
+    torch._foreach_mul_(grads, list(coef.unbind(0)))
+
+
+def allreduce_flat_(flat: Tensor, local_count: int, global_count: int, group: Optional[dist.ProcessGroup] = None,
+                    bucket_bytes: int = 8 << 20) -> None:
+    """In-place weighted gradient all-reduce on ONE flat buffer (the FAST-mode engine's gradients are views of it):
+    flat <- sum_r (n_r / N) flat_r, in bucket-sized slices so that NCCL pipelines them; no packing copies."""
+    if not dist.is_available() or not dist.is_initialized() or dist.get_world_size(group) == 1:
+        return
+    if global_count <= 0:
+        raise ValueError("global_count must be positive")
+    flat.mul_(float(local_count) / float(global_count))
+    step = max(1, bucket_bytes // flat.element_size())
+    handles = [dist.all_reduce(flat[i:i + step], op=dist.ReduceOp.SUM, group=group, async_op=True)
+               for i in range(0, flat.numel(), step)]
+    for h in handles:
+        h.wait()
 
 
 def make_adam(params: Iterable[Tensor], lr: float = 1e-3) -> torch.optim.Adam:
     """tf.keras.optimizers.Adam defaults (beta 0.9/0.999, epsilon 1e-7) (Brats.py:566)."""
-    return torch.optim.Adam(list(params), lr=lr, betas=(0.9, 0.999), eps=1e-7)
+    params = list(params)
+    fused = bool(params) and all(p.is_cuda for p in params)          # one multi-tensor kernel on the GPU
+    return torch.optim.Adam(params, lr=lr, betas=(0.9, 0.999), eps=1e-7, fused=fused)
 
 
 class DataParallelTrainer:
@@ -112,11 +132,15 @@ class DataParallelTrainer:
             loss = torch.zeros((), device=params[0].device)
             for p in params:
                 p.grad = torch.zeros_like(p)
-        allreduce_gradients(params, x_local.shape[0], global_batch, self.group)
+        if self._engine is not None and x_local.shape[0] > 0 and getattr(self.model, "mode", "fp32") == "fast":
+            allreduce_flat_(self._engine.flat_grad, x_local.shape[0], global_batch, self.group)
+        else:
+            allreduce_gradients(params, x_local.shape[0], global_batch, self.group)
         clip_by_norm_per_variable_(params, self.clipnorm)
         self.opt.step()
-        if self._engine is not None:
-            self._engine.refresh_weights()       # re-derive the bf16 tensor-core operands from the updated weights
+        # engines re-derive their bf16 tensor-core operands when they see a new version (the training engine does it
+        # inside its captured graph on every step)
+        self.model._weights_version = getattr(self.model, "_weights_version", 0) + 1
         return loss.detach()
 
     _engine = None
@@ -124,23 +148,12 @@ class DataParallelTrainer:
     def _fast_backward(self, x: Tensor, y: Tensor) -> Tensor:
         """FAST mode: tensor-core forward, data-gradient and weight-gradient chain (engine.GradientEngine), then the
         regulariser terms of Brats.py:575-576, which depend on the weights only."""
-        import ctypes as C
-
-        from . import _lib, ops
         from .engine import GradientEngine
         m = self.model
         if self._engine is None or not self._engine.matches(x):
             self._engine = GradientEngine(m, x.shape[0], x.shape[1], x.shape[2], x.shape[3], x.device, train=True)
-        nll, grads = self._engine.loss_and_weight_gradients(x, y, clip=(1e-12, 1e3))
-        lib = _lib.load()
-        scale = self.kl_factor * 0.5
+        loss, grads = self._engine.loss_and_weight_gradients(x, y, clip=(1e-12, 1e3), kl_factor=self.kl_factor)
         for name in m.conv_names:
             w, ws = getattr(m, name).weights()
-            gw, gws = grads[name]
-            _lib.check(lib.sn_kl_regularizer_bwd(_lib.ptr(w), C.c_size_t(w.numel()), _lib.ptr(ws), ws.numel(),
-                                                 w.shape[0], C.c_float(scale), _lib.ptr(gw), _lib.ptr(gws),
-                                                 _lib.stream_ptr()), "kl_regularizer_bwd")
-            w.grad, ws.grad = gw, gws
-        with torch.no_grad():
-            reg = ops.kl_regularizer([c.weights() for c in m.convs()])
-        return nll[0] + scale * reg
+            w.grad, ws.grad = grads[name]
+        return loss[0]

@@ -55,8 +55,20 @@ class InferenceEngine:
             self.prepared[name] = F.prepare_weights(w, ws, upconv=name.endswith("conv2x2"))
 
     def refresh_weights(self) -> None:
-        self._prepare_weights()
-        self._graph = None         # prepared-weight buffers were reallocated
+        """After a weight update: re-derive the bf16 operands IN PLACE (a captured graph keeps its pointers)."""
+        m = self.model
+        for name in m.conv_names:
+            if name in ("conv_input", "conv_final"):
+                continue
+            w, ws = getattr(m, name).weights()
+            F.prepare_weights(w, ws, upconv=name.endswith("conv2x2"), out=self.prepared[name])
+        self._weights_version = getattr(m, "_weights_version", 0)
+
+    def sync_weights(self) -> None:
+        """Refresh the operands if the model's weights changed since they were derived (trainers bump
+        model._weights_version after every optimiser step)."""
+        if self._weights_version != getattr(self.model, "_weights_version", 0):
+            self.refresh_weights()
 
     def _build(self) -> None:
         m = self.model
@@ -68,6 +80,7 @@ class InferenceEngine:
         if not all(c.built for c in m.convs()):
             m.build_with_input(Cin, dev)
         self._prepare_weights()
+        self._weights_version = getattr(m, "_weights_version", 0)
         steps = self._steps
         self.skip_window = {}
         self.x_in = torch.empty(self.shape, device=dev, dtype=torch.float32)
@@ -190,6 +203,7 @@ class InferenceEngine:
     def run(self, x: Tensor, return_presoftmax: bool = False):
         if not self.matches(x):
             raise RuntimeError(f"engine built for input {self.shape}, got {tuple(x.shape)}")
+        self.sync_weights()
         self.x_in.copy_(x, non_blocking=True)
         p, v = self.forward_resident()
         if return_presoftmax:
@@ -269,9 +283,20 @@ class GradientEngine(InferenceEngine):
         self.grads = {}           # training: layer name -> (g_w_mu, g_w_sigma), overwritten by every step
         logit_grads = None
         if self.train:
+            # one flat fp32 buffer in parameter order (w_mu, w_sigma per layer): the data-parallel all-reduce runs on
+            # it directly, the per-layer gradients are views
+            total = sum(w_.numel() + ws_.numel() for w_, ws_ in (getattr(m, n_).weights() for n_ in m.conv_names))
+            self.flat_grad = torch.zeros(total, device=dev, dtype=torch.float32)
+            off = 0
             for name in m.conv_names:
                 w_, ws_ = getattr(m, name).weights()
-                self.grads[name] = (torch.zeros_like(w_), torch.zeros_like(ws_))
+                gw_ = self.flat_grad[off:off + w_.numel()].view_as(w_)
+                off += w_.numel()
+                gws_ = self.flat_grad[off:off + ws_.numel()].view_as(ws_)
+                off += ws_.numel()
+                self.grads[name] = (gw_, gws_)
+            self.reg_acc = torch.zeros(1, device=dev, dtype=torch.float64)
+            self._kl_scale = 0.0
             n_max = max(w_.numel() for w_, _ in (getattr(m, n).weights() for n in m.conv_names))
             self._wg_work = torch.empty(2 * n_max + 1024, device=dev, dtype=torch.float32)
             rows = B * oh * ow
@@ -357,15 +382,30 @@ class GradientEngine(InferenceEngine):
         self.n_launches_bwd = len(steps) + 2          # + the two NLL forward kernels
 
     def refresh_weights(self) -> None:
-        """After an optimiser step: re-derive the bf16 operands IN PLACE (the captured graph keeps its pointers)."""
+        """After an optimiser step: re-derive forward AND data-gradient operands in place."""
+        super().refresh_weights()
         m = self.model
         for name in m.conv_names:
             if name in ("conv_input", "conv_final"):
                 continue
-            w, ws = getattr(m, name).weights()
-            up = name.endswith("conv2x2")
-            F.prepare_weights(w, ws, upconv=up, out=self.prepared[name])
-            F.prepare_weights_bwd(w, upconv=up, out=self.prepared_bwd[name])
+            w, _ = getattr(m, name).weights()
+            F.prepare_weights_bwd(w, upconv=name.endswith("conv2x2"), out=self.prepared_bwd[name])
+
+    def _regulariser(self) -> None:
+        """add_n(model.losses) (Brats.py:575) and its gradient, kl_scale = kl_factor * 0.5 (Brats.py:576): the value
+        accumulates into reg_acc, the gradient into the weight-gradient buffers (after the data terms were written)."""
+        import ctypes as C
+        from ._lib import check, load, ptr, stream_ptr
+        lib = load()
+        self.reg_acc.zero_()
+        for name in self.model.conv_names:
+            w, ws = getattr(self.model, name).weights()
+            gw, gws = self.grads[name]
+            check(lib.sn_kl_regularizer_fwd(ptr(w), C.c_size_t(w.numel()), ptr(ws), ws.numel(), w.shape[0],
+                                            ptr(self.reg_acc), stream_ptr()), "kl_regularizer_fwd")
+            check(lib.sn_kl_regularizer_bwd(ptr(w), C.c_size_t(w.numel()), ptr(ws), ws.numel(), w.shape[0],
+                                            C.c_float(self._kl_scale), ptr(gw), ptr(gws), stream_ptr()),
+                  "kl_regularizer_bwd")
 
     # FP32-mode weight gradient on unpacked operands (thin layers only)
     def _wgrad_f32(self, name, packed_in, mu32, var32, g_mu, g_var, rsum, w, ws, h, wd, cin, cout, k) -> None:
@@ -382,27 +422,35 @@ class GradientEngine(InferenceEngine):
         gw, gws = self.grads["conv_input"]
         ops.conv_bwd_weight_raw(B, H, W, cin, w.shape[-1], k, self.x_in, None, gm32, gv32, rs0, w, ws, gw, gws)
 
-    def loss_and_weight_gradients(self, x: Tensor, y_onehot: Tensor, clip: Tuple[float, float] = (1e-12, 1e3)):
-        """train_on_batch's data term (Brats.py:572-574,578): returns (NLL, {layer: (dNLL/dw_mu, dNLL/dw_sigma)});
-        the tensors are engine-owned and overwritten by the next call.  The regulariser terms (Brats.py:575-576) depend
-        on the weights only and are added by the caller (dp.DataParallelTrainer)."""
+    def loss_and_weight_gradients(self, x: Tensor, y_onehot: Tensor, clip: Tuple[float, float] = (1e-12, 1e3),
+                                  kl_factor: float = 0.0):
+        """train_on_batch's loss and gradients (Brats.py:572-578): loss = NLL(clip(var)) + kl_factor * 0.5 *
+        add_n(model.losses).  Returns (loss [1] device tensor, {layer: (d/dw_mu, d/dw_sigma)}); the gradients are views
+        of self.flat_grad, engine-owned and overwritten by the next call.  One CUDA-graph replay: operand refresh,
+        forward, NLL, data and weight gradients, regularisers."""
         if not self.train:
             raise RuntimeError("engine was built with train=False")
         if not self.matches(x):
             raise RuntimeError(f"engine built for input {self.shape}, got {tuple(x.shape)}")
-        if (1.0, tuple(clip)) != (self._loss_scale, self._clip):
-            self._loss_scale, self._clip = 1.0, (float(clip[0]), float(clip[1]))
-            self._graph_bwd = None
+        want = (1.0, (float(clip[0]), float(clip[1])), float(kl_factor) * 0.5)
+        if want != (self._loss_scale, self._clip, self._kl_scale):
+            self._loss_scale, self._clip, self._kl_scale = want
+            self._graph_bwd = None                       # scalars are baked into the captured launches
         self.x_in.copy_(x, non_blocking=True)
         self.y_in.copy_(y_onehot.reshape(self.y_in.shape), non_blocking=True)
-        loss, _ = self.loss_and_input_gradient_resident()
+        nll, _ = self.loss_and_input_gradient_resident()
+        loss = nll + (self._kl_scale * self.reg_acc).to(torch.float32)
         return loss, self.grads
 
     def _launch_fwd_bwd(self) -> None:
+        if self.train:
+            self.refresh_weights()       # inside the captured sequence: the operands follow every optimiser step
         self._launch_all()
         F.nll_gaussian_fwd(self.y_in, self.p, self.v, self._clip, self.nll_acc, self.nll_loss)
         for s in self._bwd_steps:
             s()
+        if self.train:
+            self._regulariser()
 
     def loss_and_input_gradient_resident(self) -> Tuple[Tensor, Tensor]:
         """Forward, loss_scale * NLL and d(loss)/dx on whatever is in self.x_in / self.y_in; returns engine-owned
@@ -432,6 +480,7 @@ class GradientEngine(InferenceEngine):
             raise RuntimeError("build the engine with train=False for input gradients")
         if not self.matches(x):
             raise RuntimeError(f"engine built for input {self.shape}, got {tuple(x.shape)}")
+        self.sync_weights()
         self.x_in.copy_(x, non_blocking=True)
         self._launch_all()
         g_p, g_v = upstream(self.p, self.v)
@@ -457,6 +506,7 @@ class GradientEngine(InferenceEngine):
         if (loss_scale, tuple(clip)) != (self._loss_scale, self._clip):
             self._loss_scale, self._clip = float(loss_scale), (float(clip[0]), float(clip[1]))
             self._graph_bwd = None                       # scalars are baked into the captured launches
+        self.sync_weights()
         self.x_in.copy_(x, non_blocking=True)
         self.y_in.copy_(y_onehot.reshape(self.y_in.shape), non_blocking=True)
         loss, g = self.loss_and_input_gradient_resident()

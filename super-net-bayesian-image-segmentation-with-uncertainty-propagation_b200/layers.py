@@ -275,6 +275,7 @@ class Density_prop_with_pad_UNET(nn.Module):
             getattr(self, n).set_weights(w, s)
         self._engine = None
         self._grad_engine = None
+        self._weights_version = getattr(self, "_weights_version", 0) + 1
         return self
 
     def build_with_input(self, in_channels: int, device) -> None:
