@@ -32,6 +32,7 @@
 #include "sn_sm100.cuh"
 
 #include <cuda.h>
+#include <stdlib.h>
 #include <mutex>
 
 namespace sn {
@@ -141,6 +142,9 @@ __global__ void __launch_bounds__(HL_THREADS, 1) conv_moments_halo_kernel(const 
   const int warp = __shfl_sync(0xffffffffu, (int)(threadIdx.x >> 5), 0);   // provably warp-uniform
   const int lane = threadIdx.x & 31;
   const int cblk = p.cblk_s[0] + p.cblk_s[1] + p.cblk_s[2] + p.cblk_s[3];
+  // Programmatic dependent launch: let the next kernel of the stream start its prologue (barriers, TMEM, resident
+  // weights) on SMs this grid has already left; it blocks in griddepcontrol.wait until this grid has completed.
+  asm volatile("griddepcontrol.launch_dependents;" ::: "memory");
   constexpr int taps = KS * KS;
 
   if (warp == 0 && lane == 0) {
@@ -173,13 +177,34 @@ __global__ void __launch_bounds__(HL_THREADS, 1) conv_moments_halo_kernel(const 
   __syncthreads();
   ptx::tc_fence_after();
   const uint32_t tmem_base = *tmem_slot_gen;
+  // Everything below that depends on the previous kernel of the stream -- activation tiles (TMA), saved activations
+  // (data-gradient epilogue) and the destination buffers -- comes after this wait.  The producer warp is the exception:
+  // it issues the RESIDENT weight loads (constants) first and waits right before its first activation load.
+  if (warp != 0) asm volatile("griddepcontrol.wait;" ::: "memory");
 
   if (warp == 0) {
     // ===================== TMA producer =====================
     if (lane == 0) {
+      bool dep_waited = false;
       int ai = 0, bi = 0;     // running A-stage / B-slot fill counters
       TileIt it;
       it.init(blockIdx.x, gridDim.x, p);
+      if (RESIDENT && blockIdx.x < p.total_tiles) {
+        // resident weights: the whole layer's operands for this CTA's N tile, before the dependency wait
+        const int ncol0 = it.nt * NT;
+        const int group = ncol0 / p.cout;
+        const int n0 = ncol0 - group * p.cout;
+        for (int cbt = 0; cbt < cblk; ++cbt)
+          for (int tap = 0; tap < taps; ++tap) {
+            const int slot = cbt * taps + tap;
+            ptx::mbar_arrive_expect_tx(b_full(slot), (uint32_t)B_SLOT);
+            const uint32_t sb_addr = b_base + slot * B_SLOT;
+#pragma unroll
+            for (int pl = 0; pl < 3; ++pl)
+              ptx::tma_load_3d(sb_addr + pl * B_PLANE, &maps.w, b_full(slot), cbt * HL_KC, p.upconv ? ncol0 : n0,
+                               p.upconv ? pl : pl * p.taps_w + tap);
+          }
+      }
       for (int tile = blockIdx.x, titer = 0; tile < p.total_tiles; tile += gridDim.x, ++titer, it.next(p)) {
         const int nt_i = it.nt, tx = it.tx, ty = it.ty, tb = it.tb;
         const int ncol0 = nt_i * NT;
@@ -189,6 +214,10 @@ __global__ void __launch_bounds__(HL_THREADS, 1) conv_moments_halo_kernel(const 
         int src = 0, cb = 0;
         for (int cbt = 0; cbt < cblk; ++cbt, ++cb) {
           while (cb >= p.cblk_s[src]) { cb = 0; ++src; }
+          if (!dep_waited) {
+            asm volatile("griddepcontrol.wait;" ::: "memory");
+            dep_waited = true;
+          }
           {
             const int stage = ai % p.sa;
             const uint32_t parity = (uint32_t)(ai / p.sa) & 1u;
@@ -207,12 +236,10 @@ __global__ void __launch_bounds__(HL_THREADS, 1) conv_moments_halo_kernel(const 
                   : "memory");
             }
           }
-          if (!RESIDENT || titer == 0) {
+          if (!RESIDENT) {
             for (int tap = 0; tap < taps; ++tap) {
               int slot;
-              if (RESIDENT) {
-                slot = cbt * taps + tap;
-              } else {
+              {
                 slot = bi % p.sb;
                 const uint32_t parity = (uint32_t)(bi / p.sb) & 1u;
                 ++bi;
@@ -663,7 +690,22 @@ static int hl_launch3(const HlMaps& maps, const HlP& p, cudaStream_t st) {
   });
   if (attr_err != cudaSuccess) return fail(SN_ERR_LAUNCH, "conv_halo: cannot reserve %d B of shared memory", HL_SMEM);
   int grid = p.total_tiles < num_sms() ? p.total_tiles : num_sms();
-  conv_moments_halo_kernel<NT, KS, RESIDENT, DGRAD><<<grid, HL_THREADS, HL_SMEM, st>>>(maps, p);
+  static const bool pdl = [] {
+    const char* e = getenv("SN_PDL");
+    return e == nullptr || e[0] != '0';
+  }();
+  cudaLaunchConfig_t cfg{};
+  cfg.gridDim = dim3((unsigned)grid);
+  cfg.blockDim = dim3(HL_THREADS);
+  cfg.dynamicSmemBytes = HL_SMEM;
+  cfg.stream = st;
+  cudaLaunchAttribute attr[1];
+  attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+  attr[0].val.programmaticStreamSerializationAllowed = 1;
+  cfg.attrs = attr;
+  cfg.numAttrs = pdl ? 1 : 0;
+  cudaError_t e = cudaLaunchKernelEx(&cfg, conv_moments_halo_kernel<NT, KS, RESIDENT, DGRAD>, maps, p);
+  if (e != cudaSuccess) return fail(SN_ERR_LAUNCH, "conv_halo launch: %s", cudaGetErrorString(e));
   return check_launch(DGRAD ? "conv_moments_halo_dgrad" : "conv_moments_halo");
 }
 

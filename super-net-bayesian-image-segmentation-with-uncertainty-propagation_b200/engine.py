@@ -23,6 +23,30 @@ from .fastops import PackedView
 Tensor = torch.Tensor
 
 
+def _capture_graph(device, launch: Callable[[], None]) -> "torch.cuda.CUDAGraph":
+    """Warm `launch` up on a side stream (lazy module loading, shared-memory attributes), then capture it.
+    Garbage is collected BEFORE and the collector is paused DURING the capture: freeing an older engine (its CUDA
+    graph, its private memory pool) in the middle of a capture is an operation CUDA does not permit and it
+    invalidates the capture (seen in the test suite, where earlier engines die at arbitrary times)."""
+    import gc
+    side = torch.cuda.Stream(device=device)
+    side.wait_stream(torch.cuda.current_stream())
+    with torch.cuda.stream(side):
+        launch()
+    torch.cuda.current_stream().wait_stream(side)
+    gc.collect()
+    was_enabled = gc.isenabled()
+    gc.disable()
+    try:
+        g = torch.cuda.CUDAGraph()
+        with torch.cuda.graph(g):
+            launch()
+    finally:
+        if was_enabled:
+            gc.enable()
+    return g
+
+
 class InferenceEngine:
     def __init__(self, model, batch: int, in_h: int, in_w: int, in_c: int, device, graph: bool = True,
                  keep_presoftmax: bool = True):
@@ -187,16 +211,7 @@ class InferenceEngine:
             self._launch_all()
         else:
             if self._graph is None:
-                # warm-up on a side stream (lazy module loading, smem attribute), then capture
-                side = torch.cuda.Stream(device=self.device)
-                side.wait_stream(torch.cuda.current_stream())
-                with torch.cuda.stream(side):
-                    self._launch_all()
-                torch.cuda.current_stream().wait_stream(side)
-                g = torch.cuda.CUDAGraph()
-                with torch.cuda.graph(g):
-                    self._launch_all()
-                self._graph = g
+                self._graph = _capture_graph(self.device, self._launch_all)
             self._graph.replay()
         return self.p, self.v
 
@@ -459,15 +474,7 @@ class GradientEngine(InferenceEngine):
             self._launch_fwd_bwd()
         else:
             if self._graph_bwd is None:
-                side = torch.cuda.Stream(device=self.device)
-                side.wait_stream(torch.cuda.current_stream())
-                with torch.cuda.stream(side):
-                    self._launch_fwd_bwd()
-                torch.cuda.current_stream().wait_stream(side)
-                g = torch.cuda.CUDAGraph()
-                with torch.cuda.graph(g):
-                    self._launch_fwd_bwd()
-                self._graph_bwd = g
+                self._graph_bwd = _capture_graph(self.device, self._launch_fwd_bwd)
             self._graph_bwd.replay()
         return self.nll_loss, self.g_x
 
