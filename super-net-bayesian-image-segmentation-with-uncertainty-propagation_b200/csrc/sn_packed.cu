@@ -618,10 +618,13 @@ int sn_final_conv_softmax_packed(const sn_packed_view* src, int32_t batch, int32
   SN_REQUIRE(aligned16(p_out) && aligned16(var_out) && (!presoftmax_mu || (aligned16(presoftmax_mu) &&
                                                                             aligned16(presoftmax_var))),
              SN_ERR_MISALIGNED, "final_conv: outputs must be 16-byte aligned");
-  const int contiguous = src->y0 == 0 && src->x0 == 0 && src->c0 == 0 && src->h == in_h && src->w == in_w &&
-                         src->c == cin;
-  const size_t smem = (((size_t)2 * cin * n_labels + n_labels + 3) & ~(size_t)3) * sizeof(float) +
-                      (contiguous ? (size_t)128 * (6 * cin + 16) : 0);
+  int contiguous = src->y0 == 0 && src->x0 == 0 && src->c0 == 0 && src->h == in_h && src->w == in_w && src->c == cin;
+  const size_t smem_w = (((size_t)2 * cin * n_labels + n_labels + 3) & ~(size_t)3) * sizeof(float);
+  size_t smem = smem_w + (contiguous ? (size_t)128 * (6 * cin + 16) : 0);
+  if (smem > 48 * 1024) {          // wide inputs: skip the coalescing stage, read the pixel rows straight from global
+    contiguous = 0;
+    smem = smem_w;
+  }
   SN_REQUIRE(smem <= 48 * 1024, SN_ERR_UNSUPPORTED, "final_conv: cin %d too large", cin);
   const int grid = ew_grid((total + 127) / 128 * 128, 128, 6);
 #define SN_FINAL(CC)                                                                                           \

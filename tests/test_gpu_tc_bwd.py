@@ -402,8 +402,9 @@ def _elbo_grads_fast_vs_oracle(S, variant, C, in_ch, B, alpha, kl):
     return errs
 
 
-def test_hippocampus_elbo_gradients_fast(S):
-    errs = _elbo_grads_fast_vs_oracle(S, "hippocampus", 3, 1, 4, 1.0, 1e-3)
+@pytest.mark.parametrize("C", [3, 5])            # 5 = the class count of Brats.py:464
+def test_hippocampus_elbo_gradients_fast(S, C):
+    errs = _elbo_grads_fast_vs_oracle(S, "hippocampus", C, 1, 4, 1.0, 1e-3)
     assert max(errs.values()) < 1e-2, errs
 
 
@@ -448,3 +449,30 @@ def test_saliency_map_fast(S):
     print("saliency rel", err)
     assert err < 1e-2, err
     assert torch.equal(relu_grad, torch.relu(grad)) and rel(pred, p) < 1e-3
+
+
+def test_fast_mode_other_width_uses_the_general_kernels(S):
+    """n_kernels = 64 (the reference's layers take any kernel_num): the shape-specialised first / last layer kernels
+    do not apply, so FAST mode must route those two layers through the general ones -- forward, input gradient and
+    weight gradients still match the oracle."""
+    from supernet_b200 import dp
+    variant, n, C, in_ch, B = "hippocampus", 64, 3, 1, 2
+    oracle = O.UNetOracle(variant, n, C, in_ch, torch.float64)
+    w = O.make_weights(variant, n, C, in_ch)
+    model = S.Density_prop_with_pad_UNET(n, C, variant=variant, mode="fast").load_weight_dict(w, device="cuda")
+    x = O.make_input(variant, B)
+    y = O.make_labels(B, 54 * 54, C, dtype=torch.float64)
+    p_ref, v_ref = oracle(x)
+    with torch.no_grad():
+        p, v = model(dev(x))
+    assert rel(p, p_ref) < 1e-3 and rel(v, v_ref) < 1e-2 and O.argmax_agreement(p.cpu(), p_ref) >= 0.999
+    g_ref, _ = oracle.fgsm_gradient(x, y)
+    _, g = S.create_adversarial_pattern(model, dev(x), dev(y))
+    assert rel(g, g_ref) < 1e-2, rel(g, g_ref)
+    oracle.requires_grad_(True)
+    rg = torch.autograd.grad(oracle.elbo_loss(x, y, kl_factor=1e-3), oracle.parameters())
+    trainer = dp.DataParallelTrainer(model, lr=0.0, kl_factor=1e-3)
+    trainer._fast_backward(dev(x), dev(y))
+    worst = max(rel(a.grad, b) for a, b in zip([q for c in model.convs() for q in c.weights()], rg))
+    print("n_kernels 64: input gradient", rel(g, g_ref), "worst weight gradient", worst)
+    assert worst < 1e-2, worst
