@@ -3,7 +3,9 @@
 // pack / unpack / fill, weight preparation, the first convolution (fp32 image in, Cin <= 8), the arg-max
 // pooling and the final 1x1 convolution fused with the softmax-Jacobian variance.
 #include "sn_common.cuh"
+#include "sn_sm100.cuh"
 
+#include <stdlib.h>
 #include <mutex>
 
 namespace sn {
@@ -319,6 +321,203 @@ __global__ void __launch_bounds__(FC_THREADS) first_conv_k3c32_kernel(int B, int
 }
 
 // ---------------------------------------------------------------------------------------------------------
+// First convolution on the tensor cores (k = 3, 32 output channels, Cin = 4 or 1; myConv_input, Brats.py:65-76).
+// GEMM view: M = 128 consecutive output pixels, K = 9*Cin (<= 36, zero-padded to 16/48), N = 32.  The input is the
+// fp32 image, so there is no packed tile for TMA to fetch: each thread builds its pixel's im2col row itself (nine
+// 16-byte loads), splits it into bf16 hi/lo and writes both A planes into shared memory in the canonical
+// SWIZZLE_128B K-major layout (128-byte rows, 16-byte chunk c of row r stored at chunk c ^ (r & 7)); the weights sit
+// in the same layout as B = [W_hi ; W_lo] (64 rows).  mean = hi x [W_hi;W_lo] (one N = 64 UMMA per K step, the two
+// column halves added in the epilogue) + lo x W_hi; the variance is rank-1, s_n * sum(x^2) over the patch, from the
+// thread's own fp32 values.  One role per CTA (build -> UMMA -> epilogue); 5 CTAs per SM overlap the phases.
+// The CUDA-core version above spends ~1500 instructions per pixel on the 1152 FMAs; here the tensor core does them.
+constexpr int FT_THREADS = 128;
+constexpr int FT_ROWB = 3 * 32 * 2 + 16;       // staged output pixel: 192 B + 16 B pad (conflict-free 16-B accesses)
+constexpr int FT_SMEM = 1024 + 2 * 16384 + 8192 + 256;   // the output stage (26 KB) reuses the two A planes (32 KB)
+constexpr int FT_CTAS_PER_SM = 5;
+
+template <int CIN>
+__global__ void __launch_bounds__(FT_THREADS) first_conv_tc_kernel(int B, int H, int W, const float* __restrict__ x,
+                                                                   const float* __restrict__ w,
+                                                                   const float* __restrict__ ws, sn_packed_view dst,
+                                                                   int relu, int contiguous) {
+  constexpr int K = 9 * CIN, COUT = 32;
+  constexpr int KSTEPS = (K + 15) / 16;
+  constexpr int CHUNKS = KSTEPS * 2;                   // 16-byte chunks (8 bf16) per A row actually read
+  extern __shared__ uint8_t ft_raw[];
+  const uint32_t base = (ptx::smem_u32(ft_raw) + 1023u) & ~1023u;
+  uint8_t* gen = ft_raw + (base - ptx::smem_u32(ft_raw));
+  uint8_t* a_hi = gen;                                 // [128 rows][128 B]
+  uint8_t* a_lo = gen + 16384;
+  uint8_t* b_w = gen + 32768;                          // [64 rows][128 B]: W_hi rows 0-31, W_lo rows 32-63
+  uint8_t* stage = gen;                                // [128][FT_ROWB]: over the A planes, dead once the UMMAs are done
+  const uint32_t bar = base + 32768 + 8192;
+  const uint32_t tmem_slot = bar + 8;
+  volatile uint32_t* tmem_slot_gen = reinterpret_cast<volatile uint32_t*>(gen + 32768 + 8192 + 8);
+  __shared__ float ss[COUT];
+  const int tid = threadIdx.x, warp = tid >> 5;
+
+  // ---- B operand: element (n, k) = W[k][n] (HWIO: k = (kh*3+kw)*CIN + c), hi in rows 0-31, lo in rows 32-63
+  for (int i = tid; i < 64 * 8; i += FT_THREADS) {     // (row, chunk): 8 bf16 each
+    const int row = i >> 3, c = i & 7;
+    const int n = row & 31;
+    uint32_t v[4];
+#pragma unroll
+    for (int e = 0; e < 4; ++e) {
+      float f[2];
+#pragma unroll
+      for (int h = 0; h < 2; ++h) {
+        const int k = c * 8 + e * 2 + h;
+        float wv = k < K ? w[k * COUT + n] : 0.f;
+        const float hi = __bfloat162float(__float2bfloat16_rn(wv));
+        f[h] = row < 32 ? hi : wv - hi;
+      }
+      v[e] = pk2(f[0], f[1]);
+    }
+    *reinterpret_cast<uint4*>(b_w + (row >> 3) * 1024 + (row & 7) * 128 + ((c ^ (row & 7)) << 4)) =
+        make_uint4(v[0], v[1], v[2], v[3]);
+  }
+  if (tid < COUT) ss[tid] = softplus_f(ws[tid]);
+  if (tid == 0) {
+    ptx::mbar_init(bar, 1);
+    ptx::fence_barrier_init();
+  }
+  if (warp == 0) {
+    ptx::tmem_alloc(tmem_slot, 64);
+    ptx::tmem_relinquish();
+  }
+  ptx::fence_proxy_async();
+  ptx::tc_fence_before();
+  __syncthreads();
+  ptx::tc_fence_after();
+  const uint32_t tmem = *tmem_slot_gen;
+
+  const int Ho = H - 2, Wo = W - 2;
+  const size_t total = (size_t)B * Ho * Wo;
+  __nv_bfloat16* out = reinterpret_cast<__nv_bfloat16*>(dst.base);
+  constexpr uint32_t idesc64 = ptx::idesc_bf16_f32(128, 64), idesc32 = ptx::idesc_bf16_f32(128, 32);
+  uint32_t parity = 0;
+  for (size_t tile0 = (size_t)blockIdx.x * 128; tile0 < total; tile0 += (size_t)gridDim.x * 128) {
+    // ---- build this thread's im2col row (row = tid), keep r = sum x^2 for the variance
+    const size_t i = tile0 + tid;
+    const bool live = i < total;
+    int xo = 0, yo = 0, b = 0;
+    if (live) {
+      xo = (int)(i % Wo);
+      size_t t = i / Wo;
+      yo = (int)(t % Ho);
+      b = (int)(t / Ho);
+    }
+    float xv[KSTEPS * 16];
+#pragma unroll
+    for (int k = K; k < KSTEPS * 16; ++k) xv[k] = 0.f;
+#pragma unroll
+    for (int kh = 0; kh < 3; ++kh)
+#pragma unroll
+      for (int kw = 0; kw < 3; ++kw) {
+        const float* px = x + (((size_t)b * H + yo + kh) * W + xo + kw) * CIN;
+        if constexpr (CIN == 4) {
+          const float4 v = live ? __ldg(reinterpret_cast<const float4*>(px)) : make_float4(0.f, 0.f, 0.f, 0.f);
+          xv[(kh * 3 + kw) * 4 + 0] = v.x; xv[(kh * 3 + kw) * 4 + 1] = v.y;
+          xv[(kh * 3 + kw) * 4 + 2] = v.z; xv[(kh * 3 + kw) * 4 + 3] = v.w;
+        } else {
+#pragma unroll
+          for (int c = 0; c < CIN; ++c) xv[(kh * 3 + kw) * CIN + c] = live ? __ldg(px + c) : 0.f;
+        }
+      }
+    float r = 0.f;
+#pragma unroll
+    for (int k = 0; k < K; ++k) r = fmaf(xv[k], xv[k], r);
+    {
+      uint8_t* rh = a_hi + (tid >> 3) * 1024 + (tid & 7) * 128;
+      uint8_t* rl = a_lo + (tid >> 3) * 1024 + (tid & 7) * 128;
+#pragma unroll
+      for (int c = 0; c < CHUNKS; ++c) {
+        uint32_t h[4], l[4];
+#pragma unroll
+        for (int e = 0; e < 4; ++e) {
+          const float f0 = xv[c * 8 + 2 * e], f1 = xv[c * 8 + 2 * e + 1];
+          h[e] = pk2(f0, f1);
+          l[e] = pk2(f0 - blo(h[e]), f1 - bhi(h[e]));
+        }
+        const int pc = (c ^ (tid & 7)) << 4;
+        *reinterpret_cast<uint4*>(rh + pc) = make_uint4(h[0], h[1], h[2], h[3]);
+        *reinterpret_cast<uint4*>(rl + pc) = make_uint4(l[0], l[1], l[2], l[3]);
+      }
+    }
+    ptx::fence_proxy_async();
+    __syncthreads();
+    if (tid == 0) {
+      ptx::tc_fence_after();
+#pragma unroll
+      for (int ks = 0; ks < KSTEPS; ++ks) {
+        const uint64_t da_hi = ptx::smem_desc_kmajor<128>(base + ks * 32);
+        const uint64_t da_lo = ptx::smem_desc_kmajor<128>(base + 16384 + ks * 32);
+        const uint64_t db = ptx::smem_desc_kmajor<128>(base + 32768 + ks * 32);
+        ptx::umma_bf16(tmem, da_hi, db, idesc64, ks > 0 ? 1u : 0u);      // hi x [W_hi ; W_lo] -> columns [0, 64)
+        ptx::umma_bf16(tmem, da_lo, db, idesc32, 1u);                     // lo x W_hi          -> columns [0, 32)
+      }
+      ptx::umma_commit(bar);
+    }
+    ptx::mbar_wait(bar, parity);
+    parity ^= 1u;
+    ptx::tc_fence_after();
+    // ---- epilogue: thread = pixel row = TMEM lane
+    uint8_t* o = contiguous ? stage + tid * FT_ROWB
+                            : reinterpret_cast<uint8_t*>(
+                                  out + ((((size_t)b * dst.h + yo + dst.y0) * dst.w + xo + dst.x0) * 3) * dst.c + dst.c0);
+    const int plane_b = contiguous ? COUT * 2 : dst.c * 2;
+    const uint32_t lane_base = tmem + ((uint32_t)(warp * 32) << 16);
+#pragma unroll
+    for (int c0 = 0; c0 < COUT; c0 += 16) {
+      uint32_t a0[16], a1[16];
+      ptx::tmem_ld16(lane_base + c0, a0);
+      ptx::tmem_ld16(lane_base + 32 + c0, a1);
+      ptx::tmem_ld_wait();
+      float mu[16], var[16];
+#pragma unroll
+      for (int j = 0; j < 16; ++j) {
+        float m = __uint_as_float(a0[j]) + __uint_as_float(a1[j]);
+        float v = ss[c0 + j] * r;
+        if (relu) {
+          v = m > 0.f ? v : 0.f;
+          m = fmaxf(m, 0.f);
+        }
+        mu[j] = m;
+        var[j] = v;
+      }
+      if (live || contiguous) {
+#pragma unroll
+        for (int h8 = 0; h8 < 16; h8 += 8) {
+          float m8[8], v8[8];
+#pragma unroll
+          for (int j = 0; j < 8; ++j) { m8[j] = mu[h8 + j]; v8[j] = var[h8 + j]; }
+          uint4 hi, lo;
+          split8(m8, hi, lo);
+          *reinterpret_cast<uint4*>(o + (c0 + h8) * 2) = hi;
+          *reinterpret_cast<uint4*>(o + plane_b + (c0 + h8) * 2) = lo;
+          *reinterpret_cast<uint4*>(o + 2 * plane_b + (c0 + h8) * 2) = pack8(v8);
+        }
+      }
+    }
+    ptx::tc_fence_before();
+    __syncthreads();                       // TMEM reads done (next tile's UMMAs may overwrite); stage complete
+    if (contiguous) {
+      const size_t remain = total - tile0;
+      const int chunks = (int)(remain < 128 ? remain : 128) * 12;
+      uint4* g = reinterpret_cast<uint4*>(out + tile0 * 3 * COUT);
+      for (int c = tid; c < chunks; c += FT_THREADS) {
+        const int pix = c / 12, part = c - pix * 12;
+        g[c] = *reinterpret_cast<const uint4*>(stage + pix * FT_ROWB + part * 16);
+      }
+      __syncthreads();
+    }
+  }
+  ptx::tc_fence_before();
+  __syncthreads();
+  if (warp == 0) ptx::tmem_dealloc(tmem, 64);
+}
+
+// ---------------------------------------------------------------------------------------------------------
 // arg-max pooling on packed windows (Brats.py:171-174,206-216); thread = (output pixel, 8 channels)
 // ---------------------------------------------------------------------------------------------------------
 __global__ void maxpool_packed_kernel(sn_packed_view src, int B, int H, int W, int c, sn_packed_view dst) {
@@ -566,6 +765,29 @@ int sn_first_conv_fwd_packed(int32_t batch, int32_t in_h, int32_t in_w, int32_t 
   int rc = check_pview(dst, batch, Ho, Wo, cout, "first_conv dst");
   if (rc) return rc;
   const int relu = (flags & SN_TC_RELU) ? 1 : 0;
+  static const bool first_tc = [] {
+    const char* e = getenv("SN_FIRST_CONV_TC");
+    return e == nullptr || e[0] != '0';
+  }();
+  if (first_tc && ksize == 3 && cout == 32 && (cin == 4 || cin == 1) && aligned16(x)) {
+    const size_t pixels = (size_t)batch * Ho * Wo;
+    static std::once_flag ft_once;
+    std::call_once(ft_once, [] {
+      cudaFuncSetAttribute(first_conv_tc_kernel<4>, cudaFuncAttributeMaxDynamicSharedMemorySize, FT_SMEM);
+      cudaFuncSetAttribute(first_conv_tc_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, FT_SMEM);
+    });
+    const size_t tiles = (pixels + 127) / 128;
+    const size_t cap = (size_t)num_sms() * FT_CTAS_PER_SM;
+    const int grid = (int)(tiles < cap ? tiles : cap);
+    const int contiguous = dst->y0 == 0 && dst->x0 == 0 && dst->c0 == 0 && dst->h == Ho && dst->w == Wo && dst->c == cout;
+    if (cin == 4)
+      first_conv_tc_kernel<4><<<grid, FT_THREADS, FT_SMEM, as_stream(st)>>>(batch, in_h, in_w, x, w_mu, w_sigma, *dst,
+                                                                            relu, contiguous);
+    else
+      first_conv_tc_kernel<1><<<grid, FT_THREADS, FT_SMEM, as_stream(st)>>>(batch, in_h, in_w, x, w_mu, w_sigma, *dst,
+                                                                            relu, contiguous);
+    return check_launch("first_conv_tc");
+  }
   if (ksize == 3 && cout == 32 && (cin == 4 || cin == 1)) {
     const size_t pixels = (size_t)batch * Ho * Wo;
     const int fc_smem_bytes = (9 * cin * 32 + 32) * (int)sizeof(float) + FC_PIX * (3 * 32 * 2 + 16);
