@@ -174,7 +174,7 @@ size_t sn_prepared_weight_bytes(int32_t ksize, int32_t cin, int32_t cout);
 int sn_prepare_weights(const float* w_mu, const float* w_sigma, int32_t ksize, int32_t cin, int32_t cout,
                        int32_t upconv, void* w_packed, float* s_out, sn_stream_t st);
 
-enum { SN_TC_RELU = 1, SN_TC_UPCONV = 2, SN_TC_DST_F32 = 4, SN_TC_IM2COL = 8, SN_TC_ROWS = 16 };
+enum { SN_TC_RELU = 1, SN_TC_UPCONV = 2, SN_TC_DST_F32 = 4, SN_TC_IM2COL = 8, SN_TC_ROWS = 16, SN_TC_EXACT = 32 };
 
 /* One fused moment convolution on the tensor cores: myConv_intermediate.call (Brats.py:118-137), optionally
  * with the ReLU gate of Brats.py:233-238 (SN_TC_RELU), reading the channel-concat of up to two packed windows
@@ -200,7 +200,11 @@ typedef struct sn_tc_conv_desc {
 } sn_tc_conv_desc;
 int sn_conv_moments_fwd_tc(const sn_tc_conv_desc* d, sn_stream_t st);
 
-/* myConv_input.call (Brats.py:65-76) (+ ReLU with SN_TC_RELU) on fp32 NHWC x (cin <= 8), written as a packed window. */
+/* myConv_input.call (Brats.py:65-76) (+ ReLU with SN_TC_RELU) on fp32 NHWC x (cin <= 8), written as a packed window.
+ * k = 3, cout = 32, cin in {1, 4} runs on the tensor cores (bf16 hi/lo image and weights, ~1e-5 relative); with
+ * SN_TC_EXACT the fp32 CUDA-core kernel is used instead: the gradient engine wants this layer's ReLU gates -- the
+ * largest tensor of the network -- decided at fp32 accuracy, because every flipped gate is a 100 % error of that
+ * element's gradient. */
 int sn_first_conv_fwd_packed(int32_t batch, int32_t in_h, int32_t in_w, int32_t cin, int32_t cout, int32_t ksize,
                              const float* x, const float* w_mu, const float* w_sigma, const sn_packed_view* dst,
                              int32_t flags, sn_stream_t st);

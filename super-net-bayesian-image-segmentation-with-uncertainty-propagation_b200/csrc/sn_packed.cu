@@ -769,7 +769,7 @@ int sn_first_conv_fwd_packed(int32_t batch, int32_t in_h, int32_t in_w, int32_t 
     const char* e = getenv("SN_FIRST_CONV_TC");
     return e == nullptr || e[0] != '0';
   }();
-  if (first_tc && ksize == 3 && cout == 32 && (cin == 4 || cin == 1) && aligned16(x)) {
+  if (first_tc && !(flags & SN_TC_EXACT) && ksize == 3 && cout == 32 && (cin == 4 || cin == 1) && aligned16(x)) {
     const size_t pixels = (size_t)batch * Ho * Wo;
     static std::once_flag ft_once;
     std::call_once(ft_once, [] {

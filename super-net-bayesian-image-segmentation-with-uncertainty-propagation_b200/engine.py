@@ -133,7 +133,8 @@ class InferenceEngine:
         w_in, ws_in = m.conv_input.weights()
         self.step_names.append("conv_input")
         self.records.append(dict(kind="first", dst=PackedView(a0)))
-        steps.append(lambda: F.first_conv_packed(self.x_in, w_in, ws_in, PackedView(a0), relu=True))
+        exact0 = bool(getattr(self, "exact_first_conv", False))     # GradientEngine: fp32-exact gates in the first layer
+        steps.append(lambda: F.first_conv_packed(self.x_in, w_in, ws_in, PackedView(a0), relu=True, exact=exact0))
         skip = new(h - 2, w - 2, n)
         conv("conv1", PackedView(a0), n, h, w, 3, PackedView(skip), True)
         h, w = h - 2, w - 2
@@ -247,6 +248,7 @@ class GradientEngine(InferenceEngine):
                  train: bool = False):
         self.want_rsum = train
         self.train = train
+        self.exact_first_conv = True
         super().__init__(model, batch, in_h, in_w, in_c, device, graph=False, keep_presoftmax=False)
         self.use_graph_bwd = graph
         self._graph_bwd: Optional[torch.cuda.CUDAGraph] = None

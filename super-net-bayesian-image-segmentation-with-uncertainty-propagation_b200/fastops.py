@@ -13,7 +13,7 @@ from typing import Optional, Tuple
 import torch
 
 from . import _lib
-from ._lib import (SN_TC_DST_F32, SN_TC_IM2COL, SN_TC_RELU, SN_TC_ROWS, SN_TC_UPCONV, check, ptr, sn_packed_view, sn_tc_conv_desc,
+from ._lib import (SN_TC_DST_F32, SN_TC_EXACT, SN_TC_IM2COL, SN_TC_RELU, SN_TC_ROWS, SN_TC_UPCONV, check, ptr, sn_packed_view, sn_tc_conv_desc,
                    sn_tc_dgrad_desc, sn_tc_wgrad_desc, stream_ptr)
 
 Tensor = torch.Tensor
@@ -101,12 +101,15 @@ def conv_moments_tc(src0: PackedView, c0: int, batch: int, in_h: int, in_w: int,
     check(_lib.load().sn_conv_moments_fwd_tc(C.byref(d), stream_ptr()), "conv_moments_fwd_tc")
 
 
-def first_conv_packed(x: Tensor, w_mu: Tensor, w_sigma: Tensor, dst: PackedView, relu: bool = True) -> None:
+def first_conv_packed(x: Tensor, w_mu: Tensor, w_sigma: Tensor, dst: PackedView, relu: bool = True,
+                      exact: bool = False) -> None:
+    """exact=True: the fp32 CUDA-core kernel instead of the tensor-core one (see SN_TC_EXACT in supernet.h)."""
     B, H, W, cin = x.shape
     k, _, _, cout = w_mu.shape
     v = dst.c_view()
+    flags = (SN_TC_RELU if relu else 0) | (SN_TC_EXACT if exact else 0)
     check(_lib.load().sn_first_conv_fwd_packed(B, H, W, cin, cout, k, ptr(x), ptr(w_mu), ptr(w_sigma), C.byref(v),
-                                               SN_TC_RELU if relu else 0, stream_ptr()), "first_conv_fwd_packed")
+                                               flags, stream_ptr()), "first_conv_fwd_packed")
 
 
 def maxpool2_packed(src: PackedView, batch: int, in_h: int, in_w: int, c: int, dst: PackedView) -> None:
