@@ -41,7 +41,10 @@ def sources():
 def _digest() -> str:
     h = hashlib.sha256()
     for p in sources() + sorted(glob.glob(os.path.join(CSRC, "*.cuh"))) + sorted(glob.glob(os.path.join(INCLUDE, "*.h"))):
-        h.update(p.encode())
+        # file NAME, not path: the stamp must stay valid when the tree is copied elsewhere (the GPU box runs from a
+        # scratch copy; a path-dependent digest made every process there rebuild, and eight ranks doing so at once
+        # corrupted each other's object files)
+        h.update(os.path.basename(p).encode())
         with open(p, "rb") as f:
             h.update(f.read())
     h.update(" ".join(NVCC_FLAGS).encode())
@@ -59,6 +62,19 @@ def build(force: bool = False, verbose: bool = False) -> str:
     """Compile every csrc/*.cu for sm_100a and link the shared library next to this file."""
     if not force and not needs_build():
         return LIB_PATH
+    import fcntl
+    lock_path = os.path.join(PKG_DIR, ".build_lock")
+    with open(lock_path, "w") as lock:
+        fcntl.flock(lock, fcntl.LOCK_EX)          # one builder at a time (torchrun starts one process per GPU)
+        try:
+            if not force and not needs_build():   # another process built it while we waited
+                return LIB_PATH
+            return _build_locked(verbose)
+        finally:
+            fcntl.flock(lock, fcntl.LOCK_UN)
+
+
+def _build_locked(verbose: bool) -> str:
     nvcc = _nvcc()
     objdir = os.path.join(PKG_DIR, "build")
     os.makedirs(objdir, exist_ok=True)
@@ -77,10 +93,12 @@ def build(force: bool = False, verbose: bool = False) -> str:
             print(out, file=sys.stderr)
         if p.returncode != 0:
             raise RuntimeError(f"nvcc failed on {src}:\n{out}")
-    link = [nvcc, "-shared", "-o", LIB_PATH, *objs, "-cudart", "static", "-Xlinker", "--no-undefined", "-lpthread", "-ldl", "-lrt"]
+    tmp_lib = LIB_PATH + f".tmp{os.getpid()}"
+    link = [nvcc, "-shared", "-o", tmp_lib, *objs, "-cudart", "static", "-Xlinker", "--no-undefined", "-lpthread", "-ldl", "-lrt"]
     r = subprocess.run(link, stdout=subprocess.PIPE, stderr=subprocess.STDOUT, text=True)
     if r.returncode != 0:
         raise RuntimeError(f"link failed:\n{r.stdout}")
+    os.replace(tmp_lib, LIB_PATH)                 # atomic: a concurrent loader never sees a half-written library
     with open(STAMP, "w") as f:
         f.write(_digest())
     return LIB_PATH

@@ -180,3 +180,20 @@ def test_noise_drivers_match_reference_semantics():
     assert R.make_noise(x, "speckle", 0.1, g).shape == x.shape
     assert R.center_crop(x, 4).shape == (2, 4, 4, 4)
     assert R.one_hot_flat(labels, 4).shape == (2, 64, 4)
+
+
+def test_build_stamp_survives_relocation(tmp_path):
+    """The GPU box runs from a scratch copy of the tree: the shipped library must be accepted there without a rebuild
+    (a path-dependent stamp once made eight torchrun ranks rebuild at the same time and corrupt the link)."""
+    import importlib.util
+    import shutil
+    S = _S()
+    assert not S.build.needs_build()
+    pkg = os.path.dirname(S.build.__file__)
+    root = tmp_path / "elsewhere"
+    shutil.copytree(pkg, root / os.path.basename(pkg), ignore=shutil.ignore_patterns("build", "__pycache__"))
+    shutil.copytree(os.path.join(ROOT, "include"), root / "include")
+    spec = importlib.util.spec_from_file_location("sn_build_copy", str(root / os.path.basename(pkg) / "build.py"))
+    mod = importlib.util.module_from_spec(spec)
+    spec.loader.exec_module(mod)
+    assert mod.ROOT == str(root) and not mod.needs_build()
