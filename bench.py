@@ -252,6 +252,8 @@ def main():
         raise SystemExit("bench.py needs a CUDA device (the product path has no CPU fallback)")
     torch.cuda.set_device(local)
     dev = torch.device("cuda", local)
+    from supernet_b200 import dp
+    numa = dp.bind_to_gpu_numa_node(local) if world > 1 else None    # node-local pinned staging for the e2e path
     if world > 1:
         dist.init_process_group("nccl", device_id=dev)
     S._lib.check(S._lib.load().sn_device_check(), "device_check")
@@ -392,6 +394,7 @@ def main():
                                    f"n_kernels {N_KERNELS}, random-init weights (BASELINE.json configs[1])",
                        "batch_per_gpu": B, "global_batch": B * world, "mode": args.mode,
                        "parallelism": f"batch-sharded x{world}, no data-path collective",
+                       "host_numa_node_rank0": numa,
                        "l2_policy": "per-step activation traffic (~%.1f GB) >> 126 MB L2, no flush needed"
                                     % (sum(r["bytes"] for r in table) * B / 1e9)},
             "e2e": {"value": round(e2e, 1), "unit": UNIT, "h2d_bytes_per_step": int(x_host.numel() * 4),

@@ -20,6 +20,44 @@ import torch.distributed as dist
 Tensor = torch.Tensor
 
 
+def _parse_cpulist(text: str) -> List[int]:
+    cpus: List[int] = []
+    for part in text.strip().split(","):
+        if not part:
+            continue
+        if "-" in part:
+            a, b = part.split("-")
+            cpus.extend(range(int(a), int(b) + 1))
+        else:
+            cpus.append(int(part))
+    return cpus
+
+
+def bind_to_gpu_numa_node(device_index: int) -> Optional[int]:
+    """Pin this process to the CPUs of the NUMA node its GPU hangs off (sysfs), BEFORE any pinned host buffer is
+    allocated, so the staging buffers of the host-to-host path are node-local.  With one process per GPU and no
+    affinity every rank's pinned memory tends to land on one socket and the other socket's GPUs DMA across the
+    inter-socket link.  Returns the node, or None when the topology is not visible (then nothing is changed)."""
+    import os
+    try:
+        props = torch.cuda.get_device_properties(device_index)
+        bdf = "%04x:%02x:%02x.0" % (props.pci_domain_id, props.pci_bus_id, props.pci_device_id)
+        with open(f"/sys/bus/pci/devices/{bdf}/numa_node") as f:
+            node = int(f.read().strip())
+        if node < 0:
+            return None
+        with open(f"/sys/devices/system/node/node{node}/cpulist") as f:
+            cpus = _parse_cpulist(f.read())
+        allowed = os.sched_getaffinity(0)
+        cpus = [c for c in cpus if c in allowed]
+        if not cpus:
+            return None
+        os.sched_setaffinity(0, cpus)
+        return node
+    except Exception:
+        return None
+
+
 def shard_bounds(global_batch: int, world_size: int, rank: int) -> Tuple[int, int]:
     """[start, stop) of `rank`'s slices: per-GPU batch = ceil(global / world); the last ranks may
     get fewer (or zero) slices."""

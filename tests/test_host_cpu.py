@@ -142,6 +142,19 @@ def _dp_worker(rank, world, port, out):
         p.grad.mul_(100.0)
     dp.clip_by_norm_per_variable_(params, 1.0)
     ok = ok and all(abs(float(p.grad.norm()) - 1.0) < 1e-5 for p in params)
+    # the FAST-mode trainer's path: ONE flat gradient buffer (per-variable gradients are views of it), reduced in place
+    for p in params:
+        p.grad = None
+    flat = torch.zeros(sum(p.numel() for p in params))
+    views, off = [], 0
+    for p in params:
+        views.append(flat[off:off + p.numel()].view_as(p))
+        off += p.numel()
+    for v, g in zip(views, torch.autograd.grad(loss_fn(x[a:b], y[a:b]), params)):
+        v.copy_(g)
+    dp.allreduce_flat_(flat, b - a, 7, bucket_bytes=32)             # several slices of the flat buffer
+    full = torch.autograd.grad(loss_fn(x, y), params)
+    ok = ok and all(torch.allclose(v, g, atol=1e-6) for v, g in zip(views, full))
     out[rank] = ok
     dist.destroy_process_group()
 
