@@ -114,3 +114,26 @@ def test_training_step_matches_oracle_adam(S):
             worst = max(O.rel_l2(a.detach().cpu().double() - b.cpu().double(), r.detach() - r0)
                         for b, a, r, r0 in zip(before, after, params, ref0))
             assert worst < 5e-2, worst
+
+
+def test_metrics_and_batch_feeding_stay_on_the_device(S):
+    """Dice / sensitivity / precision / specificity and the shard -> batch conversion run on CUDA
+    tensors (no .numpy() round trip per step, Brats.py:688-705) and agree with the CPU evaluation."""
+    import numpy as np
+    from supernet_b200 import dataio, metrics
+    g = np.random.default_rng(11)
+    x = g.random((4, 1, 64, 64)).astype(np.float32)                 # shard layout [B,C,H,W]
+    y = g.integers(0, 3, size=(4, 64, 64))
+    xt, yc, onehot = dataio.batch_from_shard(x, y, out_size=54, n_labels=3, device="cuda")
+    assert xt.is_cuda and xt.shape == (4, 64, 64, 1) and onehot.shape == (4, 54 * 54, 3)
+    _, model = _pair(S, mode="fast")
+    with torch.no_grad():
+        p, _ = model(xt)
+    pred = metrics.predictions_to_labels(p, 54, 54)
+    assert pred.is_cuda
+    rep_gpu = metrics.region_report(yc, pred)
+    rep_cpu = metrics.region_report(yc.cpu(), pred.cpu())
+    for region in rep_gpu:
+        for k, v in rep_gpu[region].items():
+            a, b = v, rep_cpu[region][k]
+            assert (np.isnan(a) and np.isnan(b)) or abs(a - b) < 1e-12
