@@ -77,6 +77,7 @@ struct HlP {
   // data gradient only: destination / saved-activation windows of the two forward sources
   HlView gdst[2], saved[2];
   int csplit, gate[2];
+  int v8;                  // every packed row segment the epilogue touches is 32-byte aligned: use 256-bit accesses
 };
 
 __device__ __forceinline__ float hl_lo(uint32_t v) { return __uint_as_float(v << 16); }
@@ -445,14 +446,22 @@ __global__ void __launch_bounds__(HL_THREADS, 1) conv_moments_halo_kernel(const 
             const int nch = gcol - (seg ? p.csplit : 0);
             const HlView& dv = p.gdst[seg];
             const HlView& sv = p.saved[seg];
-            uint4 sh0 = make_uint4(0, 0, 0, 0), sh1 = sh0, sl0 = sh0, sl1 = sh0;
+            uint32_t shw[8] = {0, 0, 0, 0, 0, 0, 0, 0}, slw[8] = {0, 0, 0, 0, 0, 0, 0, 0};
             if (valid) {
               const __nv_bfloat16* sp =
                   sv.base + ((((size_t)ob * sv.h + oy_i + sv.y0) * sv.w + ox_i + sv.x0) * 3) * sv.c + sv.c0 + nch;
-              sh0 = *reinterpret_cast<const uint4*>(sp);
-              sh1 = *reinterpret_cast<const uint4*>(sp + 8);
-              sl0 = *reinterpret_cast<const uint4*>(sp + sv.c);
-              sl1 = *reinterpret_cast<const uint4*>(sp + sv.c + 8);
+              if (p.v8) {
+                ptx::ld_global_v8(sp, shw);
+                ptx::ld_global_v8(sp + sv.c, slw);
+              } else {
+                const uint4 sh0 = *reinterpret_cast<const uint4*>(sp), sh1 = *reinterpret_cast<const uint4*>(sp + 8);
+                const uint4 sl0 = *reinterpret_cast<const uint4*>(sp + sv.c);
+                const uint4 sl1 = *reinterpret_cast<const uint4*>(sp + sv.c + 8);
+                shw[0] = sh0.x; shw[1] = sh0.y; shw[2] = sh0.z; shw[3] = sh0.w;
+                shw[4] = sh1.x; shw[5] = sh1.y; shw[6] = sh1.z; shw[7] = sh1.w;
+                slw[0] = sl0.x; slw[1] = sl0.y; slw[2] = sl0.z; slw[3] = sl0.w;
+                slw[4] = sl1.x; slw[5] = sl1.y; slw[6] = sl1.z; slw[7] = sl1.w;
+              }
             }
             uint32_t am[16], av[16];
             ptx::tmem_ld16(lane_base + c0, am);
@@ -466,8 +475,6 @@ __global__ void __launch_bounds__(HL_THREADS, 1) conv_moments_halo_kernel(const 
             } else {
               ptx::tmem_ld_wait();
             }
-            const uint32_t shw[8] = {sh0.x, sh0.y, sh0.z, sh0.w, sh1.x, sh1.y, sh1.z, sh1.w};
-            const uint32_t slw[8] = {sl0.x, sl0.y, sl0.z, sl0.w, sl1.x, sl1.y, sl1.z, sl1.w};
             const bool gate = p.gate[seg] != 0;
             const float r2 = 2.f * r;
             uint32_t hi[8], lo[8], vr[8];
@@ -487,15 +494,21 @@ __global__ void __launch_bounds__(HL_THREADS, 1) conv_moments_halo_kernel(const 
             if (valid) {
               __nv_bfloat16* d_hi =
                   dv.base + ((((size_t)ob * dv.h + oy_i + dv.y0) * dv.w + ox_i + dv.x0) * 3) * dv.c + dv.c0 + nch;
-              uint4* ph = reinterpret_cast<uint4*>(d_hi);
-              uint4* pl = reinterpret_cast<uint4*>(d_hi + dv.c);
-              uint4* pv = reinterpret_cast<uint4*>(d_hi + 2 * dv.c);
-              ph[0] = make_uint4(hi[0], hi[1], hi[2], hi[3]);
-              ph[1] = make_uint4(hi[4], hi[5], hi[6], hi[7]);
-              pl[0] = make_uint4(lo[0], lo[1], lo[2], lo[3]);
-              pl[1] = make_uint4(lo[4], lo[5], lo[6], lo[7]);
-              pv[0] = make_uint4(vr[0], vr[1], vr[2], vr[3]);
-              pv[1] = make_uint4(vr[4], vr[5], vr[6], vr[7]);
+              if (p.v8) {
+                ptx::st_global_v8(d_hi, hi);
+                ptx::st_global_v8(d_hi + dv.c, lo);
+                ptx::st_global_v8(d_hi + 2 * dv.c, vr);
+              } else {
+                uint4* ph = reinterpret_cast<uint4*>(d_hi);
+                uint4* pl = reinterpret_cast<uint4*>(d_hi + dv.c);
+                uint4* pv = reinterpret_cast<uint4*>(d_hi + 2 * dv.c);
+                ph[0] = make_uint4(hi[0], hi[1], hi[2], hi[3]);
+                ph[1] = make_uint4(hi[4], hi[5], hi[6], hi[7]);
+                pl[0] = make_uint4(lo[0], lo[1], lo[2], lo[3]);
+                pl[1] = make_uint4(lo[4], lo[5], lo[6], lo[7]);
+                pv[0] = make_uint4(vr[0], vr[1], vr[2], vr[3]);
+                pv[1] = make_uint4(vr[4], vr[5], vr[6], vr[7]);
+              }
             }
           }
         } else {
@@ -565,15 +578,21 @@ __global__ void __launch_bounds__(HL_THREADS, 1) conv_moments_halo_kernel(const 
                 lo[j] = hl_pack2(a0 - hl_lo(hi[j]), a1 - hl_hi(hi[j]));
                 vr[j] = hl_pack2(var[2 * j], var[2 * j + 1]);
               }
-              uint4* ph = reinterpret_cast<uint4*>(d_hi);
-              uint4* pl = reinterpret_cast<uint4*>(d_hi + p.dc);
-              uint4* pv = reinterpret_cast<uint4*>(d_hi + 2 * p.dc);
-              ph[0] = make_uint4(hi[0], hi[1], hi[2], hi[3]);
-              ph[1] = make_uint4(hi[4], hi[5], hi[6], hi[7]);
-              pl[0] = make_uint4(lo[0], lo[1], lo[2], lo[3]);
-              pl[1] = make_uint4(lo[4], lo[5], lo[6], lo[7]);
-              pv[0] = make_uint4(vr[0], vr[1], vr[2], vr[3]);
-              pv[1] = make_uint4(vr[4], vr[5], vr[6], vr[7]);
+              if (p.v8) {
+                ptx::st_global_v8(d_hi, hi);
+                ptx::st_global_v8(d_hi + p.dc, lo);
+                ptx::st_global_v8(d_hi + 2 * p.dc, vr);
+              } else {
+                uint4* ph = reinterpret_cast<uint4*>(d_hi);
+                uint4* pl = reinterpret_cast<uint4*>(d_hi + p.dc);
+                uint4* pv = reinterpret_cast<uint4*>(d_hi + 2 * p.dc);
+                ph[0] = make_uint4(hi[0], hi[1], hi[2], hi[3]);
+                ph[1] = make_uint4(hi[4], hi[5], hi[6], hi[7]);
+                pl[0] = make_uint4(lo[0], lo[1], lo[2], lo[3]);
+                pl[1] = make_uint4(lo[4], lo[5], lo[6], lo[7]);
+                pv[0] = make_uint4(vr[0], vr[1], vr[2], vr[3]);
+                pv[1] = make_uint4(vr[4], vr[5], vr[6], vr[7]);
+              }
             }
           }
         }
@@ -735,6 +754,11 @@ static int hl_launch_dgrad(const HlMaps& maps, const HlP& p, cudaStream_t st) {
   }
 }
 
+// 256-bit epilogue accesses need every (pixel, plane, 16-channel chunk) segment 32-byte aligned
+static bool hl_view_v8(const sn_packed_view& v) {
+  return (reinterpret_cast<uintptr_t>(v.base) & 31u) == 0 && v.c % 16 == 0 && v.c0 % 16 == 0;
+}
+
 // Tile geometry + shared-memory plan shared by the forward and the data-gradient dispatch.
 static int hl_plan(HlP& p, const HaloTiling& t, int keff, int ncols, int nt, int cblk) {
   p.tiles_x = t.tiles_x; p.tiles_y = t.tiles_y; p.tiles_b = t.tiles_b;
@@ -802,6 +826,11 @@ int conv_moments_halo_dispatch(const sn_tc_conv_desc* d, cudaStream_t stream) {
   p.dst_mu = d->dst_mu; p.dst_var = d->dst_var; p.out_h = out_h; p.out_w = out_w;
   p.s = d->s; p.s_len = d->cout;
   p.r_out = d->rsum_out;
+  static const bool use_v8 = [] {
+    const char* e = getenv("SN_V8");
+    return e == nullptr || e[0] != '0';
+  }();
+  p.v8 = use_v8 && !dst_f32 && hl_view_v8(d->dst) ? 1 : 0;
 
   HlMaps maps;
   for (int s = 0; s < 2; ++s) {
@@ -857,11 +886,17 @@ int conv_moments_halo_dgrad_dispatch(const sn_tc_dgrad_desc* d, cudaStream_t str
   p.cout = ncols;
   p.s = d->s; p.s_len = d->cout;
   p.csplit = d->in_c[1] ? d->in_c[0] : ncols;
+  p.v8 = 1;
+  {
+    const char* e = getenv("SN_V8");
+    if (e != nullptr && e[0] == '0') p.v8 = 0;
+  }
   for (int s = 0; s < 2; ++s) {
     const int ss = d->in_c[s] ? s : 0;
     p.gdst[s] = hl_view(d->g_in[ss]);
     p.saved[s] = hl_view(d->in[ss]);
     p.gate[s] = d->gate[ss];
+    if (!hl_view_v8(d->g_in[ss]) || !hl_view_v8(d->in[ss]) || d->in_c[0] % 16 != 0) p.v8 = 0;
   }
 
   HlMaps maps;
