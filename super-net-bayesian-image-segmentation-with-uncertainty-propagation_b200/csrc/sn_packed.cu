@@ -571,6 +571,68 @@ __global__ void maxpool_packed_kernel(sn_packed_view src, int B, int H, int W, i
   }
 }
 
+// Same, 16 channels per thread through 256-bit accesses (one full 32-byte sector per lane and instruction): the
+// variant used whenever the views are 32-byte aligned (every buffer of the engines is).
+__global__ void maxpool_packed16_kernel(sn_packed_view src, int B, int H, int W, int c, sn_packed_view dst) {
+  const int Ho = (H + 1) / 2, Wo = (W + 1) / 2;
+  const int g = c / 16;
+  const size_t total = (size_t)B * Ho * Wo * g;
+  const size_t stride = (size_t)gridDim.x * blockDim.x;
+  const __nv_bfloat16* in = reinterpret_cast<const __nv_bfloat16*>(src.base);
+  __nv_bfloat16* out = reinterpret_cast<__nv_bfloat16*>(dst.base);
+  for (size_t i = blockIdx.x * (size_t)blockDim.x + threadIdx.x; i < total; i += stride) {
+    const int c16 = (int)(i % g) * 16;
+    size_t t = i / g;
+    const int xo = (int)(t % Wo);
+    t /= Wo;
+    const int yo = (int)(t % Ho);
+    const int b = (int)(t / Ho);
+    float best[16];
+    uint32_t bh[8], bl[8], bv[8];      // winning (hi, lo, var) as packed bf16 pairs
+#pragma unroll
+    for (int j = 0; j < 16; ++j) best[j] = -INFINITY;
+#pragma unroll
+    for (int j = 0; j < 8; ++j) bh[j] = bl[j] = bv[j] = 0;
+#pragma unroll
+    for (int d = 0; d < 4; ++d) {
+      const int y = 2 * yo + (d >> 1), xx = 2 * xo + (d & 1);
+      if (y < H && xx < W) {
+        const __nv_bfloat16* sp =
+            in + ((((size_t)b * src.h + y + src.y0) * src.w + xx + src.x0) * 3) * src.c + src.c0 + c16;
+        uint32_t hw[8], lw[8], vw[8];
+        ptx::ld_global_v8(sp, hw);
+        ptx::ld_global_v8(sp + src.c, lw);
+        ptx::ld_global_v8(sp + 2 * src.c, vw);
+#pragma unroll
+        for (int e = 0; e < 8; ++e) {
+          const float m0 = blo(hw[e]) + blo(lw[e]), m1 = bhi(hw[e]) + bhi(lw[e]);
+          if (m0 > best[2 * e]) {
+            best[2 * e] = m0;
+            bh[e] = (bh[e] & 0xFFFF0000u) | (hw[e] & 0xFFFFu);
+            bl[e] = (bl[e] & 0xFFFF0000u) | (lw[e] & 0xFFFFu);
+            bv[e] = (bv[e] & 0xFFFF0000u) | (vw[e] & 0xFFFFu);
+          }
+          if (m1 > best[2 * e + 1]) {
+            best[2 * e + 1] = m1;
+            bh[e] = (bh[e] & 0xFFFFu) | (hw[e] & 0xFFFF0000u);
+            bl[e] = (bl[e] & 0xFFFFu) | (lw[e] & 0xFFFF0000u);
+            bv[e] = (bv[e] & 0xFFFFu) | (vw[e] & 0xFFFF0000u);
+          }
+        }
+      }
+    }
+    __nv_bfloat16* o =
+        out + ((((size_t)b * dst.h + yo + dst.y0) * dst.w + xo + dst.x0) * 3) * dst.c + dst.c0 + c16;
+    ptx::st_global_v8(o, bh);
+    ptx::st_global_v8(o + dst.c, bl);
+    ptx::st_global_v8(o + 2 * dst.c, bv);
+  }
+}
+
+static bool view_v8(const sn_packed_view* v, int c) {
+  return (reinterpret_cast<uintptr_t>(v->base) & 31u) == 0 && v->c % 16 == 0 && v->c0 % 16 == 0 && c % 16 == 0;
+}
+
 // ---------------------------------------------------------------------------------------------------------
 // final 1x1 convolution + softmax with Jacobian variance (Brats.py:367,454,269-283); thread = pixel
 // ---------------------------------------------------------------------------------------------------------
@@ -821,6 +883,11 @@ int sn_maxpool2_packed(const sn_packed_view* src, int32_t batch, int32_t in_h, i
   if (rc) return rc;
   const int Ho = (in_h + 1) / 2, Wo = (in_w + 1) / 2;
   if ((rc = check_pview(dst, batch, Ho, Wo, c, "maxpool_packed dst"))) return rc;
+  if (view_v8(src, c) && view_v8(dst, c)) {
+    const size_t total16 = (size_t)batch * Ho * Wo * (c / 16);
+    maxpool_packed16_kernel<<<ew_grid(total16, 256), 256, 0, as_stream(st)>>>(*src, batch, in_h, in_w, c, *dst);
+    return check_launch("maxpool_packed16");
+  }
   const size_t total = (size_t)batch * Ho * Wo * (c / 8);
   maxpool_packed_kernel<<<ew_grid(total, 256), 256, 0, as_stream(st)>>>(*src, batch, in_h, in_w, c, *dst);
   return check_launch("maxpool_packed");

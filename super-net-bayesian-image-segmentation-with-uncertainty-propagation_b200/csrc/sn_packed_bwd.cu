@@ -4,6 +4,7 @@
 // [n][h][w][3][c] bf16 (planes g_mean_hi, g_mean_lo, g_variance); gates and arg-max routing are recomputed from
 // the saved forward activations.  Formulas: SURVEY.md A.3 (what tf.GradientTape derives at Brats.py:578,593).
 #include "sn_common.cuh"
+#include "sn_sm100.cuh"
 
 #include <mutex>
 
@@ -142,6 +143,112 @@ __global__ void maxpool_bwd_packed_kernel(sn_packed_view in, int B, int H, int W
   }
 }
 
+// 16 channels per thread through 256-bit accesses (full 32-byte sectors); used when the views are 32-byte aligned.
+__device__ __forceinline__ void b_unpack16(const uint32_t (&u)[8], float (&f)[16]) {
+#pragma unroll
+  for (int e = 0; e < 8; ++e) { f[2 * e] = b_lo(u[e]); f[2 * e + 1] = b_hi(u[e]); }
+}
+__device__ __forceinline__ void b_split16(const float (&m)[16], uint32_t (&hi)[8], uint32_t (&lo)[8]) {
+#pragma unroll
+  for (int j = 0; j < 8; ++j) {
+    hi[j] = b_pk2(m[2 * j], m[2 * j + 1]);
+    lo[j] = b_pk2(m[2 * j] - b_lo(hi[j]), m[2 * j + 1] - b_hi(hi[j]));
+  }
+}
+
+__global__ void maxpool_bwd_packed16_kernel(sn_packed_view in, int B, int H, int W, int c, sn_packed_view gout,
+                                            sn_packed_view gin, int ky0, int kx0, int kh, int kw) {
+  const int Ho = (H + 1) / 2, Wo = (W + 1) / 2;
+  const int g = c / 16;
+  const size_t total = (size_t)B * Ho * Wo * g;
+  const size_t stride = (size_t)gridDim.x * blockDim.x;
+  const __nv_bfloat16* src = reinterpret_cast<const __nv_bfloat16*>(in.base);
+  const __nv_bfloat16* go = reinterpret_cast<const __nv_bfloat16*>(gout.base);
+  __nv_bfloat16* gi = reinterpret_cast<__nv_bfloat16*>(gin.base);
+  for (size_t i = blockIdx.x * (size_t)blockDim.x + threadIdx.x; i < total; i += stride) {
+    const int c16 = (int)(i % g) * 16;
+    size_t t = i / g;
+    const int xo = (int)(t % Wo);
+    t /= Wo;
+    const int yo = (int)(t % Ho);
+    const int b = (int)(t / Ho);
+    float best[16];
+    int arg[16];
+#pragma unroll
+    for (int j = 0; j < 16; ++j) { best[j] = -INFINITY; arg[j] = 0; }
+#pragma unroll
+    for (int d = 0; d < 4; ++d) {
+      const int y = 2 * yo + (d >> 1), x = 2 * xo + (d & 1);
+      if (y < H && x < W) {
+        const __nv_bfloat16* sp = src + pv_off(in, b, y, x) + c16;
+        uint32_t hw[8], lw[8];
+        ptx::ld_global_v8(sp, hw);
+        ptx::ld_global_v8(sp + in.c, lw);
+        float h[16], l[16];
+        b_unpack16(hw, h);
+        b_unpack16(lw, l);
+#pragma unroll
+        for (int j = 0; j < 16; ++j) {
+          const float m = h[j] + l[j];
+          if (m > best[j]) { best[j] = m; arg[j] = d; }
+        }
+      }
+    }
+    const __nv_bfloat16* gp = go + pv_off(gout, b, yo, xo) + c16;
+    float gm[16], gv[16];
+    {
+      uint32_t a[8], bq[8], cq[8];
+      ptx::ld_global_v8(gp, a);
+      ptx::ld_global_v8(gp + gout.c, bq);
+      ptx::ld_global_v8(gp + 2 * gout.c, cq);
+      float gh[16], gl[16];
+      b_unpack16(a, gh);
+      b_unpack16(bq, gl);
+      b_unpack16(cq, gv);
+#pragma unroll
+      for (int j = 0; j < 16; ++j) gm[j] = gh[j] + gl[j];
+    }
+#pragma unroll
+    for (int d = 0; d < 4; ++d) {
+      const int y = 2 * yo + (d >> 1), x = 2 * xo + (d & 1);
+      if (y < H && x < W) {
+        __nv_bfloat16* o = gi + pv_off(gin, b, y, x) + c16;
+        float m[16], v[16];
+        const bool keep = y >= ky0 && y < ky0 + kh && x >= kx0 && x < kx0 + kw;
+        if (keep) {
+          uint32_t a[8], bq[8], cq[8];
+          ptx::ld_global_v8(o, a);
+          ptx::ld_global_v8(o + gin.c, bq);
+          ptx::ld_global_v8(o + 2 * gin.c, cq);
+          float h[16], l[16];
+          b_unpack16(a, h);
+          b_unpack16(bq, l);
+          b_unpack16(cq, v);
+#pragma unroll
+          for (int j = 0; j < 16; ++j) m[j] = h[j] + l[j];
+        } else {
+#pragma unroll
+          for (int j = 0; j < 16; ++j) m[j] = v[j] = 0.f;
+        }
+#pragma unroll
+        for (int j = 0; j < 16; ++j)
+          if (arg[j] == d) { m[j] += gm[j]; v[j] += gv[j]; }
+        uint32_t hi[8], lo[8], vr[8];
+        b_split16(m, hi, lo);
+#pragma unroll
+        for (int j = 0; j < 8; ++j) vr[j] = b_pk2(v[2 * j], v[2 * j + 1]);
+        ptx::st_global_v8(o, hi);
+        ptx::st_global_v8(o + gin.c, lo);
+        ptx::st_global_v8(o + 2 * gin.c, vr);
+      }
+    }
+  }
+}
+
+static bool pv_v8(const sn_packed_view* v, int c) {
+  return (reinterpret_cast<uintptr_t>(v->base) & 31u) == 0 && v->c % 16 == 0 && v->c0 % 16 == 0 && c % 16 == 0;
+}
+
 // ---------------------------------------------------------------------------------------------------------
 // fused head backward; thread = pixel
 // ---------------------------------------------------------------------------------------------------------
@@ -155,7 +262,7 @@ __global__ void __launch_bounds__(128) head_bwd_kernel(sn_packed_view in, int B,
                                                        sn_packed_view gin, float* __restrict__ g_logit_mu,
                                                        float* __restrict__ g_logit_var, float* __restrict__ rsum_out,
                                                        const float* __restrict__ up_gp,
-                                                       const float* __restrict__ up_gv) {
+                                                       const float* __restrict__ up_gv, int v8) {
   // up_gp != nullptr: the upstream gradients w.r.t. (p, var_out) are given (saliency, Brats.py:598-609) instead of
   // being derived from the NLL; `y` and `acc` are then unused.
   extern __shared__ __align__(16) float hsm[];   // W [cin][C], W^2 [cin][C], s [C]
@@ -186,19 +293,44 @@ __global__ void __launch_bounds__(128) head_bwd_kernel(sn_packed_view in, int B,
 #pragma unroll
     for (int j = 0; j < C; ++j) m[j] = v[j] = 0.f;
     float r = 0.f;
-    for (int c8 = 0; c8 < cin; c8 += 8) {
-      float h[8], l[8], vv[8];
-      b_unpack8(*reinterpret_cast<const uint4*>(s + c8), h);
-      b_unpack8(*reinterpret_cast<const uint4*>(s + in.c + c8), l);
-      b_unpack8(*reinterpret_cast<const uint4*>(s + 2 * in.c + c8), vv);
+    for (int c16 = 0; c16 < cin; c16 += 16) {
+      float h[16], l[16], vv[16];
+      if (v8) {                              // 256-bit loads: one full 32-byte sector per lane and instruction
+        uint32_t a[8], bq[8], cq[8];
+        ptx::ld_global_v8(s + c16, a);
+        ptx::ld_global_v8(s + in.c + c16, bq);
+        ptx::ld_global_v8(s + 2 * in.c + c16, cq);
+        b_unpack16(a, h);
+        b_unpack16(bq, l);
+        b_unpack16(cq, vv);
+      } else {
 #pragma unroll
-      for (int e = 0; e < 8; ++e) {
-        const float mu = h[e] + l[e];
-        r += fmaf(mu, mu, vv[e]);
+        for (int q8 = 0; q8 < 16; q8 += 8) {
+          float h8[8], l8[8], v8f[8];
+          const bool in_range = c16 + q8 < cin;
+          if (in_range) {
+            b_unpack8(*reinterpret_cast<const uint4*>(s + c16 + q8), h8);
+            b_unpack8(*reinterpret_cast<const uint4*>(s + in.c + c16 + q8), l8);
+            b_unpack8(*reinterpret_cast<const uint4*>(s + 2 * in.c + c16 + q8), v8f);
+          }
 #pragma unroll
-        for (int j = 0; j < C; ++j) {
-          m[j] = fmaf(mu, sw[(c8 + e) * C + j], m[j]);
-          v[j] = fmaf(vv[e], sw2[(c8 + e) * C + j], v[j]);
+          for (int e = 0; e < 8; ++e) {
+            h[q8 + e] = in_range ? h8[e] : 0.f;
+            l[q8 + e] = in_range ? l8[e] : 0.f;
+            vv[q8 + e] = in_range ? v8f[e] : 0.f;
+          }
+        }
+      }
+#pragma unroll
+      for (int e = 0; e < 16; ++e) {
+        if (c16 + e < cin) {
+          const float mu = h[e] + l[e];
+          r += fmaf(mu, mu, vv[e]);
+#pragma unroll
+          for (int j = 0; j < C; ++j) {
+            m[j] = fmaf(mu, sw[(c16 + e) * C + j], m[j]);
+            v[j] = fmaf(vv[e], sw2[(c16 + e) * C + j], v[j]);
+          }
         }
       }
     }
@@ -270,6 +402,36 @@ __global__ void __launch_bounds__(128) head_bwd_kernel(sn_packed_view in, int B,
     }
     // ---- conv_final data gradient + ReLU gate of its (post-ReLU) input
     __nv_bfloat16* o = dst + pv_off(gin, b, yy, xx);
+    if (v8) {
+      for (int c16 = 0; c16 < cin; c16 += 16) {
+        uint32_t a8[8], b8[8];
+        ptx::ld_global_v8(s + c16, a8);
+        ptx::ld_global_v8(s + in.c + c16, b8);
+        float h[16], l[16], om[16], ov[16];
+        b_unpack16(a8, h);
+        b_unpack16(b8, l);
+#pragma unroll
+        for (int e = 0; e < 16; ++e) {
+          const float mu = h[e] + l[e];
+          float a = 2.f * mu * tt, vv = tt;
+#pragma unroll
+          for (int j = 0; j < C; ++j) {
+            a = fmaf(gm[j], sw[(c16 + e) * C + j], a);
+            vv = fmaf(gv[j], sw2[(c16 + e) * C + j], vv);
+          }
+          const bool on = mu > 0.f;
+          om[e] = on ? a : 0.f;
+          ov[e] = on ? vv : 0.f;
+        }
+        uint32_t hi[8], lo[8], vr[8];
+        b_split16(om, hi, lo);
+#pragma unroll
+        for (int q = 0; q < 8; ++q) vr[q] = b_pk2(ov[2 * q], ov[2 * q + 1]);
+        ptx::st_global_v8(o + c16, hi);
+        ptx::st_global_v8(o + gin.c + c16, lo);
+        ptx::st_global_v8(o + 2 * gin.c + c16, vr);
+      }
+    } else
     for (int c8 = 0; c8 < cin; c8 += 8) {
       float h[8], l[8];
       b_unpack8(*reinterpret_cast<const uint4*>(s + c8), h);
@@ -737,6 +899,12 @@ int sn_maxpool2_bwd_packed(const sn_packed_view* in, int32_t batch, int32_t in_h
   const int Ho = (in_h + 1) / 2, Wo = (in_w + 1) / 2;
   if ((rc = check_pv(g_out, batch, Ho, Wo, c, "maxpool_bwd_packed g_out"))) return rc;
   if ((rc = check_pv(g_in, batch, in_h, in_w, c, "maxpool_bwd_packed g_in"))) return rc;
+  if (pv_v8(in, c) && pv_v8(g_out, c) && pv_v8(g_in, c)) {
+    const size_t total16 = (size_t)batch * Ho * Wo * (c / 16);
+    maxpool_bwd_packed16_kernel<<<ew_grid(total16, 128), 128, 0, as_stream(st)>>>(*in, batch, in_h, in_w, c, *g_out,
+                                                                                 *g_in, keep_y0, keep_x0, keep_h, keep_w);
+    return check_launch("maxpool_bwd_packed16");
+  }
   const size_t total = (size_t)batch * Ho * Wo * (c / 8);
   maxpool_bwd_packed_kernel<<<ew_grid(total, 256), 256, 0, as_stream(st)>>>(*in, batch, in_h, in_w, c, *g_out, *g_in,
                                                                              keep_y0, keep_x0, keep_h, keep_w);
@@ -778,11 +946,12 @@ int sn_head_bwd_general(const sn_packed_view* in, int32_t batch, int32_t in_h, i
   const size_t total = (size_t)batch * in_h * in_w;
   const size_t smem = ((size_t)2 * cin * n_labels + n_labels) * sizeof(float);
   const int grid = ew_grid(total, 128, 8);
+  const int v8 = pv_v8(in, cin) && pv_v8(g_in, cin) ? 1 : 0;
 #define SN_HEAD(CC)                                                                                              \
   case CC:                                                                                                       \
     head_bwd_kernel<CC><<<grid, 128, smem, as_stream(st)>>>(*in, batch, in_h, in_w, cin, w_mu, w_sigma, y, clip_lo, \
                                                              clip_hi, acc, loss_scale, *g_in, g_logit_mu,        \
-                                                             g_logit_var, rsum_out, up_gp, up_gv);               \
+                                                             g_logit_var, rsum_out, up_gp, up_gv, v8);           \
     break;
   switch (n_labels) {
     SN_HEAD(1) SN_HEAD(2) SN_HEAD(3) SN_HEAD(4) SN_HEAD(5) SN_HEAD(6) SN_HEAD(7) SN_HEAD(8)
