@@ -11,6 +11,7 @@ rows = list(csv.reader(raw.splitlines()))
 h = rows[0]
 cols = [("Kernel Name", "kernel"), ("launch__grid_size", "grid"), ("gpu__time_duration.sum", "us"),
         ("sm__pipe_tensor_cycles_active.avg.pct_of_peak_sustained_active", "tensor%"),
+        ("sm__pipe_tc_cycles_active.avg.pct_of_peak_sustained_active", "umma_pipe%"),
         ("gpu__dram_throughput.avg.pct_of_peak_sustained_elapsed", "dram%"),
         ("lts__throughput.avg.pct_of_peak_sustained_elapsed", "L2%"),
         ("dram__bytes_read.sum", "dram_rd_MB"), ("dram__bytes_write.sum", "dram_wr_MB"),
