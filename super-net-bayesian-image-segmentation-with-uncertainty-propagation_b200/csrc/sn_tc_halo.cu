@@ -56,6 +56,7 @@ struct HlView {            // a window of a packed buffer, device side
 
 struct HlP {
   int tiles_x, tiles_y, tiles_b, tiles_n, total_tiles;
+  int pix_tiles, total_groups;   // G = 2 (two pixel tiles per weight slot): pixel tiles per N tile, (N tile, tile pair) groups
   int TWo, THo;            // valid output columns / rows per tile
   int R, THb, TN;          // halo box: columns, rows, images
   int rows_box;            // R * THb * TN  (<= 254)
@@ -111,7 +112,28 @@ struct TileIt {
   }
 };
 
-template <int NT, int KS, bool RESIDENT, bool DGRAD>
+// G = 2: every weight slot (tap, 32-channel block) serves TWO pixel tiles before it is released -- the A stage holds
+// both tiles, the two TMEM accumulator stages are the two tiles of the pair -- which halves the L2->SM weight traffic of
+// the layers whose weights do not fit in shared memory (measured 38-47 B/clk/SM of weights: the UMMA pipe of those
+// layers idled 20-35 % waiting for them).
+struct TileCoord {
+  int nt, tx, ty, tb;
+  bool store;
+};
+__device__ __forceinline__ TileCoord decode_group_tile(int grp, int t, const HlP& p) {
+  TileCoord c;
+  c.nt = grp % p.tiles_n;
+  int pt = (grp / p.tiles_n) * 2 + t;
+  c.store = pt < p.pix_tiles;
+  if (!c.store) pt = p.pix_tiles - 1;          // odd tile count: the pair's second half repeats the last tile, unsaved
+  c.tx = pt % p.tiles_x;
+  pt /= p.tiles_x;
+  c.ty = pt % p.tiles_y;
+  c.tb = pt / p.tiles_y;
+  return c;
+}
+
+template <int NT, int KS, bool RESIDENT, bool DGRAD, int G = 1>
 __global__ void __launch_bounds__(HL_THREADS, 1) conv_moments_halo_kernel(const __grid_constant__ HlMaps maps,
                                                                           const HlP p) {
   constexpr int B_PLANE = NT * HL_KC * 2;
@@ -122,7 +144,8 @@ __global__ void __launch_bounds__(HL_THREADS, 1) conv_moments_halo_kernel(const 
   extern __shared__ uint8_t smem_raw[];
   const uint32_t smem_base = (ptx::smem_u32(smem_raw) + 1023u) & ~1023u;
   uint8_t* smem_gen = smem_raw + (smem_base - ptx::smem_u32(smem_raw));
-  const int a_stage = 3 * p.a_plane;
+  static_assert(G == 1 || !RESIDENT, "two tiles per weight slot only make sense for streamed weights");
+  const int a_stage = G * 3 * p.a_plane;
   const uint32_t b_base = smem_base + p.sa * a_stage;
   const uint32_t bar_base = b_base + p.sb * B_SLOT;           // 1 KB barrier block, then 2 KB q buffers
   auto a_full = [&](int s) { return bar_base + 8u * s; };
@@ -206,12 +229,23 @@ __global__ void __launch_bounds__(HL_THREADS, 1) conv_moments_halo_kernel(const 
                                p.upconv ? pl : pl * p.taps_w + tap);
           }
       }
-      for (int tile = blockIdx.x, titer = 0; tile < p.total_tiles; tile += gridDim.x, ++titer, it.next(p)) {
-        const int nt_i = it.nt, tx = it.tx, ty = it.ty, tb = it.tb;
+      const int n_units = G == 1 ? p.total_tiles : p.total_groups;
+      for (int tile = blockIdx.x, titer = 0; tile < n_units; tile += gridDim.x, ++titer, it.next(p)) {
+        int nt_i, x0s[G], y0s[G], b0s[G];
+        if constexpr (G == 1) {
+          nt_i = it.nt;
+          x0s[0] = it.tx * p.TWo - p.pad; y0s[0] = it.ty * p.THo - p.pad; b0s[0] = it.tb * p.TN;
+        } else {
+#pragma unroll
+          for (int t = 0; t < G; ++t) {
+            const TileCoord c = decode_group_tile(tile, t, p);
+            nt_i = c.nt;
+            x0s[t] = c.tx * p.TWo - p.pad; y0s[t] = c.ty * p.THo - p.pad; b0s[t] = c.tb * p.TN;
+          }
+        }
         const int ncol0 = nt_i * NT;
         const int group = ncol0 / p.cout;
         const int n0 = ncol0 - group * p.cout;
-        const int x0 = tx * p.TWo - p.pad, y0 = ty * p.THo - p.pad, b0 = tb * p.TN;
         int src = 0, cb = 0;
         for (int cbt = 0; cbt < cblk; ++cbt, ++cb) {
           while (cb >= p.cblk_s[src]) { cb = 0; ++src; }
@@ -224,18 +258,20 @@ __global__ void __launch_bounds__(HL_THREADS, 1) conv_moments_halo_kernel(const 
             const uint32_t parity = (uint32_t)(ai / p.sa) & 1u;
             ++ai;
             ptx::mbar_wait(a_empty(stage), parity ^ 1u);
-            ptx::mbar_arrive_expect_tx(a_full(stage), (uint32_t)(3 * p.rows_box * 64));
+            ptx::mbar_arrive_expect_tx(a_full(stage), (uint32_t)(G * 3 * p.rows_box * 64));
             const uint32_t sa_addr = smem_base + stage * a_stage;
 #pragma unroll
-            for (int pl = 0; pl < 3; ++pl) {
-              asm volatile(
-                  "cp.async.bulk.tensor.4d.shared::cluster.global.mbarrier::complete_tx::bytes"
-                  " [%0], [%1, {%3, %4, %5, %6}], [%2];"
-                  :
-                  : "r"(sa_addr + pl * p.a_plane), "l"(reinterpret_cast<uint64_t>(&maps.a[src][pl])),
-                    "r"(a_full(stage)), "r"(cb * HL_KC), "r"(x0), "r"(y0), "r"(b0)
-                  : "memory");
-            }
+            for (int t = 0; t < G; ++t)
+#pragma unroll
+              for (int pl = 0; pl < 3; ++pl) {
+                asm volatile(
+                    "cp.async.bulk.tensor.4d.shared::cluster.global.mbarrier::complete_tx::bytes"
+                    " [%0], [%1, {%3, %4, %5, %6}], [%2];"
+                    :
+                    : "r"(sa_addr + (t * 3 + pl) * p.a_plane), "l"(reinterpret_cast<uint64_t>(&maps.a[src][pl])),
+                      "r"(a_full(stage)), "r"(cb * HL_KC), "r"(x0s[t]), "r"(y0s[t]), "r"(b0s[t])
+                    : "memory");
+              }
           }
           if (!RESIDENT) {
             for (int tap = 0; tap < taps; ++tap) {
@@ -284,10 +320,15 @@ __global__ void __launch_bounds__(HL_THREADS, 1) conv_moments_halo_kernel(const 
       constexpr uint32_t SLOT16 = B_SLOT >> 4, BPLANE16 = B_PLANE >> 4;
       int a_stage_i = 0, b_slot_i = 0;
       uint32_t a_par = 0, b_par = 0;
-      for (int tile = blockIdx.x, titer = 0; tile < p.total_tiles; tile += gridDim.x, ++titer) {
+      const int n_units = G == 1 ? p.total_tiles : p.total_groups;
+      for (int tile = blockIdx.x, uiter = 0; tile < n_units; tile += gridDim.x, ++uiter) {
+        // unit = one tile (G = 1, accumulator stage alternates) or a pair of tiles (G = 2, stage = tile of the pair)
+        const int titer = uiter * G;
+#pragma unroll
+        for (int t = 0; t < G; ++t)
+          ptx::mbar_wait(acc_empty((titer + t) & 1), (((uint32_t)(titer + t) >> 1) & 1u) ^ 1u);
         const int as = titer & 1;
-        ptx::mbar_wait(acc_empty(as), (((uint32_t)titer >> 1) & 1u) ^ 1u);
-        const uint32_t acc_mu = tmem_base + as * ACC_STAGE, acc_var = acc_mu + (CONCAT ? 2 * NT : NT);
+        const uint32_t acc_mu0 = tmem_base + as * ACC_STAGE;
         for (int cbt = 0; cbt < cblk; ++cbt) {
           ptx::mbar_wait(a_full(a_stage_i), a_par);
           if (RESIDENT && titer == 0) {
@@ -310,21 +351,27 @@ __global__ void __launch_bounds__(HL_THREADS, 1) conv_moments_halo_kernel(const 
               if (++b_slot_i == p.sb) { b_slot_i = 0; b_par ^= 1u; }
               b0 = b_st + (uint32_t)slot * SLOT16;
             }
-            const uint32_t a0 = a_st + (uint32_t)kh * row_shift16 + (uint32_t)kw * 4u;   // tap = row offset in the halo
+            const uint32_t a00 = a_st + (uint32_t)kh * row_shift16 + (uint32_t)kw * 4u;  // tap = row offset in the halo
             if (leader) {
 #pragma unroll
-              for (int ks = 0; ks < HL_KC / 16; ++ks) {
-                const uint32_t k16 = ks * 2;                          // 16 bf16 = 32 B along K
-                const uint32_t acc = (cbt > 0 || tap > 0 || ks > 0) ? 1u : 0u;
-                if constexpr (CONCAT) {
-                  ptx::umma_bf16(acc_mu, desc(a0 + k16), desc(b0 + k16), idesc_2n, acc);                 // hi x [Whi;Wlo]
-                  ptx::umma_bf16(acc_mu, desc(a0 + plane16 + k16), desc(b0 + k16), idesc_n, 1u);        // lo x Whi
-                } else {
-                  ptx::umma_bf16(acc_mu, desc(a0 + k16), desc(b0 + k16), idesc_n, acc);
-                  ptx::umma_bf16(acc_mu, desc(a0 + plane16 + k16), desc(b0 + k16), idesc_n, 1u);
-                  ptx::umma_bf16(acc_mu, desc(a0 + k16), desc(b0 + BPLANE16 + k16), idesc_n, 1u);
+              for (int t = 0; t < G; ++t) {
+                const uint32_t a0 = a00 + (uint32_t)t * 3u * plane16;             // tile t of the pair
+                const uint32_t acc_mu = G == 1 ? acc_mu0 : tmem_base + (uint32_t)t * ACC_STAGE;
+                const uint32_t acc_var = acc_mu + (CONCAT ? 2 * NT : NT);
+#pragma unroll
+                for (int ks = 0; ks < HL_KC / 16; ++ks) {
+                  const uint32_t k16 = ks * 2;                          // 16 bf16 = 32 B along K
+                  const uint32_t acc = (cbt > 0 || tap > 0 || ks > 0) ? 1u : 0u;
+                  if constexpr (CONCAT) {
+                    ptx::umma_bf16(acc_mu, desc(a0 + k16), desc(b0 + k16), idesc_2n, acc);               // hi x [Whi;Wlo]
+                    ptx::umma_bf16(acc_mu, desc(a0 + plane16 + k16), desc(b0 + k16), idesc_n, 1u);      // lo x Whi
+                  } else {
+                    ptx::umma_bf16(acc_mu, desc(a0 + k16), desc(b0 + k16), idesc_n, acc);
+                    ptx::umma_bf16(acc_mu, desc(a0 + plane16 + k16), desc(b0 + k16), idesc_n, 1u);
+                    ptx::umma_bf16(acc_mu, desc(a0 + k16), desc(b0 + BPLANE16 + k16), idesc_n, 1u);
+                  }
+                  ptx::umma_bf16(acc_var, desc(a0 + 2 * plane16 + k16), desc(b0 + 2 * BPLANE16 + k16), idesc_n, acc);
                 }
-                ptx::umma_bf16(acc_var, desc(a0 + 2 * plane16 + k16), desc(b0 + 2 * BPLANE16 + k16), idesc_n, acc);
               }
               if (!RESIDENT) ptx::umma_commit(b_empty(slot));
             }
@@ -332,7 +379,10 @@ __global__ void __launch_bounds__(HL_THREADS, 1) conv_moments_halo_kernel(const 
           if (leader) ptx::umma_commit(a_empty(a_stage_i));
           if (++a_stage_i == p.sa) { a_stage_i = 0; a_par ^= 1u; }
         }
-        if (leader) ptx::umma_commit(acc_full(as));
+        if (leader) {
+#pragma unroll
+          for (int t = 0; t < G; ++t) ptx::umma_commit(acc_full((titer + t) & 1));
+        }
       }
     }
   } else {
@@ -344,8 +394,11 @@ __global__ void __launch_bounds__(HL_THREADS, 1) conv_moments_halo_kernel(const 
       const int row = (warp - 2) * 32 + lane;
       int a_stage_i = 0;
       uint32_t a_par = 0;
-      for (int tile = blockIdx.x, titer = 0; tile < p.total_tiles; tile += gridDim.x, ++titer) {
-        float qa = 0.f, qb = 0.f, qc = 0.f, qd = 0.f;         // four chains for ILP
+      const int n_units = G == 1 ? p.total_tiles : p.total_groups;
+      for (int tile = blockIdx.x, uiter = 0; tile < n_units; tile += gridDim.x, ++uiter) {
+        float qsum[G];
+#pragma unroll
+        for (int t = 0; t < G; ++t) qsum[t] = 0.f;
         int src = 0, cb = 0;
         for (int cbt = 0; cbt < cblk; ++cbt, ++cb) {
           if constexpr (DGRAD) {
@@ -353,7 +406,10 @@ __global__ void __launch_bounds__(HL_THREADS, 1) conv_moments_halo_kernel(const 
           }
           ptx::mbar_wait(a_full(a_stage_i), a_par);
           if (row < p.rows_box) {
-            const uint8_t* ar = smem_gen + a_stage_i * a_stage + row * 64;
+#pragma unroll
+           for (int t = 0; t < G; ++t) {
+            float qa = 0.f, qb = 0.f, qc = 0.f, qd = 0.f;         // four chains for ILP
+            const uint8_t* ar = smem_gen + a_stage_i * a_stage + t * 3 * p.a_plane + row * 64;
 #pragma unroll
             for (int j = 0; j < 4; ++j) {
               const int ch = ((j + (row >> 1)) & 3) * 16;   // chunk rotation: conflict-free, order-insensitive sum
@@ -384,16 +440,22 @@ __global__ void __launch_bounds__(HL_THREADS, 1) conv_moments_halo_kernel(const 
                 }
               }
             }
+            qsum[t] += (qa + qb) + (qc + qd);
+           }
           }
           __syncwarp();
           if (lane == 0) ptx::mbar_arrive(a_empty(a_stage_i));
           if (++a_stage_i == p.sa) { a_stage_i = 0; a_par ^= 1u; }
         }
-        const int qs = titer & 1;
-        ptx::mbar_wait(q_empty(qs), (((uint32_t)titer >> 1) & 1u) ^ 1u);
-        qbuf[qs * 256 + row] = (qa + qb) + (qc + qd);        // rows >= rows_box hold 0
-        __syncwarp();
-        if (lane == 0) ptx::mbar_arrive(q_full(qs));
+#pragma unroll
+        for (int t = 0; t < G; ++t) {
+          const int titer = uiter * G + t;
+          const int qs = titer & 1;
+          ptx::mbar_wait(q_empty(qs), (((uint32_t)titer >> 1) & 1u) ^ 1u);
+          qbuf[qs * 256 + row] = qsum[t];                      // rows >= rows_box hold 0
+          __syncwarp();
+          if (lane == 0) ptx::mbar_arrive(q_full(qs));
+        }
       }
     } else {
       // ===================== epilogue (warps 10-17) =====================
@@ -407,7 +469,17 @@ __global__ void __launch_bounds__(HL_THREADS, 1) conv_moments_halo_kernel(const 
       const int n = yy / p.THb;
       TileIt it;
       it.init(blockIdx.x, gridDim.x, p);
-      for (int tile = blockIdx.x, titer = 0; tile < p.total_tiles; tile += gridDim.x, ++titer, it.next(p)) {
+      // G = 2: the "tiles" of this CTA are the halves of its tile pairs, in order (stage = half of the pair)
+      const int n_tiles_cta = G == 1 ? (p.total_tiles > (int)blockIdx.x ? (p.total_tiles - 1 - (int)blockIdx.x) / (int)gridDim.x + 1 : 0)
+                                     : 2 * (p.total_groups > (int)blockIdx.x ? (p.total_groups - 1 - (int)blockIdx.x) / (int)gridDim.x + 1 : 0);
+      for (int titer = 0; titer < n_tiles_cta; ++titer) {
+        TileCoord tc;
+        if constexpr (G == 1) {
+          tc.nt = it.nt; tc.tx = it.tx; tc.ty = it.ty; tc.tb = it.tb; tc.store = true;
+          it.next(p);
+        } else {
+          tc = decode_group_tile((int)blockIdx.x + (titer >> 1) * (int)gridDim.x, titer & 1, p);
+        }
         const int as = titer & 1;
         const uint32_t par = ((uint32_t)titer >> 1) & 1u;
         ptx::mbar_wait(q_full(as), par);
@@ -427,10 +499,10 @@ __global__ void __launch_bounds__(HL_THREADS, 1) conv_moments_halo_kernel(const 
         if (lane == 0) ptx::mbar_arrive(q_empty(as));
 
         // ---- tile coordinates
-        const int nt_i = it.nt, tx = it.tx, ty = it.ty, tb = it.tb;
+        const int nt_i = tc.nt, tx = tc.tx, ty = tc.ty, tb = tc.tb;
         const int gcol0 = nt_i * NT + half * NH;               // first column (parity group, channel) of this warp
         const int ox_i = tx * p.TWo + x, oy_i = ty * p.THo + y, ob = tb * p.TN + n;
-        const bool valid = x < p.TWo && y < p.THo && n < p.TN && ox_i < p.Wo && oy_i < p.Ho && ob < p.B;
+        const bool valid = tc.store && x < p.TWo && y < p.THo && n < p.TN && ox_i < p.Wo && oy_i < p.Ho && ob < p.B;
         if (!DGRAD && p.r_out != nullptr && half == 0 && nt_i == 0 && valid)
           p.r_out[((size_t)ob * p.Ho + oy_i) * p.Wo + ox_i] = r;
         ptx::mbar_wait(acc_full(as), par);
@@ -699,16 +771,17 @@ static int hl_make_weight_map(CUtensorMap* out, const void* w_packed, int taps, 
   return SN_OK;
 }
 
-template <int NT, int KS, bool RESIDENT, bool DGRAD>
+template <int NT, int KS, bool RESIDENT, bool DGRAD, int G = 1>
 static int hl_launch3(const HlMaps& maps, const HlP& p, cudaStream_t st) {
   static std::once_flag once;
   static cudaError_t attr_err = cudaSuccess;
   std::call_once(once, [] {
-    attr_err = cudaFuncSetAttribute(conv_moments_halo_kernel<NT, KS, RESIDENT, DGRAD>,
+    attr_err = cudaFuncSetAttribute(conv_moments_halo_kernel<NT, KS, RESIDENT, DGRAD, G>,
                                     cudaFuncAttributeMaxDynamicSharedMemorySize, HL_SMEM);
   });
   if (attr_err != cudaSuccess) return fail(SN_ERR_LAUNCH, "conv_halo: cannot reserve %d B of shared memory", HL_SMEM);
-  int grid = p.total_tiles < num_sms() ? p.total_tiles : num_sms();
+  const int units = G == 1 ? p.total_tiles : p.total_groups;
+  int grid = units < num_sms() ? units : num_sms();
   static const bool pdl = [] {
     const char* e = getenv("SN_PDL");
     return e == nullptr || e[0] != '0';
@@ -723,13 +796,17 @@ static int hl_launch3(const HlMaps& maps, const HlP& p, cudaStream_t st) {
   attr[0].val.programmaticStreamSerializationAllowed = 1;
   cfg.attrs = attr;
   cfg.numAttrs = pdl ? 1 : 0;
-  cudaError_t e = cudaLaunchKernelEx(&cfg, conv_moments_halo_kernel<NT, KS, RESIDENT, DGRAD>, maps, p);
+  cudaError_t e = cudaLaunchKernelEx(&cfg, conv_moments_halo_kernel<NT, KS, RESIDENT, DGRAD, G>, maps, p);
   if (e != cudaSuccess) return fail(SN_ERR_LAUNCH, "conv_halo launch: %s", cudaGetErrorString(e));
   return check_launch(DGRAD ? "conv_moments_halo_dgrad" : "conv_moments_halo");
 }
 
 template <int NT>
 static int hl_launch(const HlMaps& maps, const HlP& p, cudaStream_t st) {
+  if (p.total_groups > 0) {            // two pixel tiles per weight slot (streamed weights, k = 3 or 1)
+    if (p.ksize == 3) return hl_launch3<NT, 3, false, false, 2>(maps, p, st);
+    if (p.ksize == 1) return hl_launch3<NT, 1, false, false, 2>(maps, p, st);
+  }
   switch (p.ksize * 2 + (p.b_resident ? 1 : 0)) {
     case 2: return hl_launch3<NT, 1, false, false>(maps, p, st);
     case 3: return hl_launch3<NT, 1, true, false>(maps, p, st);
@@ -744,6 +821,10 @@ static int hl_launch(const HlMaps& maps, const HlP& p, cudaStream_t st) {
 // output parities become four K-concatenated sources).
 template <int NT>
 static int hl_launch_dgrad(const HlMaps& maps, const HlP& p, cudaStream_t st) {
+  if (p.total_groups > 0) {
+    if (p.ksize == 3) return hl_launch3<NT, 3, false, true, 2>(maps, p, st);
+    if (p.ksize == 1) return hl_launch3<NT, 1, false, true, 2>(maps, p, st);
+  }
   switch (p.ksize * 2 + (p.b_resident ? 1 : 0)) {
     case 2: return hl_launch3<NT, 1, false, true>(maps, p, st);
     case 3: return hl_launch3<NT, 1, true, true>(maps, p, st);
@@ -791,6 +872,27 @@ static int hl_plan(HlP& p, const HaloTiling& t, int keff, int ncols, int nt, int
     SN_REQUIRE(p.sb >= 2, SN_ERR_UNSUPPORTED, "conv_halo: shared memory plan failed");
   }
   if (p.sa > HL_MAX_ASTAGES) p.sa = HL_MAX_ASTAGES;
+  // streamed weights: let every weight slot serve two pixel tiles (G = 2) when there are enough tile pairs to keep
+  // every SM busy and the doubled A stages still leave >= 3 weight slots
+  p.pix_tiles = p.tiles_x * p.tiles_y * p.tiles_b;
+  p.total_groups = 0;
+  static const bool dual = [] {
+    const char* e = getenv("SN_DUAL");
+    return e == nullptr || e[0] != '0';
+  }();
+  // (measured at batch 64: +11 % on the 64-column layers conv3 / up3_conv1, whose UMMA pipe idled waiting for weights;
+  //  -10..25 % on the 128-column layers, where the pair's two epilogues can no longer hide behind the next tile's
+  //  UMMAs -- so only N tiles of 64 columns use it)
+  if (dual && nt == 64 && !p.b_resident && (keff == 3 || keff == 1)) {
+    const long long groups = (long long)p.tiles_n * ((p.pix_tiles + 1) / 2);
+    const int a_stage2 = 2 * a_stage;
+    const int sb2 = (avail - 2 * a_stage2) / b_slot;
+    if (groups >= num_sms() && sb2 >= 3) {
+      p.total_groups = (int)groups;
+      p.sa = 2;
+      p.sb = sb2 > HL_MAX_BSLOTS ? HL_MAX_BSLOTS : sb2;
+    }
+  }
   return SN_OK;
 }
 
