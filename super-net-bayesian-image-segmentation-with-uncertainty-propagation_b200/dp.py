@@ -161,25 +161,52 @@ class DataParallelTrainer:
     def step(self, x_local: Tensor, y_local: Tensor, global_batch: int) -> Tensor:
         params = [p for p in self.model.parameters() if p.requires_grad]
         self.opt.zero_grad(set_to_none=True)
-        if x_local.shape[0] > 0 and getattr(self.model, "mode", "fp32") == "fast":
-            loss = self._fast_backward(x_local, y_local)
-        elif x_local.shape[0] > 0:
-            loss = self.model.elbo_loss(x_local, y_local, self.kl_factor)
-            loss.backward()
-        else:                       # an empty shard still takes part in the collective
-            loss = torch.zeros((), device=params[0].device)
-            for p in params:
-                p.grad = torch.zeros_like(p)
-        if self._engine is not None and x_local.shape[0] > 0 and getattr(self.model, "mode", "fp32") == "fast":
-            allreduce_flat_(self._engine.flat_grad, x_local.shape[0], global_batch, self.group)
+        n_local = x_local.shape[0]
+        if getattr(self.model, "mode", "fp32") == "fast":
+            # ONE collective sequence for every rank of a fast-mode job: fixed-size slices of a flat buffer in
+            # parameter order.  A rank whose shard is empty (global_batch < world * ceil-split) contributes a zeroed
+            # buffer of the same size, so the number and sizes of the all_reduce calls match across ranks.
+            if n_local > 0:
+                loss = self._fast_backward(x_local, y_local)
+                flat = self._engine.flat_grad
+            else:
+                loss = torch.zeros((), device=params[0].device)
+                flat = self._zero_flat_grad()
+            allreduce_flat_(flat, n_local, global_batch, self.group)
         else:
-            allreduce_gradients(params, x_local.shape[0], global_batch, self.group)
+            if n_local > 0:
+                loss = self.model.elbo_loss(x_local, y_local, self.kl_factor)
+                loss.backward()
+            else:                       # an empty shard still takes part in the collective
+                loss = torch.zeros((), device=params[0].device)
+                for p in params:
+                    p.grad = torch.zeros_like(p)
+            allreduce_gradients(params, n_local, global_batch, self.group)
         clip_by_norm_per_variable_(params, self.clipnorm)
         self.opt.step()
         # engines re-derive their bf16 tensor-core operands when they see a new version (the training engine does it
         # inside its captured graph on every step)
         self.model._weights_version = getattr(self.model, "_weights_version", 0) + 1
         return loss.detach()
+
+    _empty_flat = None
+
+    def _zero_flat_grad(self) -> Tensor:
+        """Zeroed flat gradient in the engine's parameter order (w_mu, w_sigma per layer of model.conv_names), with
+        every p.grad a view of it: what an empty shard feeds the all-reduce."""
+        m = self.model
+        pairs = [getattr(m, name).weights() for name in m.conv_names]
+        total = sum(w.numel() + ws.numel() for w, ws in pairs)
+        if self._empty_flat is None or self._empty_flat.numel() != total:
+            self._empty_flat = torch.zeros(total, device=pairs[0][0].device, dtype=torch.float32)
+        flat = self._empty_flat.zero_()
+        off = 0
+        for w, ws in pairs:
+            w.grad = flat[off:off + w.numel()].view_as(w)
+            off += w.numel()
+            ws.grad = flat[off:off + ws.numel()].view_as(ws)
+            off += ws.numel()
+        return flat
 
     _engine = None
 

@@ -86,12 +86,18 @@ class InferenceEngine:
                 continue
             w, ws = getattr(m, name).weights()
             F.prepare_weights(w, ws, upconv=name.endswith("conv2x2"), out=self.prepared[name])
-        self._weights_version = getattr(m, "_weights_version", 0)
+        self._weights_version = self._weights_stamp()
+
+    def _weights_stamp(self):
+        """Changes whenever any conv weight is written in place -- optimizer.step(), load_state_dict(),
+        layer.set_weights(), load_weight_dict(): torch bumps Tensor._version on every in-place write, so the stamp
+        is derived from the parameters themselves, not from callers remembering to bump a counter."""
+        m = self.model
+        return (getattr(m, "_weights_version", 0),) + tuple(p._version for c in m.convs() for p in c.weights())
 
     def sync_weights(self) -> None:
-        """Refresh the operands if the model's weights changed since they were derived (trainers bump
-        model._weights_version after every optimiser step)."""
-        if self._weights_version != getattr(self.model, "_weights_version", 0):
+        """Refresh the derived operands (bf16 splits, W^2, softplus) if any weight changed since they were made."""
+        if self._weights_version != self._weights_stamp():
             self.refresh_weights()
 
     def _build(self) -> None:
@@ -104,7 +110,7 @@ class InferenceEngine:
         if not all(c.built for c in m.convs()):
             m.build_with_input(Cin, dev)
         self._prepare_weights()
-        self._weights_version = getattr(m, "_weights_version", 0)
+        self._weights_version = self._weights_stamp()
         steps = self._steps
         self.skip_window = {}
         self.x_in = torch.empty(self.shape, device=dev, dtype=torch.float32)
@@ -559,6 +565,7 @@ class StreamingPipeline:
             self.done[slot].synchronize()        # the slot's previous outputs must have landed before reuse
         eng, st = self.engines[slot], self.streams[slot]
         with torch.cuda.stream(st):
+            eng.sync_weights()                   # operands follow in-place weight updates (every engine has its own)
             eng.x_in.copy_(x_host, non_blocking=True)
             p, v = eng.forward_resident()
             self.p_host[slot].copy_(p, non_blocking=True)

@@ -137,3 +137,86 @@ def test_metrics_and_batch_feeding_stay_on_the_device(S):
         for k, v in rep_gpu[region].items():
             a, b = v, rep_cpu[region][k]
             assert (np.isnan(a) and np.isnan(b)) or abs(a - b) < 1e-12
+
+
+# ------------------------------------------------------------------------------------------------------------
+# BASELINE.json configs[2] at BraTS shapes: testing()'s noise sweep and the targeted PGD loop through mode='fast'
+# ------------------------------------------------------------------------------------------------------------
+def _brats_pair(S, C=4):
+    oracle = O.UNetOracle("brats", 32, C, 4, torch.float64)
+    w32 = O.make_weights("brats", 32, C, 4)
+    model = S.Density_prop_with_pad_UNET(32, C, variant="brats", mode="fast").load_weight_dict(w32, device="cuda")
+    return oracle, model
+
+
+def test_brats_noise_sweep_fast_mode(S):
+    """testing() at BraTS shapes (Brats.py:1530: gaussain_noise_std in {0.005, 0.01}; :1542-1551 noise_on in
+    {'B', 'O', all}; noise masked with the labels :1257-1276, clipped to the clean range :1276) through mode='fast',
+    every noisy batch against the fp64 oracle at the north-star bars.  Input and noise carry the alpha scale of
+    SURVEY.md 8d (the mean path is degree-1 homogeneous)."""
+    from supernet_b200 import robustness as R
+    oracle, model = _brats_pair(S)
+    a = O.BRATS_ALPHA
+    x = O.make_input("brats", 1, alpha=a)
+    g = torch.Generator().manual_seed(11)
+    labels = torch.randint(0, 4, (1, 204, 204), generator=g)
+    cases = [(0.0, "all")] + [(s, w) for s in (0.005, 0.01) for w in ("B", "O", "all")]
+    for std, where in cases:
+        xn = R.apply_noise(x, labels, R.make_noise(x, "gaussian", std * a, g), where) if std > 0 else x
+        p_ref, v_ref, mf_ref, sf_ref = oracle(xn, True)
+        with torch.no_grad():
+            p, v, mf, sf = model(xn.cuda(), return_presoftmax=True)
+        errs = dict(std=std, where=where, p=O.rel_l2(p.cpu(), p_ref), v=O.rel_l2(v.cpu(), v_ref),
+                    pre_mu=O.rel_l2(mf.cpu().reshape(mf_ref.shape), mf_ref),
+                    pre_var=O.rel_l2(sf.cpu().reshape(sf_ref.shape), sf_ref),
+                    argmax=O.argmax_agreement(p.cpu(), p_ref))
+        print(errs)
+        assert errs["p"] < 1e-3 and errs["pre_mu"] < 1e-3, errs
+        assert errs["v"] < 1e-2 and errs["pre_var"] < 1e-2, errs
+        assert errs["argmax"] >= 0.999, errs
+        assert float(v.min()) >= 0.0 and bool(torch.isfinite(v).all())
+        mv, mv_ref = R.mean_predicted_class_variance(p, v), R.mean_predicted_class_variance(p_ref, v_ref)
+        assert abs(mv - mv_ref) < 1e-2 * mv_ref, (mv, mv_ref)
+        if std > 0:
+            assert float(xn.min()) >= float(x.min()) and float(xn.max()) <= float(x.max())
+            assert R.snr_db(x, xn) > 0
+
+
+def test_brats_targeted_pgd_fast_mode(S):
+    """Three steps of the targeted loop (Brats.py:969-983: relabel class -> adv_class, adv_x += step * sign(grad),
+    clip to the eps-ball and to the clean range) at BraTS shapes through the tensor-core gradient chain.  The oracle
+    walks the same trajectory (its own adversarial input is fed to both sides each step), so every step compares one
+    create_adversarial_pattern call (Brats.py:582-596) on identical inputs: the gradient at the 1e-2 bar of SURVEY.md
+    8d and the sign -- what the attack consumes -- at >= 99 % of the significant pixels."""
+    from supernet_b200 import robustness as R
+    oracle, model = _brats_pair(S)
+    a = O.BRATS_ALPHA
+    x = O.make_input("brats", 1, alpha=a)
+    g = torch.Generator().manual_seed(7)
+    labels = torch.randint(0, 4, (1, 186, 186), generator=g)
+    masked = torch.where(labels == 2, torch.full_like(labels, 1), labels)          # Brats.py:972-975
+    y = R.one_hot_flat(masked, 4)
+    eps = 1e-4 * a                                                                  # Brats.py:474, alpha-scaled
+    step = eps / 2
+    lo, hi = x.min(), x.max()
+    adv = x.clone()
+    for it in range(3):
+        g_ref, loss_ref = oracle.fgsm_gradient(adv, y.double())
+        loss, g_fast = model.input_gradient_fast(adv.cuda(), y.cuda())
+        err = O.rel_l2(g_fast.cpu(), g_ref)
+        big = g_ref.abs() > 1e-3 * g_ref.abs().max()
+        agree = float((torch.sign(g_ref)[big] == torch.sign(g_fast.cpu().double())[big]).double().mean())
+        print(dict(step=it, grad_rel=err, sign_agreement=agree, loss=float(loss), loss_ref=float(loss_ref)))
+        assert abs(float(loss) - float(loss_ref)) < 2e-3 * abs(float(loss_ref))
+        assert err < 1e-2 and agree >= 0.99, (it, err, agree)
+        adv = torch.clamp(adv + step * torch.sign(g_ref).float(), x - eps, x + eps)   # Brats.py:981-982
+        adv = torch.minimum(torch.maximum(adv, lo), hi)                              # :983
+    # the driver itself (robustness.pgd_targeted) lands inside the eps-ball and the clean range
+    advp = R.pgd_targeted(model, x.cuda(), labels.cuda(), source_class=2, target_class=1, epsilon=eps, steps=3,
+                          step_size=step)
+    assert float((advp.cpu() - x).abs().max()) <= eps * (1 + 1e-6)
+    assert float(advp.min()) >= float(lo) and float(advp.max()) <= float(hi)
+    # and it follows the oracle's trajectory wherever the signs agree (>= 99 % of the pixels end up identical)
+    same = float(((advp.cpu() - adv).abs() <= 1e-3 * eps).double().mean())
+    print(dict(trajectory_match=same))
+    assert same >= 0.97, same

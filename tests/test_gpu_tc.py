@@ -206,7 +206,7 @@ def test_tc_rejects_bad_arguments(S):
 # ------------------------------------------------------------------------------------------------------------
 # whole-network parity of mode='fast' (north_star bars: mean maps 1e-3, variance maps 1e-2, argmax >= 99.9 %)
 # ------------------------------------------------------------------------------------------------------------
-def _fast_vs_oracle(S, variant, C, in_ch, B, alpha):
+def _fast_vs_oracle(S, variant, C, in_ch, B, alpha, presoftmax_only=False):
     oracle = O.UNetOracle(variant, 32, C, in_ch, torch.float64)
     w32 = O.make_weights(variant, 32, C, in_ch)
     model = S.Density_prop_with_pad_UNET(32, C, variant=variant, mode="fast").load_weight_dict(w32, device="cuda")
@@ -223,9 +223,13 @@ def _fast_vs_oracle(S, variant, C, in_ch, B, alpha):
                 p=rel(p, p_ref), v=rel(v, v_ref), argmax=O.argmax_agreement(p.cpu(), p_ref))
     print(variant, errs)
     assert bool(torch.isfinite(p).all()) and bool(torch.isfinite(v).all()) and float(v.min()) >= 0.0
-    assert errs["pre_mu"] < 1e-3 and errs["p"] < 1e-3, errs
-    assert errs["pre_var"] < 1e-2 and errs["v"] < 1e-2, errs
+    assert bool(torch.isfinite(mf).all()) and bool(torch.isfinite(sf).all()) and float(sf.min()) >= 0.0
+    assert errs["pre_mu"] < 1e-3 and errs["pre_var"] < 1e-2, errs
     assert errs["argmax"] >= 0.999, errs
+    if presoftmax_only:
+        return errs
+    assert errs["p"] < 1e-3 and errs["v"] < 1e-2, errs
+    return errs
 
 
 def test_hippocampus_fast_mode(S):
@@ -235,6 +239,14 @@ def test_hippocampus_fast_mode(S):
 @pytest.mark.parametrize("C", [4, 5])
 def test_brats_fast_mode(S, C):
     _fast_vs_oracle(S, "brats", C, 4, 2, O.BRATS_ALPHA)  # configs[1], alpha-scaled input
+
+
+def test_brats_fast_mode_full_scale_input_vs_oracle(S):
+    """alpha = 1: the mean path is exactly homogeneous under a power-of-two alpha, the variance path is not
+    (the additive sigma_fill border), so this is a different operating point from BRATS_ALPHA.  The softmax saturates
+    there (logits ~1e4: 74 % of the output variances underflow), so the bars are checked on the pre-softmax
+    moments and on the arg-max labels."""
+    _fast_vs_oracle(S, "brats", 4, 4, 2, 1.0, presoftmax_only=True)
 
 
 def test_fast_matches_fp32_mode_at_full_scale_input(S):
@@ -269,3 +281,41 @@ def test_streaming_pipeline_matches_engine(S):
         with torch.no_grad():
             p_ref, v_ref = model(x.cuda())
         assert torch.equal(p, p_ref.cpu()) and torch.equal(v, v_ref.cpu())
+
+
+def test_fast_engines_follow_inplace_weight_updates(S):
+    """a plain torch optimizer.step() / load_state_dict() writes the Parameters in place without telling the
+    model; an existing InferenceEngine (and every engine of a StreamingPipeline) must re-derive its bf16 operands, W^2
+    and softplus(w_sigma) from them, otherwise conv_input / conv_final (live Parameters) and the tensor-core layers
+    (cached operands) silently mix old and new weights."""
+    from supernet_b200.engine import StreamingPipeline
+    w32 = O.make_weights("hippocampus", 32, 3, 1)
+    model = S.Density_prop_with_pad_UNET(32, 3, variant="hippocampus", mode="fast").load_weight_dict(w32, device="cuda")
+    x = O.make_input("hippocampus", 2)
+    pipe = StreamingPipeline(model, 2, 64, 64, 1, "cuda", depth=2)
+    with torch.no_grad():
+        p0, v0 = model(x.cuda())
+    opt = torch.optim.SGD(model.parameters(), lr=0.05)
+    g = torch.Generator().manual_seed(3)
+    for p_ in model.parameters():
+        p_.grad = torch.randn(p_.shape, generator=g).cuda() * p_.detach().abs().mean()
+    opt.step()                                                   # in-place update, no version counter bumped by hand
+    with torch.no_grad():
+        p1, v1 = model(x.cuda())                                 # same engine, same captured graph
+    fresh = S.Density_prop_with_pad_UNET(32, 3, variant="hippocampus", mode="fast")
+    fresh.build_with_input(1, "cuda")
+    fresh.load_state_dict(model.state_dict())
+    with torch.no_grad():
+        p2, v2 = fresh(x.cuda())
+    assert not torch.equal(p0, p1)
+    assert torch.equal(p1, p2) and torch.equal(v1, v2)
+    xh = x.pin_memory()
+    for _ in range(2):                                           # both engines of the pipeline
+        ph, vh = pipe.result(pipe.submit(xh))
+        assert torch.equal(ph, p2.cpu()) and torch.equal(vh, v2.cpu())
+    # load_state_dict into the live model: back to the original weights, same engine
+    orig = S.Density_prop_with_pad_UNET(32, 3, variant="hippocampus", mode="fp32").load_weight_dict(w32, device="cuda")
+    model.load_state_dict(orig.state_dict())
+    with torch.no_grad():
+        p3, v3 = model(x.cuda())
+    assert torch.equal(p3, p0) and torch.equal(v3, v0)

@@ -167,6 +167,86 @@ def test_gradient_allreduce_two_gloo_ranks():
     assert out[0] and out[1]
 
 
+class _StubConv:
+    def __init__(self, w, ws):
+        self.w, self.ws = w, ws
+
+    def weights(self):
+        return self.w, self.ws
+
+
+class _StubFastModel(torch.nn.Module):
+    """mode='fast' stand-in with the model surface DataParallelTrainer touches (conv_names, layer.weights())."""
+    mode = "fast"
+    conv_names = ["a", "b"]
+
+    def __init__(self):
+        super().__init__()
+        g = torch.Generator().manual_seed(5)
+        self.wa = torch.nn.Parameter(torch.randn(6, 5, generator=g))
+        self.sa = torch.nn.Parameter(torch.randn(5, generator=g))
+        self.wb = torch.nn.Parameter(torch.randn(5, 3, generator=g))
+        self.sb = torch.nn.Parameter(torch.randn(3, generator=g))
+        self.a, self.b = _StubConv(self.wa, self.sa), _StubConv(self.wb, self.sb)
+
+    def loss(self, x, y):
+        h = torch.relu(x @ self.wa) * torch.nn.functional.softplus(self.sa)
+        return ((h @ self.wb + self.sb - y) ** 2).mean()
+
+
+def _dp_empty_shard_worker(rank, world, port, out):
+    """global batch 1 on 2 ranks -> rank 1's shard is empty.  Both ranks must issue the SAME collective
+    sequence in fast mode (fixed slices of one flat buffer); gloo fails or hangs on a mismatch."""
+    sys.path.insert(0, ROOT)
+    import types
+    from supernet_b200 import dp
+    os.environ["MASTER_ADDR"] = "127.0.0.1"
+    os.environ["MASTER_PORT"] = str(port)
+    dist.init_process_group("gloo", rank=rank, world_size=world, timeout=__import__("datetime").timedelta(seconds=60))
+    model = _StubFastModel()
+    g = torch.Generator().manual_seed(9)
+    x, y = torch.randn(1, 6, generator=g), torch.randn(1, 3, generator=g)
+    trainer = dp.DataParallelTrainer(model, lr=1e-2, kl_factor=0.0)
+    calls = []
+
+    def fake_fast_backward(xs, ys):           # what GradientEngine does: gradients are views of ONE flat buffer
+        params = [model.wa, model.sa, model.wb, model.sb]
+        flat = torch.zeros(sum(p.numel() for p in params))
+        off = 0
+        loss = model.loss(xs, ys)
+        for p, g_ in zip(params, torch.autograd.grad(loss, params)):
+            flat[off:off + p.numel()].copy_(g_.reshape(-1))
+            p.grad = flat[off:off + p.numel()].view_as(p)
+            off += p.numel()
+        trainer._engine = types.SimpleNamespace(flat_grad=flat)
+        calls.append(xs.shape[0])
+        return loss.detach()
+
+    trainer._fast_backward = fake_fast_backward
+    ref = _StubFastModel()
+    ref_opt = dp.make_adam(ref.parameters(), lr=1e-2)
+    ok = True
+    for _ in range(2):
+        a, b = dp.shard_bounds(1, world, rank)
+        trainer.step(x[a:b], y[a:b], global_batch=1)
+        ref_opt.zero_grad()
+        ref.loss(x, y).backward()
+        dp.clip_by_norm_per_variable_(list(ref.parameters()), 1.0)
+        ref_opt.step()
+        ok = ok and all(torch.allclose(p, q, atol=1e-6) for p, q in zip(model.parameters(), ref.parameters()))
+    ok = ok and len(calls) == (2 if rank == 0 else 0)
+    out[rank] = ok
+    dist.destroy_process_group()
+
+
+def test_fast_mode_empty_shard_issues_the_same_collectives():
+    mgr = mp.Manager()
+    out = mgr.dict()
+    port = _free_port()
+    mp.spawn(_dp_empty_shard_worker, args=(2, port, out), nprocs=2, join=True)
+    assert out[0] and out[1]
+
+
 def test_noise_drivers_match_reference_semantics():
     """apply_noise / snr / salt_and_pepper against a numpy restatement of Brats.py:1247-1283."""
     import numpy as np
