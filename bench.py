@@ -158,35 +158,78 @@ def cpu_baseline(seconds_budget: float = 15.0, form: str = "as_written"):
                       f"conv2d + extract_patches + 3 matmuls per layer)"}
 
 
-def aux_backward(model, B, dev, steps=10):
-    """Side measurements, not the headline (BASELINE.json configs[2] and [3]): the FAST-mode FGSM chain
-    (create_adversarial_pattern, Brats.py:582-596: forward + 0.5 NLL + input gradient) and the training chain
-    (train_on_batch, Brats.py:569-580: forward + NLL + data and weight gradients; optimiser excluded) on the tensor
-    cores, batch resident, CUDA-graph replay, CUDA events."""
+def aux_backward(model, B, dev, world=1, rank=0, steps=10, warmup=3):
+    """Side measurements, not the headline (BASELINE.json configs[2] and [3]), batch B per GPU on every rank:
+      fgsm   the FAST-mode create_adversarial_pattern chain (Brats.py:582-596: forward + 0.5 NLL + input gradient),
+             batch resident, CUDA-graph replay, no collective (slices are independent);
+      train  train_on_batch (Brats.py:569-580) through dp.DataParallelTrainer.step: forward + NLL + data and weight
+             gradients + regularisers (one CUDA graph), the NCCL all-reduce of the flat 31 MB gradient over all ranks,
+             per-variable clipnorm and Adam.  After the timed steps the replicas' weights are compared.
+    Timed with CUDA events between barriers, max over ranks; slices/s are whole-job."""
+    import torch.distributed as dist
     from oracle import supernet_oracle as O
+    from supernet_b200 import dp
     from supernet_b200.engine import GradientEngine
-    res = {"batch": B, "note": "resident batch, one CUDA graph per chain, single GPU"}
-    for key, train in (("fgsm", False), ("train", True)):
-        eng = GradientEngine(model, B, IN_HW, IN_HW, IN_CH, dev, graph=True, train=train)
-        if train:
-            eng._loss_scale, eng._clip = 1.0, (1e-12, 1e3)
-        eng.x_in.copy_(O.make_input("brats", B, alpha=O.BRATS_ALPHA))
-        eng.y_in.copy_(O.make_labels(B, OUT_HW * OUT_HW, N_LABELS))
-        for _ in range(3):
-            eng.loss_and_input_gradient_resident()
+
+    def barrier():
         torch.cuda.synchronize()
+        if world > 1:
+            dist.barrier()
+            torch.cuda.synchronize()
+
+    def timed(fn):
+        for _ in range(warmup):
+            fn()
+        barrier()
         a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
         a.record()
         for _ in range(steps):
-            eng.loss_and_input_gradient_resident()
+            fn()
         b.record()
-        torch.cuda.synchronize()
-        ms = a.elapsed_time(b) / steps
-        res[key] = {"ms_per_step": round(ms, 3), "slices_per_s": round(B / ms * 1e3, 1),
+        barrier()
+        ms = a.elapsed_time(b)
+        if world > 1:
+            t = torch.tensor([ms], device=dev, dtype=torch.float64)
+            dist.all_reduce(t, op=dist.ReduceOp.MAX)
+            ms = float(t)
+        return ms / steps
+
+    res = {"batch_per_gpu": B, "n_gpus": world,
+           "note": "CUDA events between barriers, max over ranks; whole-job slices/s"}
+    x = O.make_input("brats", B, seed=2025 + rank, alpha=O.BRATS_ALPHA).to(dev)
+    y = O.make_labels(B, OUT_HW * OUT_HW, N_LABELS, seed=7 + rank).to(dev)
+    # ---- FGSM chain ------------------------------------------------------------------------------------------
+    eng = GradientEngine(model, B, IN_HW, IN_HW, IN_CH, dev, graph=True, train=False)
+    eng.x_in.copy_(x)
+    eng.y_in.copy_(y)
+    ms = timed(eng.loss_and_input_gradient_resident)
+    res["fgsm"] = {"ms_per_step": round(ms, 3), "slices_per_s": round(world * B / ms * 1e3, 1),
+                   "launches_per_step": len(eng.step_names) + 2 + len(eng._bwd_steps),
+                   "algorithmic_gflop_per_slice": 40.4, "collective": None}
+    del eng
+    torch.cuda.empty_cache()
+    # ---- training step ---------------------------------------------------------------------------------------
+    trainer = dp.DataParallelTrainer(model, lr=1e-4, kl_factor=1e-5)
+    ms = timed(lambda: trainer.step(x, y, global_batch=B * world))
+    eng = trainer._engine
+    res["train"] = {"ms_per_step": round(ms, 3), "slices_per_s": round(world * B / ms * 1e3, 1),
                     "launches_per_step": len(eng.step_names) + 2 + len(eng._bwd_steps),
-                    "algorithmic_gflop_per_slice": round((2 if not train else 3) * 20.19, 1)}
-        del eng
-        torch.cuda.empty_cache()
+                    "algorithmic_gflop_per_slice": 60.6,
+                    "includes": "gradient all-reduce (NCCL), per-variable clipnorm, Adam",
+                    "collective": (f"all_reduce(sum) of the flat fp32 gradient, {eng.flat_grad.numel() * 4} B, "
+                                   f"{world} ranks") if world > 1 else None}
+    if world == 1:      # the chain alone (no optimiser), comparable with the round-1 figure
+        res["train"]["chain_only_ms"] = round(timed(eng.loss_and_input_gradient_resident), 3)
+    # replicas in sync: every rank holds bit-identical weights after the sharded steps
+    chk = torch.stack([p.detach().double().sum() for p in model.parameters()]).sum().reshape(1)
+    if world > 1:
+        lo, hi = chk.clone(), chk.clone()
+        dist.all_reduce(lo, op=dist.ReduceOp.MIN)
+        dist.all_reduce(hi, op=dist.ReduceOp.MAX)
+        res["train"]["replicas_in_sync"] = bool(float(lo) == float(hi))
+    res["train"]["finite"] = bool(torch.isfinite(chk).all())
+    del trainer, eng
+    torch.cuda.empty_cache()
     return res
 
 
@@ -383,6 +426,11 @@ def main():
                     "peak_source": f"{pk['source']} bf16 sustained", "share_of_step": round(tc_ms / sum(per), 3),
                     "algorithmic_gflop_per_slice": round(flops_slice / 1e9, 3)}
 
+    # ---- FGSM / training side measurements: every rank takes part (the training step all-reduces over NCCL) ----
+    aux = None
+    if args.mode == "fast" and not args.no_aux:
+        aux = aux_backward(model, B, dev, world, rank)
+
     if rank == 0:
         out = {
             "metric": METRIC, "value": round(value, 1), "unit": UNIT, "n_gpus": world, "steps": args.steps,
@@ -407,8 +455,8 @@ def main():
         if roofline:
             out["roofline"] = roofline
             out["kernels"] = kernels
-        if args.mode == "fast" and world == 1 and not args.no_aux:
-            out["aux"] = aux_backward(model, B, dev)
+        if aux is not None:
+            out["aux"] = aux
         if not args.no_cpu_baseline and world == 1:
             out["cpu_baseline"] = cpu_baseline()
         print(json.dumps(out))

@@ -174,7 +174,8 @@ size_t sn_prepared_weight_bytes(int32_t ksize, int32_t cin, int32_t cout);
 int sn_prepare_weights(const float* w_mu, const float* w_sigma, int32_t ksize, int32_t cin, int32_t cout,
                        int32_t upconv, void* w_packed, float* s_out, sn_stream_t st);
 
-enum { SN_TC_RELU = 1, SN_TC_UPCONV = 2, SN_TC_DST_F32 = 4, SN_TC_IM2COL = 8, SN_TC_ROWS = 16, SN_TC_EXACT = 32 };
+enum { SN_TC_RELU = 1, SN_TC_UPCONV = 2, SN_TC_DST_F32 = 4, SN_TC_IM2COL = 8, SN_TC_ROWS = 16, SN_TC_EXACT = 32,
+       SN_TC_KWC = 64, SN_TC_NO_KWC = 128 };
 
 /* One fused moment convolution on the tensor cores: myConv_intermediate.call (Brats.py:118-137), optionally
  * with the ReLU gate of Brats.py:233-238 (SN_TC_RELU), reading the channel-concat of up to two packed windows
@@ -185,6 +186,10 @@ enum { SN_TC_RELU = 1, SN_TC_UPCONV = 2, SN_TC_DST_F32 = 4, SN_TC_IM2COL = 8, SN
  *   - SN_TC_DST_F32: write fp32 NHWC mean/variance (dst_mu, dst_var: contiguous [batch,out_h,out_w,cout])
  *     instead of the packed window dst;
  *   - SN_TC_IM2COL: run the first-generation kernel (one CTA per 128-pixel tile, TMA im2col loads per tap)
+ *   - SN_TC_KWC / SN_TC_NO_KWC: force / forbid the kw-concatenated variant of the halo kernel (32 output columns per
+ *     tile, k = 3, width >= 32: the three taps of a filter row are N columns of one UMMA and are summed with a lane
+ *     shift in the epilogue; packed rows leave through TMA stores).  Default: the library's choice (layers with >= 2
+ *     input channel blocks).  Same results to rounding either way; an A/B and test switch like SN_TC_IM2COL.
  *     instead of the default persistent halo-tiled kernel; same results, kept for A/B measurements. */
 typedef struct sn_tc_conv_desc {
   sn_packed_view src[2];

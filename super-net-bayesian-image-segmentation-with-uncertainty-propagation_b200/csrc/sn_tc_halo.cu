@@ -40,6 +40,8 @@ namespace sn {
 constexpr int HL_BM = 128;
 constexpr int HL_KC = 32;
 constexpr int HL_THREADS = 576;       // 18 warps: TMA, UMMA, 8 x q reduction, 8 x epilogue
+constexpr int HL_THREADS_2SETS = 832; // 26 warps: a second set of 8 epilogue warps (kw-concatenated kernels)
+__host__ __device__ constexpr int hl_threads(bool kwc) { return kwc ? HL_THREADS_2SETS : HL_THREADS; }
 constexpr int HL_MAX_BSLOTS = 36;
 constexpr int HL_MAX_ASTAGES = 4;
 constexpr int HL_SMEM = 232448;        // 227 KB: always requested so exactly one CTA owns an SM (and its TMEM)
@@ -47,7 +49,9 @@ constexpr int HL_SMEM = 232448;        // 227 KB: always requested so exactly on
 struct HlMaps {
   CUtensorMap a[4][3];     // forward: up to two concatenated sources; data gradient of an up-conv: four parity views
   CUtensorMap w;
+  CUtensorMap d;           // destination window (c, plane, x, y, n) for the TMA-store epilogue
 };
+constexpr int HL_STG_BUF = 6144;      // staging buffer of one (epilogue set, tile row): 30 pixels x 3 planes x 32 channels
 
 struct HlView {            // a window of a packed buffer, device side
   __nv_bfloat16* base;
@@ -79,6 +83,10 @@ struct HlP {
   HlView gdst[2], saved[2];
   int csplit, gate[2];
   int v8;                  // every packed row segment the epilogue touches is 32-byte aligned: use 256-bit accesses
+  int kwc;                 // kw-concatenated variant (see the kernel): R = 32, one weight slot per filter row
+  int tma_store;           // forward KWC, packed destination: rows leave through shared memory + TMA tensor stores
+  int dbg;                 // SN_HL_DBG knob experiments (profiling only; results are wrong when non-zero): 1 epilogue
+                           // skips its work, 2 one UMMA group per tile, 4 reducers skip their loads, 8 no global stores
 };
 
 __device__ __forceinline__ float hl_lo(uint32_t v) { return __uint_as_float(v << 16); }
@@ -133,14 +141,25 @@ __device__ __forceinline__ TileCoord decode_group_tile(int grp, int t, const HlP
   return c;
 }
 
-template <int NT, int KS, bool RESIDENT, bool DGRAD, int G = 1>
-__global__ void __launch_bounds__(HL_THREADS, 1) conv_moments_halo_kernel(const __grid_constant__ HlMaps maps,
+// KWC ("kw-concatenated", NT = 32, k = 3): the three kw taps of a filter row become N columns of ONE UMMA,
+//   D[j, kw*NT + n] = sum_{kh, c} A[j + kh*R, c] * W[kh, kw, c, n]      (N = 3*NT = 96, A fetched once per kh)
+//   out[j, n]       = sum_kw D[j + kw, kw*NT + n]                        (epilogue: warp shuffles across TMEM lanes)
+// Why: a UMMA streams its operands from shared memory at 128 B/clk (tools/probe_mma_rate.cu: 44.8 / 48.1 / 64.1 cycles
+// at N = 32 / 64 / 128 = (4 KB of A + N*32 B of B) / 128), so at N = 32 the 4 KB A tile costs 45 cycles for 16 cycles
+// of math.  One A fetch for three taps cuts the UMMAs per (kh, K step) from 9 (414 cycles) to 4 of N = 96 (~224).
+// The lane shift must stay inside one 32-lane TMEM quarter (a warp only reads its own quarter), so the halo box is
+// R = 32 columns wide: quarter = one output row of the tile, lanes 30 / 31 are the halo margin that is junk anyway.
+template <int NT, int KS, bool RESIDENT, bool DGRAD, int G = 1, bool KWC = false>
+__global__ void __launch_bounds__(hl_threads(KWC), 1) conv_moments_halo_kernel(const __grid_constant__ HlMaps maps,
                                                                           const HlP p) {
-  constexpr int B_PLANE = NT * HL_KC * 2;
+  static_assert(!KWC || (NT == 32 && KS == 3 && G == 1), "kw-concatenation: 32-column tiles of a 3x3 conv");
+  constexpr int NB = KWC ? KS * NT : NT;                  // rows (GEMM N) of one weight plane of a slot
+  constexpr int SLOTS_PER_CB = KWC ? KS : KS * KS;        // weight slots per 32-channel block: filter rows / taps
+  constexpr int B_PLANE = NB * HL_KC * 2;
   constexpr int B_SLOT = 3 * B_PLANE;
-  constexpr bool CONCAT = NT <= 64;                       // hi x [W_hi ; W_lo] as one UMMA of N = 2*NT
-  constexpr int ACC_STAGE = CONCAT ? 3 * NT : 2 * NT;     // TMEM columns per accumulator stage
-  constexpr int TMEM_COLS = NT == 32 ? 256 : 512;         // 2 stages, rounded up to a power of two
+  constexpr bool CONCAT = !KWC && NT <= 64;               // hi x [W_hi ; W_lo] as one UMMA of N = 2*NT
+  constexpr int ACC_STAGE = KWC ? 2 * NB : (CONCAT ? 3 * NT : 2 * NT);     // TMEM columns per accumulator stage
+  constexpr int TMEM_COLS = 2 * ACC_STAGE <= 256 ? 256 : 512;              // 2 stages, rounded up to a power of two
   extern __shared__ uint8_t smem_raw[];
   const uint32_t smem_base = (ptx::smem_u32(smem_raw) + 1023u) & ~1023u;
   uint8_t* smem_gen = smem_raw + (smem_base - ptx::smem_u32(smem_raw));
@@ -176,6 +195,7 @@ __global__ void __launch_bounds__(HL_THREADS, 1) conv_moments_halo_kernel(const 
       if (p.cblk_s[s])
         for (int pl = 0; pl < 3; ++pl) ptx::prefetch_tensormap(&maps.a[s][pl]);
     ptx::prefetch_tensormap(&maps.w);
+    if (KWC && !DGRAD && p.tma_store) ptx::prefetch_tensormap(&maps.d);
     for (int s = 0; s < p.sa; ++s) {
       ptx::mbar_init(a_full(s), 1);
       ptx::mbar_init(a_empty(s), 9);          // UMMA commit + the 8 reducer warps
@@ -196,7 +216,7 @@ __global__ void __launch_bounds__(HL_THREADS, 1) conv_moments_halo_kernel(const 
     ptx::tmem_alloc(tmem_slot, TMEM_COLS);
     ptx::tmem_relinquish();
   }
-  for (int i = threadIdx.x; i < p.s_len; i += HL_THREADS) s_sm[i] = p.s[i];
+  for (int i = threadIdx.x; i < p.s_len; i += hl_threads(KWC)) s_sm[i] = p.s[i];
   ptx::tc_fence_before();
   __syncthreads();
   ptx::tc_fence_after();
@@ -209,6 +229,23 @@ __global__ void __launch_bounds__(HL_THREADS, 1) conv_moments_halo_kernel(const 
   if (warp == 0) {
     // ===================== TMA producer =====================
     if (lane == 0) {
+      // one weight slot: the three operand planes of tap `tap` (KWC: of filter row `tap`, its kw taps stacked along N)
+      auto load_b_slot = [&](uint32_t sb_addr, uint32_t bar, int cbt, int tap, int ncol0, int n0) {
+#pragma unroll
+        for (int pl = 0; pl < 3; ++pl) {
+          if constexpr (KWC) {
+#pragma unroll
+            for (int kw = 0; kw < KS; ++kw)
+              ptx::tma_load_3d(sb_addr + pl * B_PLANE + kw * (NT * HL_KC * 2), &maps.w, bar, cbt * HL_KC, n0,
+                               pl * p.taps_w + tap * KS + kw);
+          } else {
+            // regular conv: weights [3*taps][cout][cin], rows n0.. of tap `tap`; up-conv: [3][4*cout][cin], the N
+            // tile may span several parity groups (rows ncol0.. of the (parity, channel) axis)
+            ptx::tma_load_3d(sb_addr + pl * B_PLANE, &maps.w, bar, cbt * HL_KC, p.upconv ? ncol0 : n0,
+                             p.upconv ? pl : pl * p.taps_w + tap);
+          }
+        }
+      };
       bool dep_waited = false;
       int ai = 0, bi = 0;     // running A-stage / B-slot fill counters
       TileIt it;
@@ -219,14 +256,10 @@ __global__ void __launch_bounds__(HL_THREADS, 1) conv_moments_halo_kernel(const 
         const int group = ncol0 / p.cout;
         const int n0 = ncol0 - group * p.cout;
         for (int cbt = 0; cbt < cblk; ++cbt)
-          for (int tap = 0; tap < taps; ++tap) {
-            const int slot = cbt * taps + tap;
+          for (int tap = 0; tap < SLOTS_PER_CB; ++tap) {
+            const int slot = cbt * SLOTS_PER_CB + tap;
             ptx::mbar_arrive_expect_tx(b_full(slot), (uint32_t)B_SLOT);
-            const uint32_t sb_addr = b_base + slot * B_SLOT;
-#pragma unroll
-            for (int pl = 0; pl < 3; ++pl)
-              ptx::tma_load_3d(sb_addr + pl * B_PLANE, &maps.w, b_full(slot), cbt * HL_KC, p.upconv ? ncol0 : n0,
-                               p.upconv ? pl : pl * p.taps_w + tap);
+            load_b_slot(b_base + slot * B_SLOT, b_full(slot), cbt, tap, ncol0, n0);
           }
       }
       const int n_units = G == 1 ? p.total_tiles : p.total_groups;
@@ -274,7 +307,7 @@ __global__ void __launch_bounds__(HL_THREADS, 1) conv_moments_halo_kernel(const 
               }
           }
           if (!RESIDENT) {
-            for (int tap = 0; tap < taps; ++tap) {
+            for (int tap = 0; tap < SLOTS_PER_CB; ++tap) {
               int slot;
               {
                 slot = bi % p.sb;
@@ -283,13 +316,7 @@ __global__ void __launch_bounds__(HL_THREADS, 1) conv_moments_halo_kernel(const 
                 ptx::mbar_wait(b_empty(slot), parity ^ 1u);
               }
               ptx::mbar_arrive_expect_tx(b_full(slot), (uint32_t)B_SLOT);
-              const uint32_t sb_addr = b_base + slot * B_SLOT;
-              // regular conv: weights [3*taps][cout][cin], rows n0.. of tap `tap`; up-conv: [3][4*cout][cin], the N
-              // tile may span several parity groups (rows ncol0.. of the (parity, channel) axis)
-#pragma unroll
-              for (int pl = 0; pl < 3; ++pl)
-                ptx::tma_load_3d(sb_addr + pl * B_PLANE, &maps.w, b_full(slot), cbt * HL_KC,
-                                 p.upconv ? ncol0 : n0, p.upconv ? pl : pl * p.taps_w + tap);
+              load_b_slot(b_base + slot * B_SLOT, b_full(slot), cbt, tap, ncol0, n0);
             }
           }
         }
@@ -306,7 +333,7 @@ __global__ void __launch_bounds__(HL_THREADS, 1) conv_moments_halo_kernel(const 
       // All 32 lanes run this loop (uniform control flow keeps the descriptor arithmetic in the uniform datapath);
       // one elected lane issues the UMMAs and commits.  Taps and K steps are fully unrolled so every descriptor is
       // "per-stage base + immediate": the issuing thread must sustain one UMMA per ~45 cycles.
-      constexpr uint32_t idesc_n = ptx::idesc_bf16_f32(HL_BM, NT);
+      constexpr uint32_t idesc_n = ptx::idesc_bf16_f32(HL_BM, NB);
       constexpr uint32_t idesc_2n = ptx::idesc_bf16_f32(HL_BM, CONCAT ? 2 * NT : NT);
       // descriptor = constant high word | (1 << 16 | address >> 4) in the low word (smem < 256 KB: 14 bits);
       // high word of smem_desc_kmajor<64>: SBO = 512 B >> 4 at bits [32,46), version 1 at bit 46, SW64 (4) at [61,64)
@@ -332,14 +359,15 @@ __global__ void __launch_bounds__(HL_THREADS, 1) conv_moments_halo_kernel(const 
         for (int cbt = 0; cbt < cblk; ++cbt) {
           ptx::mbar_wait(a_full(a_stage_i), a_par);
           if (RESIDENT && titer == 0) {
-            for (int tap = 0; tap < taps; ++tap) ptx::mbar_wait(b_full(cbt * taps + tap), 0);
+            for (int tap = 0; tap < SLOTS_PER_CB; ++tap) ptx::mbar_wait(b_full(cbt * SLOTS_PER_CB + tap), 0);
           }
           ptx::tc_fence_after();
           const uint32_t a_st = a_lo_base + a_stage_i * stage16;
-          uint32_t b_st = b_lo_base + (RESIDENT ? (uint32_t)(cbt * taps) * SLOT16 : 0u);
+          uint32_t b_st = b_lo_base + (RESIDENT ? (uint32_t)(cbt * SLOTS_PER_CB) * SLOT16 : 0u);
 #pragma unroll
-          for (int tap = 0; tap < taps; ++tap) {
-            const int kh = tap / KS, kw = tap % KS;                  // compile-time after unrolling
+          for (int tap = 0; tap < SLOTS_PER_CB; ++tap) {
+            // compile-time after unrolling; KWC: one slot per filter row, the kw shift happens in the epilogue
+            const int kh = KWC ? tap : tap / KS, kw = KWC ? 0 : tap % KS;
             uint32_t b0;
             int slot = 0;
             if (RESIDENT) {
@@ -352,12 +380,12 @@ __global__ void __launch_bounds__(HL_THREADS, 1) conv_moments_halo_kernel(const 
               b0 = b_st + (uint32_t)slot * SLOT16;
             }
             const uint32_t a00 = a_st + (uint32_t)kh * row_shift16 + (uint32_t)kw * 4u;  // tap = row offset in the halo
-            if (leader) {
+            if (leader && (!(p.dbg & 2) || tap == 0)) {
 #pragma unroll
               for (int t = 0; t < G; ++t) {
                 const uint32_t a0 = a00 + (uint32_t)t * 3u * plane16;             // tile t of the pair
                 const uint32_t acc_mu = G == 1 ? acc_mu0 : tmem_base + (uint32_t)t * ACC_STAGE;
-                const uint32_t acc_var = acc_mu + (CONCAT ? 2 * NT : NT);
+                const uint32_t acc_var = acc_mu + (CONCAT ? 2 * NT : NB);
 #pragma unroll
                 for (int ks = 0; ks < HL_KC / 16; ++ks) {
                   const uint32_t k16 = ks * 2;                          // 16 bf16 = 32 B along K
@@ -373,8 +401,8 @@ __global__ void __launch_bounds__(HL_THREADS, 1) conv_moments_halo_kernel(const 
                   ptx::umma_bf16(acc_var, desc(a0 + 2 * plane16 + k16), desc(b0 + 2 * BPLANE16 + k16), idesc_n, acc);
                 }
               }
-              if (!RESIDENT) ptx::umma_commit(b_empty(slot));
             }
+            if (leader && !RESIDENT) ptx::umma_commit(b_empty(slot));
           }
           if (leader) ptx::umma_commit(a_empty(a_stage_i));
           if (++a_stage_i == p.sa) { a_stage_i = 0; a_par ^= 1u; }
@@ -405,7 +433,7 @@ __global__ void __launch_bounds__(HL_THREADS, 1) conv_moments_halo_kernel(const 
             while (cb >= p.cblk_s[src]) { cb = 0; ++src; }
           }
           ptx::mbar_wait(a_full(a_stage_i), a_par);
-          if (row < p.rows_box) {
+          if (row < p.rows_box && !(p.dbg & 4)) {
 #pragma unroll
            for (int t = 0; t < G; ++t) {
             float qa = 0.f, qb = 0.f, qc = 0.f, qd = 0.f;         // four chains for ILP
@@ -458,9 +486,15 @@ __global__ void __launch_bounds__(HL_THREADS, 1) conv_moments_halo_kernel(const 
         }
       }
     } else {
-      // ===================== epilogue (warps 10-17) =====================
+      // ===================== epilogue (warps 10-17; kw-concatenated kernels: 10-25 in two sets) =====================
+      // With the UMMA count per tile halved (KWC) this role's per-warp dependent chain (barrier waits, TMEM loads,
+      // shuffles, converts, stores: ~500 instructions per tile at ~0.17 IPC) is the longest path per tile (ncu: the
+      // issuer waits on acc_empty, the reduction warps on q_empty).  Two sets of eight warps take alternate tiles, set s
+      // always draining accumulator stage s.
+      constexpr int ESETS = KWC ? 2 : 1;
+      const int eset = (warp - 10) >> 3;
       const int q = warp & 3;                   // TMEM lane quarter this warp may access
-      const int half = (warp - 10) >> 2;        // which half of the tile's NT columns this warp converts
+      const int half = ((warp - 10) >> 2) & 1;  // which half of the tile's NT columns this warp converts
       constexpr int NH = NT / 2;
       const int row = q * 32 + lane;            // GEMM row == TMEM lane == halo pixel index
       const int x = row % p.R;
@@ -477,6 +511,7 @@ __global__ void __launch_bounds__(HL_THREADS, 1) conv_moments_halo_kernel(const 
         if constexpr (G == 1) {
           tc.nt = it.nt; tc.tx = it.tx; tc.ty = it.ty; tc.tb = it.tb; tc.store = true;
           it.next(p);
+          if (ESETS == 2 && (titer & 1) != eset) continue;     // the other set's tile
         } else {
           tc = decode_group_tile((int)blockIdx.x + (titer >> 1) * (int)gridDim.x, titer & 1, p);
         }
@@ -502,12 +537,69 @@ __global__ void __launch_bounds__(HL_THREADS, 1) conv_moments_halo_kernel(const 
         const int nt_i = tc.nt, tx = tc.tx, ty = tc.ty, tb = tc.tb;
         const int gcol0 = nt_i * NT + half * NH;               // first column (parity group, channel) of this warp
         const int ox_i = tx * p.TWo + x, oy_i = ty * p.THo + y, ob = tb * p.TN + n;
-        const bool valid = tc.store && x < p.TWo && y < p.THo && n < p.TN && ox_i < p.Wo && oy_i < p.Ho && ob < p.B;
+        const bool valid = tc.store && x < p.TWo && y < p.THo && n < p.TN && ox_i < p.Wo && oy_i < p.Ho && ob < p.B &&
+                           !(p.dbg & 8);
         if (!DGRAD && p.r_out != nullptr && half == 0 && nt_i == 0 && valid)
           p.r_out[((size_t)ob * p.Ho + oy_i) * p.Wo + ox_i] = r;
         ptx::mbar_wait(acc_full(as), par);
         ptx::tc_fence_after();
+        if (p.dbg & 1) {
+          ptx::tc_fence_before();
+          __syncwarp();
+          if (lane == 0) ptx::mbar_arrive(acc_empty(as));
+          continue;
+        }
         const uint32_t lane_base = tmem_base + ((uint32_t)(q * 32) << 16) + as * ACC_STAGE + half * NH;
+        // 16 mean and 16 variance accumulator columns (c0 .. c0+15 of this warp's half) of this thread's GEMM row
+        // TMA-store epilogue (KWC forward): the two warps of a (set, quarter) pair stage their tile row -- 30 pixels x
+        // [hi | lo | var] x 32 channels = 5760 contiguous bytes, 64-byte swizzled so the 192-byte pixel stride is
+        // bank-conflict free -- and one lane hands it to the TMA.  Why: a lane-per-pixel st.global.v8 touches 32 cache
+        // lines per instruction = 32 LSU wavefronts (758 of the 2185 LSU wavefronts per tile, ncu); the LSU data pipe,
+        // not the UMMA pipe, bounded the kw-concatenated kernel.
+        const bool tma_st = KWC && !DGRAD && p.tma_store;
+        const uint32_t stg = bar_base + 5120u + (uint32_t)(eset * 4 + q) * HL_STG_BUF;
+        const uint32_t pair_bar = 1u + (uint32_t)(eset * 4 + q);
+        auto stage32 = [&](int pl, const uint32_t (&w8)[8]) {      // this lane's 16 channels of plane pl
+          const uint32_t L = (uint32_t)lane * 192u + (uint32_t)pl * 64u + (uint32_t)half * 32u;
+          const uint32_t x4 = ((L >> 7) & 3u) << 4;                 // SWIZZLE_64B: bits [4,6) ^= bits [7,9)
+          ptx::st_shared_v4(stg + (L ^ x4), w8[0], w8[1], w8[2], w8[3]);
+          ptx::st_shared_v4(stg + ((L + 16u) ^ x4), w8[4], w8[5], w8[6], w8[7]);
+        };
+        if (tma_st) {
+          if (half == 0 && lane == 0) ptx::bulk_wait_read0();       // the pair's previous store has left the buffer
+          ptx::named_barrier(pair_bar, 64);
+        }
+        // KWC: out[j] = D[j][kw = 0] + D[j+1][kw = 1] + D[j+2][kw = 2]; rows j+1, j+2 are the next TMEM lanes = the next
+        // threads of this warp (R = 32: a quarter is one tile row; lanes 30, 31 wrap into junk and are never stored)
+        auto load_kwc16 = [&](uint32_t taddr, uint32_t (&a)[16]) {
+          uint32_t t1[16], t2[16];
+          ptx::tmem_ld16(taddr, a);
+          ptx::tmem_ld16(taddr + NT, t1);
+          ptx::tmem_ld16(taddr + 2 * NT, t2);
+          ptx::tmem_ld_wait();
+#pragma unroll
+          for (int j = 0; j < 16; ++j)
+            a[j] = __float_as_uint(__uint_as_float(a[j]) + __shfl_down_sync(0xffffffffu, __uint_as_float(t1[j]), 1) +
+                                   __shfl_down_sync(0xffffffffu, __uint_as_float(t2[j]), 2));
+        };
+        auto load_acc16 = [&](int c0, uint32_t (&am)[16], uint32_t (&av)[16]) {
+          if constexpr (KWC) {
+            load_kwc16(lane_base + c0, am);
+            load_kwc16(lane_base + NB + c0, av);
+          } else {
+            ptx::tmem_ld16(lane_base + c0, am);
+            ptx::tmem_ld16(lane_base + (CONCAT ? 2 * NT : NT) + c0, av);
+            if constexpr (CONCAT) {
+              uint32_t am2[16];
+              ptx::tmem_ld16(lane_base + NT + c0, am2);     // the hi x W_lo half of the mean
+              ptx::tmem_ld_wait();
+#pragma unroll
+              for (int j = 0; j < 16; ++j) am[j] = __float_as_uint(__uint_as_float(am[j]) + __uint_as_float(am2[j]));
+            } else {
+              ptx::tmem_ld_wait();
+            }
+          }
+        };
         if constexpr (DGRAD) {
           // ---- data gradient: g_mu = acc_mu + 2 mu_saved T, g_var = acc_var + T, T = r; then the
           // ReLU gate of the layer that produced the forward input (Brats.py:233-238: the gate is mu_saved > 0)
@@ -536,17 +628,7 @@ __global__ void __launch_bounds__(HL_THREADS, 1) conv_moments_halo_kernel(const 
               }
             }
             uint32_t am[16], av[16];
-            ptx::tmem_ld16(lane_base + c0, am);
-            ptx::tmem_ld16(lane_base + (CONCAT ? 2 * NT : NT) + c0, av);
-            if constexpr (CONCAT) {
-              uint32_t am2[16];
-              ptx::tmem_ld16(lane_base + NT + c0, am2);
-              ptx::tmem_ld_wait();
-#pragma unroll
-              for (int j = 0; j < 16; ++j) am[j] = __float_as_uint(__uint_as_float(am[j]) + __uint_as_float(am2[j]));
-            } else {
-              ptx::tmem_ld_wait();
-            }
+            load_acc16(c0, am, av);
             const bool gate = p.gate[seg] != 0;
             const float r2 = 2.f * r;
             uint32_t hi[8], lo[8], vr[8];
@@ -604,18 +686,104 @@ __global__ void __launch_bounds__(HL_THREADS, 1) conv_moments_halo_kernel(const 
               d_hi = p.dst + ((((size_t)ob * p.dh + oy + p.dy0) * p.dw + ox + p.dx0) * 3) * p.dc + p.dc0 + nch;
             }
           }
-          uint32_t am[16], av[16];
-          ptx::tmem_ld16(lane_base + c0, am);
-          ptx::tmem_ld16(lane_base + (CONCAT ? 2 * NT : NT) + c0, av);
-          if constexpr (CONCAT) {
-            uint32_t am2[16];
-            ptx::tmem_ld16(lane_base + NT + c0, am2);     // the hi x W_lo half of the mean
-            ptx::tmem_ld_wait();
+          if constexpr (KWC) {
+            // mean first, then variance (one 16-bit gate mask in between): half the live registers of the joint form,
+            // which matters at the 72 registers per thread the two epilogue sets leave
+            uint32_t gate = 0xFFFFu;
+            {
+              uint32_t am[16];
+              load_kwc16(lane_base + c0, am);
+              if (p.relu) {
+                gate = 0;
 #pragma unroll
-            for (int j = 0; j < 16; ++j) am[j] = __float_as_uint(__uint_as_float(am[j]) + __uint_as_float(am2[j]));
-          } else {
-            ptx::tmem_ld_wait();
+                for (int j = 0; j < 16; ++j) {
+                  const float mj = __uint_as_float(am[j]);
+                  gate |= (mj > 0.f ? 1u : 0u) << j;
+                  am[j] = __float_as_uint(fmaxf(mj, 0.f));
+                }
+              }
+              if (tma_st ? x < p.TWo : valid) {
+                if (p.dst_f32) {
+#pragma unroll
+                  for (int j = 0; j < 16; j += 4)
+                    *reinterpret_cast<uint4*>(f_mu + j) = make_uint4(am[j], am[j + 1], am[j + 2], am[j + 3]);
+                } else {
+                  uint32_t hi[8], lo[8];
+#pragma unroll
+                  for (int j = 0; j < 8; ++j) {
+                    const float a0 = __uint_as_float(am[2 * j]), a1 = __uint_as_float(am[2 * j + 1]);
+                    hi[j] = hl_pack2(a0, a1);
+                    lo[j] = hl_pack2(a0 - hl_lo(hi[j]), a1 - hl_hi(hi[j]));
+                  }
+                  if (tma_st) {
+                    stage32(0, hi);
+                    stage32(1, lo);
+                  } else if (p.v8) {
+                    ptx::st_global_v8(d_hi, hi);
+                    ptx::st_global_v8(d_hi + p.dc, lo);
+                  } else {
+                    uint4* ph = reinterpret_cast<uint4*>(d_hi);
+                    uint4* pl = reinterpret_cast<uint4*>(d_hi + p.dc);
+                    ph[0] = make_uint4(hi[0], hi[1], hi[2], hi[3]);
+                    ph[1] = make_uint4(hi[4], hi[5], hi[6], hi[7]);
+                    pl[0] = make_uint4(lo[0], lo[1], lo[2], lo[3]);
+                    pl[1] = make_uint4(lo[4], lo[5], lo[6], lo[7]);
+                  }
+                }
+              }
+            }
+            {
+              uint32_t av[16];
+              load_kwc16(lane_base + NB + c0, av);
+#pragma unroll
+              for (int j4 = 0; j4 < 16; j4 += 4) {
+                const float4 s4 = *reinterpret_cast<const float4*>(s_sm + nch + j4);   // warp-uniform: broadcast
+                const float sv[4] = {s4.x, s4.y, s4.z, s4.w};
+#pragma unroll
+                for (int e = 0; e < 4; ++e) {
+                  const int j = j4 + e;
+                  const float vj = fmaxf(fmaf(sv[e], r, __uint_as_float(av[j])), 0.f);   // all terms >= 0
+                  av[j] = (gate >> j) & 1u ? __float_as_uint(vj) : 0u;
+                }
+              }
+              if (tma_st ? x < p.TWo : valid) {
+                if (p.dst_f32) {
+#pragma unroll
+                  for (int j = 0; j < 16; j += 4)
+                    *reinterpret_cast<uint4*>(f_var + j) = make_uint4(av[j], av[j + 1], av[j + 2], av[j + 3]);
+                } else {
+                  uint32_t vr[8];
+#pragma unroll
+                  for (int j = 0; j < 8; ++j) vr[j] = hl_pack2(__uint_as_float(av[2 * j]), __uint_as_float(av[2 * j + 1]));
+                  if (tma_st) {
+                    stage32(2, vr);
+                  } else if (p.v8) {
+                    ptx::st_global_v8(d_hi + 2 * p.dc, vr);
+                  } else {
+                    uint4* pv = reinterpret_cast<uint4*>(d_hi + 2 * p.dc);
+                    pv[0] = make_uint4(vr[0], vr[1], vr[2], vr[3]);
+                    pv[1] = make_uint4(vr[4], vr[5], vr[6], vr[7]);
+                  }
+                }
+              }
+            }
+            if (tma_st) {
+              // both TMEM phases of this warp are in registers / staged: release the accumulator stage to the issuer
+              // before the store handshake
+              ptx::tc_fence_before();
+              __syncwarp();
+              if (lane == 0) ptx::mbar_arrive(acc_empty(as));
+              ptx::fence_proxy_async();                               // generic-proxy writes -> visible to the TMA
+              ptx::named_barrier(pair_bar, 64);
+              if (half == 0 && lane == 0 && tc.store && oy_i < p.Ho && ob < p.B && !(p.dbg & 8)) {
+                ptx::tma_store_5d(&maps.d, stg, nt_i * NT, 0, tx * p.TWo, oy_i, ob);
+                ptx::bulk_commit_group();
+              }
+            }
+            continue;
           }
+          uint32_t am[16], av[16];
+          load_acc16(c0, am, av);
           float mu[16], var[16];
 #pragma unroll
           for (int j4 = 0; j4 < 16; j4 += 4) {
@@ -669,10 +837,13 @@ __global__ void __launch_bounds__(HL_THREADS, 1) conv_moments_halo_kernel(const 
           }
         }
         }
-        ptx::tc_fence_before();
-        __syncwarp();
-        if (lane == 0) ptx::mbar_arrive(acc_empty(as));    // this warp's TMEM reads of stage `as` are done
+        if (!tma_st) {
+          ptx::tc_fence_before();
+          __syncwarp();
+          if (lane == 0) ptx::mbar_arrive(acc_empty(as));    // this warp's TMEM reads of stage `as` are done
+        }
       }
+      if (KWC && !DGRAD && p.tma_store && half == 0 && lane == 0) ptx::bulk_wait_read0();   // staging must outlive the reads
     }
   }
 
@@ -740,6 +911,40 @@ static HaloTiling choose_tiling(int batch, int in_h, int in_w, int k) {
   return best;
 }
 
+// kw-concatenated variant: the halo box is exactly 32 columns wide (30 output columns), so that the epilogue's +1 / +2
+// row shifts stay inside one 32-lane TMEM quarter; a tile is 4 output rows (quarter = row).
+static HaloTiling kwc_tiling(int batch, int in_h, int in_w) {
+  const int Ho = in_h - 2, Wo = in_w - 2;
+  HaloTiling t{};
+  t.R = 32; t.TWo = 30; t.TN = 1;
+  t.THo = Ho < 4 ? Ho : 4;
+  t.THb = t.THo + 2;
+  t.tiles_x = (Wo + t.TWo - 1) / t.TWo;
+  t.tiles_y = (Ho + t.THo - 1) / t.THo;
+  t.tiles_b = batch;
+  t.eff = (double)Ho * Wo / ((double)t.tiles_x * t.tiles_y * HL_BM);
+  return t;
+}
+
+// Use it for 32-column tiles of 3x3 convs with >= 2 channel blocks, when the fixed 30-column tile width does not waste
+// much more of the GEMM rows than the free choice would.  Measured at batch 64 (profiles/r02_kwc_knobs.md): the UMMA pipe
+// time per tile halves (83 % -> 46 % busy), but the kernel then runs into the CUDA-core side -- ~10 k warp instructions
+// per 128-pixel tile between the epilogue (64 extra shuffles per thread) and the q-reduction warps, LSU data pipe at
+// 64-69 % -- so with ONE channel block (conv1, up4_conv2: 24 UMMAs per tile) it only ties with the tap-shift kernel
+// (0.263 vs 0.252 ms), while with two (up4_conv1: 48 vs 108 UMMAs) it wins (0.355 vs 0.44 ms).  SN_KWC=2 forces it for
+// every eligible layer, SN_KWC=0 disables it.
+static bool kwc_wanted(int flags, int nt, int keff, int in_w, int cblk, const HaloTiling& free_choice,
+                       const HaloTiling& kwc) {
+  static const int env_mode = [] {
+    const char* e = getenv("SN_KWC");
+    return e == nullptr ? 1 : atoi(e);
+  }();
+  const int mode = (flags & SN_TC_NO_KWC) ? 0 : ((flags & SN_TC_KWC) ? 2 : env_mode);
+  if (mode == 0 || nt != 32 || keff != 3 || in_w < 32) return false;
+  if (mode == 2) return true;
+  return cblk >= 2 && kwc.eff >= 0.65 * free_choice.eff;
+}
+
 // Tensor map of one plane of a packed window.  `step` = 2 with origin (oy, ox) addresses the pixels (2y+oy, 2x+ox):
 // the four parity views the data gradient of an up-conv reads.  Everything outside the window reads as zero
 // (TMA out-of-bounds fill), which is how the data gradient gets its (k-1)-wide zero border.
@@ -759,6 +964,23 @@ static int hl_make_act_map(CUtensorMap* out, const sn_packed_view& v, int plane,
   return SN_OK;
 }
 
+// Destination window as a 5-D tensor (channel, plane, x, y, image) for the TMA-store epilogue: the box is one tile row
+// (30 pixels x 3 planes x 32 channels, 64-byte swizzled in shared memory); whatever lies outside the window is clipped.
+static int hl_make_dst_map(CUtensorMap* out, const sn_packed_view& v, int cout, int out_h, int out_w, int batch,
+                           int box_w) {
+  const size_t pix = (size_t)3 * v.c * 2;
+  char* base = reinterpret_cast<char*>(v.base) + ((((size_t)v.y0 * v.w + v.x0) * 3) * v.c + v.c0) * sizeof(__nv_bfloat16);
+  cuuint64_t dims[5] = {(cuuint64_t)cout, 3, (cuuint64_t)out_w, (cuuint64_t)out_h, (cuuint64_t)batch};
+  cuuint64_t strides[4] = {(cuuint64_t)v.c * 2, pix, (cuuint64_t)v.w * pix, (cuuint64_t)v.h * v.w * pix};
+  cuuint32_t box[5] = {32, 3, (cuuint32_t)box_w, 1, 1};
+  cuuint32_t estr[5] = {1, 1, 1, 1, 1};
+  CUresult r = hl_encode_tiled()(out, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 5, base, dims, strides, box, estr,
+                                 CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_64B,
+                                 CU_TENSOR_MAP_L2_PROMOTION_L2_128B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  if (r != CUDA_SUCCESS) return fail(SN_ERR_DRIVER, "cuTensorMapEncodeTiled(destination) failed (%d)", (int)r);
+  return SN_OK;
+}
+
 static int hl_make_weight_map(CUtensorMap* out, const void* w_packed, int taps, int cout, int cin, int nt) {
   cuuint64_t dims[3] = {(cuuint64_t)cin, (cuuint64_t)cout, (cuuint64_t)(3 * taps)};
   cuuint64_t strides[2] = {(cuuint64_t)cin * 2, (cuuint64_t)cin * cout * 2};
@@ -771,12 +993,12 @@ static int hl_make_weight_map(CUtensorMap* out, const void* w_packed, int taps, 
   return SN_OK;
 }
 
-template <int NT, int KS, bool RESIDENT, bool DGRAD, int G = 1>
+template <int NT, int KS, bool RESIDENT, bool DGRAD, int G = 1, bool KWC = false>
 static int hl_launch3(const HlMaps& maps, const HlP& p, cudaStream_t st) {
   static std::once_flag once;
   static cudaError_t attr_err = cudaSuccess;
   std::call_once(once, [] {
-    attr_err = cudaFuncSetAttribute(conv_moments_halo_kernel<NT, KS, RESIDENT, DGRAD, G>,
+    attr_err = cudaFuncSetAttribute(conv_moments_halo_kernel<NT, KS, RESIDENT, DGRAD, G, KWC>,
                                     cudaFuncAttributeMaxDynamicSharedMemorySize, HL_SMEM);
   });
   if (attr_err != cudaSuccess) return fail(SN_ERR_LAUNCH, "conv_halo: cannot reserve %d B of shared memory", HL_SMEM);
@@ -788,7 +1010,7 @@ static int hl_launch3(const HlMaps& maps, const HlP& p, cudaStream_t st) {
   }();
   cudaLaunchConfig_t cfg{};
   cfg.gridDim = dim3((unsigned)grid);
-  cfg.blockDim = dim3(HL_THREADS);
+  cfg.blockDim = dim3(hl_threads(KWC));
   cfg.dynamicSmemBytes = HL_SMEM;
   cfg.stream = st;
   cudaLaunchAttribute attr[1];
@@ -796,13 +1018,19 @@ static int hl_launch3(const HlMaps& maps, const HlP& p, cudaStream_t st) {
   attr[0].val.programmaticStreamSerializationAllowed = 1;
   cfg.attrs = attr;
   cfg.numAttrs = pdl ? 1 : 0;
-  cudaError_t e = cudaLaunchKernelEx(&cfg, conv_moments_halo_kernel<NT, KS, RESIDENT, DGRAD, G>, maps, p);
+  cudaError_t e = cudaLaunchKernelEx(&cfg, conv_moments_halo_kernel<NT, KS, RESIDENT, DGRAD, G, KWC>, maps, p);
   if (e != cudaSuccess) return fail(SN_ERR_LAUNCH, "conv_halo launch: %s", cudaGetErrorString(e));
   return check_launch(DGRAD ? "conv_moments_halo_dgrad" : "conv_moments_halo");
 }
 
 template <int NT>
 static int hl_launch(const HlMaps& maps, const HlP& p, cudaStream_t st) {
+  if constexpr (NT == 32) {
+    if (p.kwc) {
+      return p.b_resident ? hl_launch3<32, 3, true, false, 1, true>(maps, p, st)
+                          : hl_launch3<32, 3, false, false, 1, true>(maps, p, st);
+    }
+  }
   if (p.total_groups > 0) {            // two pixel tiles per weight slot (streamed weights, k = 3 or 1)
     if (p.ksize == 3) return hl_launch3<NT, 3, false, false, 2>(maps, p, st);
     if (p.ksize == 1) return hl_launch3<NT, 1, false, false, 2>(maps, p, st);
@@ -821,6 +1049,12 @@ static int hl_launch(const HlMaps& maps, const HlP& p, cudaStream_t st) {
 // output parities become four K-concatenated sources).
 template <int NT>
 static int hl_launch_dgrad(const HlMaps& maps, const HlP& p, cudaStream_t st) {
+  if constexpr (NT == 32) {
+    if (p.kwc) {
+      return p.b_resident ? hl_launch3<32, 3, true, true, 1, true>(maps, p, st)
+                          : hl_launch3<32, 3, false, true, 1, true>(maps, p, st);
+    }
+  }
   if (p.total_groups > 0) {
     if (p.ksize == 3) return hl_launch3<NT, 3, false, true, 2>(maps, p, st);
     if (p.ksize == 1) return hl_launch3<NT, 1, false, true, 2>(maps, p, st);
@@ -841,7 +1075,17 @@ static bool hl_view_v8(const sn_packed_view& v) {
 }
 
 // Tile geometry + shared-memory plan shared by the forward and the data-gradient dispatch.
-static int hl_plan(HlP& p, const HaloTiling& t, int keff, int ncols, int nt, int cblk) {
+static int hl_plan(HlP& p, const HaloTiling& t, int keff, int ncols, int nt, int cblk, bool kwc = false,
+                   bool tma_store = false) {
+  p.kwc = kwc ? 1 : 0;
+  p.tma_store = tma_store ? 1 : 0;
+  {
+    static const int dbg = [] {
+      const char* e = getenv("SN_HL_DBG");
+      return e ? atoi(e) : 0;
+    }();
+    p.dbg = dbg;
+  }
   p.tiles_x = t.tiles_x; p.tiles_y = t.tiles_y; p.tiles_b = t.tiles_b;
   p.tiles_n = ncols / nt;
   const long long total = (long long)p.tiles_x * p.tiles_y * p.tiles_b * p.tiles_n;
@@ -849,16 +1093,18 @@ static int hl_plan(HlP& p, const HaloTiling& t, int keff, int ncols, int nt, int
   p.total_tiles = (int)total;
   p.TWo = t.TWo; p.THo = t.THo; p.R = t.R; p.THb = t.THb; p.TN = t.TN;
   p.rows_box = t.R * t.THb * t.TN;
-  const int rows_alloc = HL_BM + (keff - 1) * (t.R + 1);
+  // rows the shifted A operands reach: taps shift by kh*R + kw (KWC: by kh*R only, the kw shift is in the epilogue)
+  const int rows_alloc = HL_BM + (keff - 1) * (kwc ? t.R : t.R + 1);
   const int rows_need = rows_alloc > p.rows_box ? rows_alloc : p.rows_box;
   SN_REQUIRE(rows_need <= 256, SN_ERR_UNSUPPORTED, "conv_halo: halo tile of %d rows", rows_need);
   p.a_plane = ((rows_need * 64 + 1023) / 1024) * 1024;
   p.ksize = keff;
   // shared-memory plan: [A stages][B slots][1 KB barriers][2 KB q buffers][2 KB s], 1 KB alignment slack
-  const int avail = HL_SMEM - 1024 - 1024 - 2048 - 2048;
+  // (+ 8 staging buffers behind s when the epilogue stores through TMA)
+  const int avail = HL_SMEM - 1024 - 1024 - 2048 - 2048 - (tma_store ? 8 * HL_STG_BUF : 0);
   const int a_stage = 3 * p.a_plane;
-  const int b_slot = 3 * nt * HL_KC * 2;
-  const int resident_slots = cblk * keff * keff;
+  const int b_slot = 3 * (kwc ? keff * nt : nt) * HL_KC * 2;
+  const int resident_slots = cblk * (kwc ? keff : keff * keff);
   if (p.tiles_n == 1 && resident_slots <= HL_MAX_BSLOTS && resident_slots * b_slot + 2 * a_stage <= avail) {
     p.b_resident = 1;
     p.sb = resident_slots;
@@ -911,13 +1157,28 @@ int conv_moments_halo_dispatch(const sn_tc_conv_desc* d, cudaStream_t stream) {
   const int cin = d->src_c[0] + d->src_c[1];
   const int cblk = cin / HL_KC;
 
-  const HaloTiling t = choose_tiling(d->batch, d->in_h, d->in_w, keff);
+  HaloTiling t = choose_tiling(d->batch, d->in_h, d->in_w, keff);
   SN_REQUIRE(t.eff > 0, SN_ERR_UNSUPPORTED, "conv_halo: no tiling for %dx%d k=%d", d->in_h, d->in_w, keff);
   SN_REQUIRE(d->cout <= 512, SN_ERR_UNSUPPORTED, "conv_halo: cout %d > 512", d->cout);
+  bool kwc = false;
+  if (nt == 32 && keff == 3 && !upconv) {
+    const HaloTiling tk = kwc_tiling(d->batch, d->in_h, d->in_w);
+    if (kwc_wanted(d->flags, nt, keff, d->in_w, cblk, t, tk)) { t = tk; kwc = true; }
+  }
 
+  static const bool tma_store_on = [] {
+    const char* e = getenv("SN_TMA_STORE");
+    return e == nullptr || e[0] != '0';
+  }();
+  bool tma_store = kwc && !dst_f32 && tma_store_on;
   HlP p{};
   int rc;
-  if ((rc = hl_plan(p, t, keff, ncols, nt, cblk))) return rc;
+  if (tma_store) {
+    // the 48 KB of staging must leave room for resident weights and >= 2 activation stages
+    HlP probe{};
+    if ((rc = hl_plan(probe, t, keff, ncols, nt, cblk, kwc, true)) || !probe.b_resident || probe.sa < 2) tma_store = false;
+  }
+  if ((rc = hl_plan(p, t, keff, ncols, nt, cblk, kwc, tma_store))) return rc;
   p.taps_w = taps_w;
   p.cblk_s[0] = d->src_c[0] / HL_KC; p.cblk_s[1] = d->src_c[1] / HL_KC;
   p.Ho = Ho; p.Wo = Wo; p.B = d->batch;
@@ -945,6 +1206,8 @@ int conv_moments_halo_dispatch(const sn_tc_conv_desc* d, cudaStream_t stream) {
   // regular: [3*taps][cout][cin]; up-conv: [3][4*cout][cin] (same memory, parity and channel fused into one axis)
   if ((rc = hl_make_weight_map(&maps.w, d->w_packed, upconv ? 1 : taps_w, upconv ? ncols : d->cout, cin, nt)))
     return rc;
+  maps.d = maps.w;
+  if (p.tma_store && (rc = hl_make_dst_map(&maps.d, d->dst, d->cout, out_h, out_w, d->batch, t.TWo))) return rc;
   switch (nt) {
     case 128: return hl_launch<128>(maps, p, stream);
     case 64: return hl_launch<64>(maps, p, stream);
@@ -974,13 +1237,18 @@ int conv_moments_halo_dgrad_dispatch(const sn_tc_dgrad_desc* d, cudaStream_t str
   const int nsrc = upconv ? 4 : 1;
   const int cblk = nsrc * d->cout / HL_KC;
 
-  const HaloTiling t = choose_tiling(d->batch, gh, gw, keff);
+  HaloTiling t = choose_tiling(d->batch, gh, gw, keff);
   SN_REQUIRE(t.eff > 0, SN_ERR_UNSUPPORTED, "conv_halo dgrad: no tiling for %dx%d k=%d", gh, gw, keff);
   SN_REQUIRE(d->cout <= 512, SN_ERR_UNSUPPORTED, "conv_halo dgrad: cout %d > 512", d->cout);
+  bool kwc = false;
+  if (nt == 32 && keff == 3 && !upconv) {
+    const HaloTiling tk = kwc_tiling(d->batch, gh, gw);
+    if (kwc_wanted(d->flags, nt, keff, gw, cblk, t, tk)) { t = tk; kwc = true; }
+  }
 
   HlP p{};
   int rc;
-  if ((rc = hl_plan(p, t, keff, ncols, nt, cblk))) return rc;
+  if ((rc = hl_plan(p, t, keff, ncols, nt, cblk, kwc))) return rc;
   p.taps_w = keff * keff;
   for (int s = 0; s < nsrc; ++s) p.cblk_s[s] = d->cout / HL_KC;
   p.pad = pad;
@@ -1010,6 +1278,7 @@ int conv_moments_halo_dgrad_dispatch(const sn_tc_dgrad_desc* d, cudaStream_t str
   }
   // transposed weights [3][taps][N = cin][K = nsrc * cout]
   if ((rc = hl_make_weight_map(&maps.w, d->wt_packed, keff * keff, ncols, nsrc * d->cout, nt))) return rc;
+  maps.d = maps.w;          // unused
   switch (nt) {
     case 128: return hl_launch_dgrad<128>(maps, p, stream);
     case 64: return hl_launch_dgrad<64>(maps, p, stream);

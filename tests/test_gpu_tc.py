@@ -71,14 +71,29 @@ TC_CASES = [
     (120, 30, 30, 64, 32, 3),  # ~6 tiles per persistent CTA, two channel blocks per tile, resident weights
     (40, 40, 40, 64, 64, 3),   # ~3.5 tiles per CTA, streamed weights (18 x 12 KB does not fit)
     (64, 24, 24, 128, 128, 3), # ~3 tiles per CTA, NT = 128, four channel blocks
+    # kw-concatenated variant (NT = 32, k = 3, width >= 32: 30-column tiles, taps of a filter row as UMMA N columns)
+    (2, 33, 32, 32, 32, 3),    # exactly one 32-wide halo box per row, 31 output rows (last tile row partial)
+    (1, 5, 40, 32, 32, 3),     # fewer output rows (3) than the tile's four quarters; second column tile nearly empty
+    (3, 36, 45, 64, 32, 3),    # two channel blocks, resident weights (6 slots)
+    (64, 50, 64, 128, 32, 3),  # four channel blocks: weights streamed through the slot ring, ~26 tiles per CTA
 ]
+
+
+def _kwc_eligible(case):
+    B, H, W, cin, cout, k = case
+    return k == 3 and cout % 64 != 0 and W >= 32
 
 
 @pytest.mark.parametrize("case", TC_CASES)
 @pytest.mark.parametrize("relu", [False, True])
-@pytest.mark.parametrize("im2col", [False, True], ids=["halo", "im2col"])
+@pytest.mark.parametrize("im2col", [False, True, "kwc", "nokwc"], ids=["halo", "im2col", "kwc", "nokwc"])
 def test_conv_tc_f32_dst(S, case, relu, im2col):
     F = S.fastops
+    kwc = None
+    if isinstance(im2col, str):            # the two halo variants, forced (SN_TC_KWC / SN_TC_NO_KWC)
+        if not _kwc_eligible(case):
+            pytest.skip("shape not eligible for the kw-concatenated kernel")
+        kwc, im2col = im2col == "kwc", False
     B, H, W, cin, cout, k = case
     mu, var, w, ws = rand_layer(B, H, W, cin, cout, k, seed=sum(case))
     m_ref, v_ref = O.conv_intermediate_conv_form(mu, var, w, ws)
@@ -89,7 +104,7 @@ def test_conv_tc_f32_dst(S, case, relu, im2col):
     Ho, Wo = H - k + 1, W - k + 1
     m = torch.full((B, Ho, Wo, cout), float("nan"), device="cuda")
     v = torch.full((B, Ho, Wo, cout), float("nan"), device="cuda")
-    F.conv_moments_tc(src, cin, B, H, W, k, cout, wp, s, relu=relu, dst_f32=(m, v), im2col=im2col)
+    F.conv_moments_tc(src, cin, B, H, W, k, cout, wp, s, relu=relu, dst_f32=(m, v), im2col=im2col, kwc=kwc)
     torch.cuda.synchronize()
     assert bool(torch.isfinite(m).all()) and bool(torch.isfinite(v).all())
     assert rel(m, m_ref) < MEAN_TOL, rel(m, m_ref)
@@ -122,6 +137,52 @@ def test_conv_tc_packed_window_concat(S, im2col):
     m, v = F.unpack_moments(out)
     assert rel(m, m_ref) < MEAN_TOL and rel(v, v_ref) < VAR_TOL
     assert torch.equal(v[:, 0].cpu(), torch.full_like(v[:, 0].cpu(), float(torch.tensor(0.1).bfloat16())))
+
+
+@pytest.mark.parametrize("shape", [(2, 12, 40), (3, 37, 70), (1, 6, 33)])
+@pytest.mark.parametrize("cin0", [32, 0], ids=["concat", "single"])
+def test_conv_tc_kwc_packed_window_concat(S, shape, cin0):
+    """The kw-concatenated 32-column kernel with a packed destination: rows leave through shared memory + TMA tensor
+    stores (SN_TMA_STORE=0: the direct 256-bit stores).  Two sources (decoder window + cropped encoder window), output
+    into the interior of a pre-filled padded buffer: the border must stay bit-exact, partial tiles (last tile column /
+    tile row) must be clipped, the second image must not be touched by the first one's boxes."""
+    F = S.fastops
+    B, H, W = shape
+    k, cout = 3, 32
+    mu_d, var_d, _, _ = rand_layer(B, H, W, 32, cout, k, seed=15)
+    mu_e, var_e, _, _ = rand_layer(B, H + 4, W + 4, 32, cout, k, seed=16)
+    _, _, w, ws = rand_layer(B, H, W, 32 + cin0, cout, k, seed=17)
+    if cin0:                    # two channel blocks: no room for the staging buffers -> direct stores
+        m_in, v_in = O.conc(mu_d, var_d, mu_e, var_e)
+    else:                       # one channel block: rows leave through shared memory + TMA stores
+        m_in, v_in = mu_e[:, 2:2 + H, 2:2 + W], var_e[:, 2:2 + H, 2:2 + W]
+    m_ref, v_ref = O.relu(*O.conv_intermediate_conv_form(m_in, v_in, w, ws))
+    m_ref, v_ref = O.padding(m_ref, v_ref, (2, 2), 0.1)
+    dbuf = F.pack_moments(dev(mu_d), dev(var_d))
+    ebuf = F.pack_moments(dev(mu_e), dev(var_e))
+    out = F.packed_empty(B, H - 2 + 4, W - 2 + 4, cout, "cuda")
+    F.packed_fill(out, 0.1)
+    wp, s = F.prepare_weights(dev(w), dev(ws))
+    def run(dst):
+        if cin0:
+            F.conv_moments_tc(F.PackedView(dbuf), 32, B, H, W, k, cout, wp, s, dst=dst, relu=True,
+                              src1=F.PackedView(ebuf, 2, 2, 0), c1=32, kwc=True)
+        else:
+            F.conv_moments_tc(F.PackedView(ebuf, 2, 2, 0), 32, B, H, W, k, cout, wp, s, dst=dst, relu=True, kwc=True)
+    run(F.PackedView(out, 2, 2, 0))
+    m, v = F.unpack_moments(out)
+    assert rel(m, m_ref) < MEAN_TOL and rel(v, v_ref) < VAR_TOL
+    fill = float(torch.tensor(0.1).bfloat16())
+    border = torch.ones_like(v, dtype=torch.bool)
+    border[:, 2:-2, 2:-2] = False
+    assert bool((v[border] == fill).all()) and bool((m[border] == 0).all())
+    # a destination that is a channel slice of a wider buffer (the store's tensor map carries the buffer's strides)
+    wide = F.packed_empty(B, H - 2, W - 2, 64, "cuda")
+    F.packed_fill(wide, 0.25)
+    run(F.PackedView(wide, 0, 0, 32))
+    mw, vw = F.unpack_moments(wide)
+    assert torch.equal(mw[..., 32:], m[:, 2:-2, 2:-2]) and torch.equal(vw[..., 32:], v[:, 2:-2, 2:-2])
+    assert bool((mw[..., :32] == 0).all()) and bool((vw[..., :32] == 0.25).all())
 
 
 @pytest.mark.parametrize("case", [(2, 6, 6, 64, 32), (1, 9, 7, 128, 64), (2, 5, 5, 256, 128), (3, 30, 41, 32, 32)])

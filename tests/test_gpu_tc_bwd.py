@@ -59,14 +59,19 @@ DGRAD_CASES = [
     (2, 70, 150, 32, 32, 3),    # column tiles, resident weights
     (40, 30, 30, 32, 64, 3),    # many tiles per persistent CTA
     (20, 24, 24, 128, 128, 3),  # streamed weights, NT = 128
+    (3, 36, 45, 32, 128, 3),    # kw-concatenated variant (N = cin = 32), K = 4 blocks: weights streamed
+    (2, 33, 30, 32, 32, 3),     # kw-concatenated: the zero-extended gradient is exactly one 32-wide box
 ]
 
 
 @pytest.mark.parametrize("case", DGRAD_CASES)
 @pytest.mark.parametrize("gate", [False, True])
-def test_conv_dgrad_tc(S, case, gate):
+@pytest.mark.parametrize("kwc", [None, True, False], ids=["auto", "kwc", "nokwc"])
+def test_conv_dgrad_tc(S, case, gate, kwc):
     F = S.fastops
     B, H, W, cin, cout, k = case
+    if kwc is not None and not (k == 3 and cin % 64 != 0 and W - k + 1 + 2 * (k - 1) >= 32):
+        pytest.skip("shape not eligible for the kw-concatenated kernel")
     mu_pre, var_pre, w, ws = layer(B, H, W, cin, cout, k, seed=sum(case))
     Ho, Wo = H - k + 1, W - k + 1
     gm = rnd((B, Ho, Wo, cout), 77)
@@ -82,12 +87,12 @@ def test_conv_dgrad_tc(S, case, gate):
     g_in.fill_(float("nan"))
     wt = F.prepare_weights_bwd(dev(w))
     _, s = F.prepare_weights(dev(w), dev(ws))
-    F.conv_moments_bwd_data_tc(g_out, B, H, W, k, cout, wt, s, saved, F.PackedView(g_in), cin, gate)
+    F.conv_moments_bwd_data_tc(g_out, B, H, W, k, cout, wt, s, saved, F.PackedView(g_in), cin, gate, kwc=kwc)
     a, b = F.unpack_moments(g_in)
     torch.cuda.synchronize()
     assert bool(torch.isfinite(a).all()) and bool(torch.isfinite(b).all())
     e_m, e_v = rel(a, mu_pre.grad), rel(b, var_pre.grad)
-    print(case, gate, e_m, e_v)
+    print(case, gate, kwc, e_m, e_v)
     assert e_m < G_TOL and e_v < G_TOL, (e_m, e_v)
     if gate:
         off = (mu_pre.detach() <= 0)

@@ -51,8 +51,8 @@ int main() {
     if (rowb == 64) cudaFuncSetAttribute(rate<64>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
     else cudaFuncSetAttribute(rate<128>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
     for (int same : {1, 0})
-      for (int N : {32, 64, 128, 256})
-        for (int shift : {0, 1, 8, 43}) {
+      for (int N : {32, 48, 64, 96, 128, 192, 256})
+        for (int shift : {0, 43}) {
           if (rowb == 64) rate<64><<<1, 128, smem>>>(N, shift, iters, same, d);
           else rate<128><<<1, 128, smem>>>(N, shift, iters, same, d);
           cudaError_t e = cudaDeviceSynchronize();
