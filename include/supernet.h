@@ -216,6 +216,13 @@ int sn_first_conv_fwd_packed(int32_t batch, int32_t in_h, int32_t in_w, int32_t 
 /* mymaxpooling (Brats.py:171-174) on an in_h x in_w x c packed window -> packed window (2x2/2, SAME). */
 int sn_maxpool2_packed(const sn_packed_view* src, int32_t batch, int32_t in_h, int32_t in_w, int32_t c,
                        const sn_packed_view* dst, sn_stream_t st);
+/* myReLU.call (Brats.py:233-238) on a packed window: mean = hi + lo; where mean > 0 (strict, TF ReluGrad) the three
+ * planes are copied, elsewhere all three are zero.  gate = 0: plain window-to-window copy (mypadding / crop of a tensor
+ * that is already in memory).  src and dst windows are h x w x c (c % 8 == 0); in place is allowed when they coincide.
+ * The engines never call this (the gate is a conv-epilogue flag); the layer-by-layer FAST API does. */
+int sn_relu_packed(const sn_packed_view* src, int32_t batch, int32_t h, int32_t w, int32_t c,
+                   const sn_packed_view* dst, int32_t gate, sn_stream_t stream);
+
 /* conv_final (k = 1, Brats.py:367,454) fused with mysoftmax (Brats.py:269-283): packed window in (cin == 32),
  * fp32 [batch*in_h*in_w, n_labels] probabilities and variances out; presoftmax_{mu,var} optional (may be NULL). */
 int sn_final_conv_softmax_packed(const sn_packed_view* src, int32_t batch, int32_t in_h, int32_t in_w, int32_t cin,

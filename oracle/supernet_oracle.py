@@ -391,20 +391,34 @@ class UNetOracle:
         f = conv_intermediate_as_written if self.form == "as_written" else conv_intermediate_conv_form
         return f(mu, var, *self.weights[name])
 
-    def forward(self, x: Tensor, return_presoftmax: bool = False, taps: Optional[dict] = None):
-        """call(), Brats.py:377-457 / Hippocampus.py:373-421."""
+    def forward(self, x: Tensor, return_presoftmax: bool = False, taps: Optional[dict] = None,
+                trajectory: Optional[Dict[str, Tuple[Tensor, Tensor]]] = None):
+        """call(), Brats.py:377-457 / Hippocampus.py:373-421.
+
+        ``trajectory`` (layer name -> post-activation (mean, variance) another implementation computed for the same
+        input) re-runs the graph ON THAT FORWARD TRAJECTORY: every conv output takes the given value (straight-through:
+        the autograd formulas stay this function's) and every ReLU gate / pooling arg-max is decided by the given
+        values.  Autograd through it is the exact gradient arithmetic given those decisions, which separates "the
+        other forward flipped a gate" from "the other backward is inaccurate" in a gradient comparison."""
         x = x.to(self.dtype)
         fill = self.sigma_fill
         levels = 4 if self.variant == "brats" else 2
 
-        def tap(name, m, s):
+        def post(name, m, s, has_relu):
+            if trajectory is None or name not in trajectory:
+                m, s = relu(m, s) if has_relu else (m, s)
+            else:
+                mf, sf = (t.to(self.dtype) for t in trajectory[name])
+                if has_relu:
+                    gate = (mf > 0).to(self.dtype)
+                    m, s = m * gate, s * gate
+                m, s = m + (mf - m).detach(), s + (sf - s).detach()
             if taps is not None:
                 taps[name] = (m.detach(), s.detach())
+            return m, s
 
-        m, s = self._first(x)
-        m, s = relu(m, s); tap("conv_input", m, s)
-        m, s = self._conv("conv1", m, s)
-        m, s = relu(m, s); tap("conv1", m, s)
+        m, s = post("conv_input", *self._first(x), True)
+        m, s = post("conv1", *self._conv("conv1", m, s), True)
         skips = [(m, s)]
         ci = 2
         for lvl in range(1, levels + 1):
@@ -413,23 +427,20 @@ class UNetOracle:
                 m, s = padding(m, s, (1, 0), fill)                         # mypad1, Brats.py:407
             for _ in range(2):
                 name = f"conv{ci}"
-                m, s = self._conv(name, m, s)
-                m, s = relu(m, s); tap(name, m, s)
+                m, s = post(name, *self._conv(name, m, s), True)
                 ci += 1
             if lvl < levels:
                 skips.append((m, s))
         for d in range(1, levels + 1):
             me, se = skips[levels - d]
             m, s = upsampling(m, s)
-            m, s = self._conv(f"up{d}_conv2x2", m, s); tap(f"up{d}_conv2x2", m, s)
+            m, s = post(f"up{d}_conv2x2", *self._conv(f"up{d}_conv2x2", m, s), False)
             m, s = padding(m, s, (3, 3), fill)                             # mypad_up6
             m, s = conc(m, s, me, se)
-            m, s = self._conv(f"up{d}_conv1", m, s)
-            m, s = relu(m, s); tap(f"up{d}_conv1", m, s)
+            m, s = post(f"up{d}_conv1", *self._conv(f"up{d}_conv1", m, s), True)
             m, s = padding(m, s, (2, 2), fill)                             # mypad
-            m, s = self._conv(f"up{d}_conv2", m, s)
-            m, s = relu(m, s); tap(f"up{d}_conv2", m, s)
-        mf, sf = self._conv("conv_final", m, s); tap("conv_final", mf, sf)
+            m, s = post(f"up{d}_conv2", *self._conv(f"up{d}_conv2", m, s), True)
+        mf, sf = post("conv_final", *self._conv("conv_final", m, s), False)
         sm = softmax_as_written if self.form == "as_written" else softmax_closed_form
         p, v = sm(mf, sf)
         if return_presoftmax:
@@ -439,21 +450,21 @@ class UNetOracle:
     __call__ = forward
 
     # -- losses (Brats.py:569-596) ------------------------------------------------------
-    def elbo_loss(self, x: Tensor, y_onehot: Tensor, kl_factor: float = 1e-5) -> Tensor:
+    def elbo_loss(self, x: Tensor, y_onehot: Tensor, kl_factor: float = 1e-5, trajectory=None) -> Tensor:
         """train_on_batch loss, Brats.py:572-576."""
-        p, v = self.forward(x)
+        p, v = self.forward(x, trajectory=trajectory)
         nll = nll_gaussian(y_onehot.to(self.dtype), p, torch.clamp(v, 1e-12, 1e3))
         return nll + kl_factor * 0.5 * self.regularization()
 
-    def adversarial_loss(self, x: Tensor, y_onehot: Tensor) -> Tensor:
+    def adversarial_loss(self, x: Tensor, y_onehot: Tensor, trajectory=None) -> Tensor:
         """create_adversarial_pattern loss, Brats.py:587-590: 0.5 * NLL with clip [-1e4, 1e3]."""
-        p, v = self.forward(x)
+        p, v = self.forward(x, trajectory=trajectory)
         return 0.5 * nll_gaussian(y_onehot.to(self.dtype), p, torch.clamp(v, -1e4, 1e3))
 
-    def fgsm_gradient(self, x: Tensor, y_onehot: Tensor) -> Tuple[Tensor, Tensor]:
+    def fgsm_gradient(self, x: Tensor, y_onehot: Tensor, trajectory=None) -> Tuple[Tensor, Tensor]:
         """Brats.py:583-596: returns (d loss / d x, loss)."""
         x = x.detach().clone().to(self.dtype).requires_grad_(True)
-        loss = self.adversarial_loss(x, y_onehot)
+        loss = self.adversarial_loss(x, y_onehot, trajectory=trajectory)
         (g,) = torch.autograd.grad(loss, x)
         return g, loss.detach()
 

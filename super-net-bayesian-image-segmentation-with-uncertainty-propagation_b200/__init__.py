@@ -6,9 +6,10 @@ The directory name carries the reference's name and is not a valid identifier; i
 `supernet_b200` shim at the repo root.
 """
 from . import _lib, build, ops  # noqa: F401
-from .layers import (Density_prop_with_pad_UNET, create_adversarial_pattern, myConc, myConv_input,  # noqa: F401
-                     myConv_intermediate, mymaxpooling, mypadding, myReLU, mysoftmax, myupsampling, nll_gaussian,
-                     sigma_regularizer)
+from .fastlayers import PackedMoments  # noqa: F401
+from .layers import (Density_prop_with_pad_UNET, create_adversarial_pattern, fast_mode, myConc,  # noqa: F401
+                     myConv_input, myConv_intermediate, mymaxpooling, mypadding, myReLU, mysoftmax, myupsampling,
+                     nll_gaussian, set_default_mode, sigma_regularizer)
 
 
 
@@ -19,6 +20,7 @@ def available_modes():
     return ["fp32"] + (["fast"] if hasattr(lib, "sn_conv_moments_fwd_tc") else [])
 
 
-__all__ = ["available_modes", "Density_prop_with_pad_UNET", "create_adversarial_pattern", "myConc", "myConv_input",
+__all__ = ["available_modes", "fast_mode", "set_default_mode", "PackedMoments", "Density_prop_with_pad_UNET",
+           "create_adversarial_pattern", "myConc", "myConv_input",
            "myConv_intermediate", "mymaxpooling", "mypadding", "myReLU", "mysoftmax", "myupsampling",
            "nll_gaussian", "sigma_regularizer", "ops", "build"]

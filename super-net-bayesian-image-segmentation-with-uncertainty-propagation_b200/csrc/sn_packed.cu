@@ -571,6 +571,49 @@ __global__ void maxpool_packed_kernel(sn_packed_view src, int B, int H, int W, i
   }
 }
 
+
+// ---------------------------------------------------------------------------------------------------------
+// myReLU (Brats.py:233-238) / plain window copy on packed windows; thread = (pixel, 8 channels).  Inside the engines the
+// gate is a conv-epilogue flag and windows are address arithmetic; this kernel serves the layer-by-layer FAST API when a
+// ReLU or a pad follows something that is already in memory (fastlayers.py).
+// ---------------------------------------------------------------------------------------------------------
+__global__ void relu_copy_packed_kernel(sn_packed_view src, int B, int H, int W, int c, sn_packed_view dst, int gate) {
+  const int g = c / 8;
+  const size_t total = (size_t)B * H * W * g;
+  const size_t stride = (size_t)gridDim.x * blockDim.x;
+  const __nv_bfloat16* in = reinterpret_cast<const __nv_bfloat16*>(src.base);
+  __nv_bfloat16* out = reinterpret_cast<__nv_bfloat16*>(dst.base);
+  for (size_t i = blockIdx.x * (size_t)blockDim.x + threadIdx.x; i < total; i += stride) {
+    const int c8 = (int)(i % g) * 8;
+    size_t t = i / g;
+    const int x = (int)(t % W);
+    t /= W;
+    const int y = (int)(t % H);
+    const int b = (int)(t / H);
+    const __nv_bfloat16* sp = in + ((((size_t)b * src.h + y + src.y0) * src.w + x + src.x0) * 3) * src.c + src.c0 + c8;
+    uint4 h = *reinterpret_cast<const uint4*>(sp);
+    uint4 l = *reinterpret_cast<const uint4*>(sp + src.c);
+    uint4 v = *reinterpret_cast<const uint4*>(sp + 2 * src.c);
+    if (gate) {
+      uint32_t hw[4] = {h.x, h.y, h.z, h.w}, lw[4] = {l.x, l.y, l.z, l.w}, vw[4] = {v.x, v.y, v.z, v.w};
+#pragma unroll
+      for (int e = 0; e < 4; ++e) {
+        // strict mean > 0 (TF ReluGrad), mean = hi + lo
+        const uint32_t k0 = (blo(hw[e]) + blo(lw[e])) > 0.f ? 0x0000FFFFu : 0u;
+        const uint32_t k1 = (bhi(hw[e]) + bhi(lw[e])) > 0.f ? 0xFFFF0000u : 0u;
+        hw[e] &= k0 | k1; lw[e] &= k0 | k1; vw[e] &= k0 | k1;
+      }
+      h = make_uint4(hw[0], hw[1], hw[2], hw[3]);
+      l = make_uint4(lw[0], lw[1], lw[2], lw[3]);
+      v = make_uint4(vw[0], vw[1], vw[2], vw[3]);
+    }
+    __nv_bfloat16* o = out + ((((size_t)b * dst.h + y + dst.y0) * dst.w + x + dst.x0) * 3) * dst.c + dst.c0 + c8;
+    *reinterpret_cast<uint4*>(o) = h;
+    *reinterpret_cast<uint4*>(o + dst.c) = l;
+    *reinterpret_cast<uint4*>(o + 2 * dst.c) = v;
+  }
+}
+
 // Same, 16 channels per thread through 256-bit accesses (one full 32-byte sector per lane and instruction): the
 // variant used whenever the views are 32-byte aligned (every buffer of the engines is).
 __global__ void maxpool_packed16_kernel(sn_packed_view src, int B, int H, int W, int c, sn_packed_view dst) {
@@ -891,6 +934,17 @@ int sn_maxpool2_packed(const sn_packed_view* src, int32_t batch, int32_t in_h, i
   const size_t total = (size_t)batch * Ho * Wo * (c / 8);
   maxpool_packed_kernel<<<ew_grid(total, 256), 256, 0, as_stream(st)>>>(*src, batch, in_h, in_w, c, *dst);
   return check_launch("maxpool_packed");
+}
+
+int sn_relu_packed(const sn_packed_view* src, int32_t batch, int32_t h, int32_t w, int32_t c,
+                   const sn_packed_view* dst, int32_t gate, sn_stream_t st) {
+  SN_REQUIRE(batch > 0 && h > 0 && w > 0 && c > 0, SN_ERR_BAD_ARG, "relu_packed: bad shape");
+  int rc = check_pview(src, batch, h, w, c, "relu_packed src");
+  if (rc) return rc;
+  if ((rc = check_pview(dst, batch, h, w, c, "relu_packed dst"))) return rc;
+  const size_t total = (size_t)batch * h * w * (c / 8);
+  relu_copy_packed_kernel<<<ew_grid(total, 256), 256, 0, as_stream(st)>>>(*src, batch, h, w, c, *dst, gate ? 1 : 0);
+  return check_launch("relu_packed");
 }
 
 int sn_final_conv_softmax_packed(const sn_packed_view* src, int32_t batch, int32_t in_h, int32_t in_w, int32_t cin,

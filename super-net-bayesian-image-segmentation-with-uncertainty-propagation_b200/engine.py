@@ -222,6 +222,24 @@ class InferenceEngine:
             self._graph.replay()
         return self.p, self.v
 
+    def saved_activations(self):
+        """layer name -> (mean, variance) fp32 NHWC of every conv output as this engine last computed it (post-ReLU
+        where the layer has one; the interior of padded buffers).  What the layer-by-layer reference API would have
+        returned at that point; used by the gradient tests to tell forward-decision errors from backward errors."""
+        out = {}
+        for r in self.records:
+            if r["kind"] == "first":
+                name, v = "conv_input", r["dst"]
+                oh, ow, c = v.buf.shape[1], v.buf.shape[2], v.buf.shape[4]
+            elif r["kind"] == "conv":
+                name, v, c = r["name"], r["dst"], r["cout"]
+                oh, ow = (2 * r["h"], 2 * r["w"]) if r["upconv"] else (r["h"] - r["k"] + 1, r["w"] - r["k"] + 1)
+            else:
+                continue
+            t = v.buf[:, v.y0:v.y0 + oh, v.x0:v.x0 + ow, :, v.c0:v.c0 + c].float()
+            out[name] = (t[..., 0, :] + t[..., 1, :], t[..., 2, :])
+        return out
+
     def run(self, x: Tensor, return_presoftmax: bool = False):
         if not self.matches(x):
             raise RuntimeError(f"engine built for input {self.shape}, got {tuple(x.shape)}")

@@ -17,9 +17,41 @@ from typing import Dict, List, Optional, Sequence, Tuple
 import torch
 from torch import nn
 
+import contextlib
+
+from . import fastlayers as FL
 from . import ops
 
 Tensor = torch.Tensor
+
+# ---- execution mode of the per-layer API -------------------------------------------------------------------
+# 'fp32': CUDA-core fp32 kernels with autograd (1e-5 parity, training through torch autograd).
+# 'fast': tcgen05 tensor-core kernels on packed moments (inference; fastlayers.py).  The mode is chosen where the
+# pair (mean, sigma) is BORN -- myConv_input -- and every later layer follows the kind of pair it is handed.
+_DEFAULT_MODE = "fp32"
+
+
+def set_default_mode(mode: str) -> None:
+    """Mode of myConv_input layers constructed without an explicit `mode=`."""
+    global _DEFAULT_MODE
+    if mode not in ("fp32", "fast"):
+        raise ValueError("mode must be 'fp32' or 'fast'")
+    _DEFAULT_MODE = mode
+
+
+def get_default_mode() -> str:
+    return _DEFAULT_MODE
+
+
+@contextlib.contextmanager
+def fast_mode(enabled: bool = True):
+    """with fast_mode(): ...  -- layer-by-layer code (Brats.py:379-455 style) runs on the tensor cores."""
+    prev = _DEFAULT_MODE
+    set_default_mode("fast" if enabled else "fp32")
+    try:
+        yield
+    finally:
+        set_default_mode(prev)
 
 
 def _truncated_normal_(t: Tensor, mean: float, std: float, gen: Optional[torch.Generator] = None) -> Tensor:
@@ -82,13 +114,19 @@ class myConv_input(_MomentConv):
     mu = x (*) w_mu;  sigma[b,i,j,n] = softplus(w_sigma[n]) * sum_{patch} x^2."""
 
     def __init__(self, kernel_num=128, kernel_size=3, kernel_stride=1, padding="VALID", mean_mu=0, mean_sigma=0.1,
-                 sigma_min=-12, sigma_max=-4.6, in_channels: Optional[int] = None):
+                 sigma_min=-12, sigma_max=-4.6, in_channels: Optional[int] = None, mode: Optional[str] = None):
         super().__init__(kernel_num, kernel_size, kernel_stride, padding, mean_mu, mean_sigma, sigma_min, sigma_max,
                          in_channels, "w_mu1", "w_sigma1")
+        if mode not in (None, "fp32", "fast"):
+            raise ValueError("mode must be None, 'fp32' or 'fast'")
+        self.mode = mode            # None: layers.get_default_mode() at call time
 
     def forward(self, inputs: Tensor):
         if not self.built:
             self._build(inputs.shape[-1], inputs.device)
+        if (self.mode or _DEFAULT_MODE) == "fast":
+            m, s = FL.conv_input(self, inputs)
+            return FL.relu(m, s) if self.fuse_relu else (m, s)
         return ops.conv_moments(inputs, None, self.w_mu1, self.w_sigma1, self.fuse_relu)
 
 
@@ -102,6 +140,8 @@ class myConv_intermediate(_MomentConv):
                          in_channels, "w_mu", "w_sigma")
 
     def forward(self, inputs: Tensor, sigma_input: Tensor):
+        if FL.is_handle(inputs):                     # FAST mode: the pair is a packed-moments handle
+            return FL.conv_intermediate(self, inputs, sigma_input)
         if not self.built:
             self._build(inputs.shape[-1], inputs.device)
         return ops.conv_moments(inputs, sigma_input, self.w_mu, self.w_sigma, self.fuse_relu)
@@ -111,6 +151,8 @@ class myupsampling(nn.Module):
     """Zero-stuffing up-sampling of both moments to 2H+1 (Brats.py:140-148, unpool :178-203)."""
 
     def forward(self, mu_in: Tensor, sigma_in: Tensor):
+        if FL.is_handle(mu_in):
+            return FL.upsampling(mu_in, sigma_in)
         return ops.unpool(mu_in), ops.unpool(sigma_in)
 
 
@@ -126,6 +168,8 @@ class mypadding(nn.Module):
         self.mode = "CONSTANT"
 
     def forward(self, mu_in: Tensor, sigma_in: Tensor):
+        if FL.is_handle(mu_in):
+            return FL.padding(self, mu_in, sigma_in)
         a, b = self.pad_size
         return ops.pad_hw(mu_in, a, b, 0.0), ops.pad_hw(sigma_in, a, b, self.sigma_fill)
 
@@ -134,6 +178,8 @@ class mymaxpooling(nn.Module):
     """2x2/2 max-pool of the mean; the variance is taken at the arg-max (Brats.py:166-174, 206-216)."""
 
     def forward(self, mu_in: Tensor, sigma_in: Tensor):
+        if FL.is_handle(mu_in):
+            return FL.maxpooling(mu_in, sigma_in)
         return ops.maxpool2_moments(mu_in, sigma_in)
 
 
@@ -141,6 +187,8 @@ class myReLU(nn.Module):
     """mu -> relu(mu), sigma -> sigma * 1[mu > 0] (Brats.py:227-238)."""
 
     def forward(self, mu_in: Tensor, Sigma_in: Tensor):
+        if FL.is_handle(mu_in):
+            return FL.relu(mu_in, Sigma_in)
         return ops.relu_moments(mu_in, Sigma_in)
 
 
@@ -148,6 +196,8 @@ class myConc(nn.Module):
     """Centre-crop the encoder moments to the decoder size and concat [decoder, encoder] (Brats.py:241-261)."""
 
     def forward(self, muD: Tensor, SigmaD: Tensor, muE: Tensor, SigmaE: Tensor):
+        if FL.is_handle(muD):
+            return FL.conc(muD, SigmaD, muE, SigmaE)
         return ops.crop_concat(muD, muE), ops.crop_concat(SigmaD, SigmaE)
 
 
@@ -155,6 +205,8 @@ class mysoftmax(nn.Module):
     """Softmax over classes with Jacobian-propagated variance, flattened to [B, H*W, C] (Brats.py:264-283)."""
 
     def forward(self, mu_in: Tensor, sigma_in: Tensor):
+        if FL.is_handle(mu_in):
+            return FL.softmax(mu_in, sigma_in)
         B, Cc = mu_in.shape[0], mu_in.shape[-1]
         p, v = ops.softmax_moments(mu_in, sigma_in)
         return p.reshape(B, -1, Cc), v.reshape(B, -1, Cc)
@@ -338,10 +390,24 @@ class Density_prop_with_pad_UNET(nn.Module):
             m, s = self.mypad(m, s)                                  # :420
             m, s = self._cr(f"up{d}_conv2", m, s)                    # :421-422
         mf, sf = self.conv_final(m, s)                               # :454
+        if FL.is_handle(mf) and return_presoftmax:                   # FAST handles: one fused launch gives all four
+            p, v, pre = mf.run(True)
+            return p, v, pre[0], pre[1]
         outputs, Sigma = self.mysoft(mf, sf)                         # :455
         if return_presoftmax:
             return outputs, Sigma, mf, sf
         return outputs, Sigma
+
+    def forward_layerwise_fast(self, x: Tensor, return_presoftmax: bool = False):
+        """The same graph as _forward_fp32 -- one reference-style layer call after the other -- with the pair travelling
+        as a packed-moments handle (fastlayers.py): every conv is a tcgen05 launch, eager, no engine, no CUDA graph."""
+        prev = self.conv_input.mode
+        self.conv_input.mode = "fast"
+        try:
+            with torch.no_grad():
+                return self._forward_fp32(x, return_presoftmax)
+        finally:
+            self.conv_input.mode = prev
 
     def _forward_fast(self, x: Tensor, return_presoftmax: bool = False):
         from .engine import InferenceEngine

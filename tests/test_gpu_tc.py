@@ -156,8 +156,14 @@ def test_conv_tc_kwc_packed_window_concat(S, shape, cin0):
         m_in, v_in = O.conc(mu_d, var_d, mu_e, var_e)
     else:                       # one channel block: rows leave through shared memory + TMA stores
         m_in, v_in = mu_e[:, 2:2 + H, 2:2 + W], var_e[:, 2:2 + H, 2:2 + W]
-    m_ref, v_ref = O.relu(*O.conv_intermediate_conv_form(m_in, v_in, w, ws))
+    m_pre, v_pre = O.conv_intermediate_conv_form(m_in, v_in, w, ws)
+    m_ref, v_ref = O.relu(m_pre, v_pre)
     m_ref, v_ref = O.padding(m_ref, v_ref, (2, 2), 0.1)
+    # a pre-activation mean within rounding of zero may be gated differently than in fp64 (one such element, +2e-6 vs
+    # -1e-7, carries a variance of 51 in the (3, 37, 70) case): those few elements are excluded from the variance norm
+    near0 = torch.zeros_like(v_ref, dtype=torch.bool)
+    near0[:, 2:-2, 2:-2] = m_pre.abs() < 1e-5 * m_pre.abs().max()
+    assert float(near0.double().mean()) < 1e-4
     dbuf = F.pack_moments(dev(mu_d), dev(var_d))
     ebuf = F.pack_moments(dev(mu_e), dev(var_e))
     out = F.packed_empty(B, H - 2 + 4, W - 2 + 4, cout, "cuda")
@@ -171,7 +177,7 @@ def test_conv_tc_kwc_packed_window_concat(S, shape, cin0):
             F.conv_moments_tc(F.PackedView(ebuf, 2, 2, 0), 32, B, H, W, k, cout, wp, s, dst=dst, relu=True, kwc=True)
     run(F.PackedView(out, 2, 2, 0))
     m, v = F.unpack_moments(out)
-    assert rel(m, m_ref) < MEAN_TOL and rel(v, v_ref) < VAR_TOL
+    assert rel(m, m_ref) < MEAN_TOL and rel(v.cpu()[~near0], v_ref[~near0]) < VAR_TOL
     fill = float(torch.tensor(0.1).bfloat16())
     border = torch.ones_like(v, dtype=torch.bool)
     border[:, 2:-2, 2:-2] = False

@@ -254,13 +254,19 @@ def _fgsm_fast_vs_oracle(S, variant, C, in_ch, B, alpha):
     torch.cuda.synchronize()
     assert torch.equal(g, g2)
     loss, _ = model.input_gradient_fast(dev(x), dev(y))
+    # the same gradient by exact (fp64) arithmetic on the FAST forward's trajectory: its conv outputs, its ReLU gates,
+    # its pooling arg-max decisions (UNetOracle.forward(trajectory=...))
+    traj = {k: (m.cpu(), v.cpu()) for k, (m, v) in model.grad_engine_for(dev(x)).saved_activations().items()}
+    g_traj, _ = oracle.fgsm_gradient(x, y, trajectory=traj)
     big = g_ref.abs() > 1e-3 * g_ref.abs().max()
     agree = float((torch.sign(g_ref)[big] == sign.cpu().double()[big]).double().mean())
-    err = rel(g, g_ref)
-    print(variant, "input-gradient rel", err, "sign agreement", agree, "loss", float(loss), float(loss_ref))
+    err, err_bwd, err_fwd = rel(g, g_ref), rel(g, g_traj), rel(g_traj, g_ref)
+    print(variant, "input-gradient rel", err, "= backward arithmetic", err_bwd, "+ forward decisions", err_fwd,
+          "sign agreement", agree, "loss", float(loss), float(loss_ref))
     assert g.shape == x.shape and bool(torch.isfinite(g).all())
     assert abs(float(loss) - float(loss_ref)) < 2e-3 * abs(float(loss_ref))
-    assert err < 1e-2, err
+    assert err_bwd < 1e-3, err_bwd          # the tensor-core backward chain itself (measured 7e-5 at BraTS depth)
+    assert err < 1e-2, err                  # end to end, SURVEY.md 8d
     assert agree >= 0.99, agree
 
 
@@ -269,10 +275,13 @@ def test_hippocampus_fgsm_fast(S):
 
 
 def test_brats_fgsm_fast(S):
-    # 23 layers deep the error is dominated by ReLU-gate / arg-max decisions that differ from the fp64 oracle's: a
-    # fraction f of flipped gates is a relative L2 error of sqrt(f) in that layer's gradient (measured: switching only
-    # the first convolution from fp32 to bf16 hi/lo operands moves this number from 9.2e-3 to 1.2e-2, which is why the
-    # gradient engine keeps that layer fp32-exact).  The sign, which is what FGSM consumes, agrees to 99.94 %.
+    # 23 layers deep the end-to-end error (9.2e-3) is ENTIRELY the forward's: the bf16x3 activations carry ~1e-5
+    # relative error, a few ReLU gates / pooling arg-max decisions near zero differ from the fp64 oracle's, and a
+    # fraction f of flipped gates is a relative L2 error of sqrt(f) in that layer's gradient.  On the FAST forward's
+    # own trajectory the tensor-core backward matches exact arithmetic to 7e-5 (tools/grad_error_split.py,
+    # profiles/r02_grad_error_split.md), so wider gradient planes would not move the number; only a more accurate
+    # forward would (which is why the gradient engine keeps the first convolution fp32-exact: 1.2e-2 -> 9.2e-3).
+    # The sign, which is what FGSM consumes, agrees to 99.94 %.
     _fgsm_fast_vs_oracle(S, "brats", 4, 4, 1, O.BRATS_ALPHA)
 
 
@@ -400,27 +409,36 @@ def _elbo_grads_fast_vs_oracle(S, variant, C, in_ch, B, alpha, kl):
     rg = torch.autograd.grad(ref, oracle.parameters())
     trainer = dp.DataParallelTrainer(model, lr=0.0, kl_factor=kl)      # lr 0: gradients only
     loss = trainer._fast_backward(dev(x), dev(y))
+    # exact arithmetic on the FAST forward's trajectory (its conv outputs, ReLU gates, arg-max decisions)
+    traj = {k: (m.cpu(), v.cpu()) for k, (m, v) in trainer._engine.saved_activations().items()}
+    tg = torch.autograd.grad(oracle.elbo_loss(x, y, kl_factor=kl, trajectory=traj), oracle.parameters())
     params = [p for c in model.convs() for p in c.weights()]
-    errs = {}
-    for (name, kind), a, b in zip([(n, k) for n in model.conv_names for k in ("w_mu", "w_sigma")], params, rg):
+    errs, errs_bwd = {}, {}
+    for (name, kind), a, b, t in zip([(n, k) for n in model.conv_names for k in ("w_mu", "w_sigma")], params, rg, tg):
         errs[f"{name}.{kind}"] = rel(a.grad, b)
-    worst = max(errs, key=errs.get)
-    print(variant, "loss", float(loss), float(ref), "worst", worst, errs[worst])
-    print({k: round(v, 5) for k, v in errs.items()})
+        errs_bwd[f"{name}.{kind}"] = rel(a.grad, t)
+    worst, worst_b = max(errs, key=errs.get), max(errs_bwd, key=errs_bwd.get)
+    print(variant, "loss", float(loss), float(ref), "worst vs oracle", worst, errs[worst],
+          "worst vs exact arithmetic on the FAST trajectory", worst_b, errs_bwd[worst_b])
+    print({k: (round(v, 5), round(errs_bwd[k], 5)) for k, v in errs.items()})
     assert abs(float(loss) - float(ref)) < 2e-3 * abs(float(ref))
-    return errs
+    return errs, errs_bwd
 
 
 @pytest.mark.parametrize("C", [3, 5])            # 5 = the class count of Brats.py:464
 def test_hippocampus_elbo_gradients_fast(S, C):
-    errs = _elbo_grads_fast_vs_oracle(S, "hippocampus", C, 1, 4, 1.0, 1e-3)
+    errs, errs_bwd = _elbo_grads_fast_vs_oracle(S, "hippocampus", C, 1, 4, 1.0, 1e-3)
     assert max(errs.values()) < 1e-2, errs
+    assert max(errs_bwd.values()) < 1e-2, errs_bwd
 
 
 def test_brats_elbo_gradients_fast(S):
-    errs = _elbo_grads_fast_vs_oracle(S, "brats", 4, 4, 1, O.BRATS_ALPHA, 1e-5)
-    # 23 layers deep the bf16 variance-gradient plane and the gate / arg-max flips of the bf16x3 forward compound
-    # (the input gradient of the same network sits at 9e-3): 2e-2 per tensor at BraTS depth
+    errs, errs_bwd = _elbo_grads_fast_vs_oracle(S, "brats", 4, 4, 1, O.BRATS_ALPHA, 1e-5)
+    # SURVEY.md 8d's 1e-2 per tensor holds for the backward chain itself (gradients vs exact arithmetic on the FAST
+    # forward's trajectory).  Against the fp64 oracle's own trajectory the gate / arg-max decisions of the bf16x3
+    # forward add their sqrt(flipped fraction) on top (the input gradient of the same network: 9.2e-3, of which 7e-5
+    # is the backward's), which takes the worst tensor (one w_sigma) to 1.8e-2: bar 2e-2 there.
+    assert max(errs_bwd.values()) < 1e-2, errs_bwd
     assert max(errs.values()) < 2e-2, errs
 
 

@@ -237,3 +237,32 @@ def test_golden_fixtures_match_oracle():
     mu, var, w, ws = (torch.from_numpy(lay[k]) for k in ("mu", "var", "w", "ws"))
     m, vv = O.conv_intermediate_conv_form(mu, var, w, ws)
     assert np.allclose(m.numpy(), lay["m_out"], rtol=1e-12) and np.allclose(vv.numpy(), lay["v_out"], rtol=1e-12)
+
+
+def test_forward_on_own_trajectory_is_the_identity():
+    """UNetOracle.forward(trajectory=...) with the oracle's own layer outputs reproduces outputs and gradients; with a
+    trajectory whose gates differ, the gates of the TRAJECTORY decide (the straight-through construction the FAST-mode
+    gradient tests rely on)."""
+    orc = O.UNetOracle("hippocampus", 32, 3, 1, torch.float64)
+    x = O.make_input("hippocampus", 1)
+    y = O.make_labels(1, 54 * 54, 3, dtype=torch.float64)
+    taps = {}
+    p0, v0 = orc.forward(x, taps=taps)
+    p1, v1 = orc.forward(x, trajectory=taps)
+    assert torch.allclose(p0, p1, atol=1e-14) and torch.allclose(v0, v1, atol=1e-14)
+    g0, l0 = orc.fgsm_gradient(x, y)
+    g1, l1 = orc.fgsm_gradient(x, y, trajectory=taps)
+    assert O.rel_l2(g1, g0) < 1e-12 and abs(float(l0) - float(l1)) < 1e-14
+    # close one open gate of conv1 in the trajectory: that unit's output and gradient path must vanish
+    m, s = taps["conv1"]
+    idx = (m > 0).nonzero()[0]
+    m2, s2 = m.clone(), s.clone()
+    m2[tuple(idx)] = 0.0
+    s2[tuple(idx)] = 0.0
+    t2 = dict(taps)
+    t2["conv1"] = (m2, s2)
+    taps2 = {}
+    orc.forward(x, taps=taps2, trajectory=t2)
+    assert float(taps2["conv1"][0][tuple(idx)]) == 0.0
+    g2, _ = orc.fgsm_gradient(x, y, trajectory=t2)
+    assert O.rel_l2(g2, g0) > 0
