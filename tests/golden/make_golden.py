@@ -34,6 +34,13 @@ def main():
     m, vv = O.conv_intermediate_as_written(mu, var, w, ws)
     np.savez_compressed(os.path.join(HERE, "layers_fp64.npz"), mu=mu.numpy(), var=var.numpy(), w=w.numpy(),
                         ws=ws.numpy(), m_out=m.numpy(), v_out=vv.numpy())
+    # a Keras-3 `.weights.h5` checkpoint in the reference model's layout (Brats.py:732): Hippocampus graph at
+    # n_kernels = 8 (147 KB), attribute-named layer groups, written by the in-repo HDF5 writer (no h5py here)
+    import supernet_b200  # noqa: F401
+    from supernet_b200 import dataio
+    names = [s.name for s in O.unet_conv_specs("hippocampus", 8, 3, 1)]
+    dataio.to_keras_h5(os.path.join(HERE, "keras3_hippocampus_n8.weights.h5"), O.make_weights("hippocampus", 8, 3, 1),
+                       names)
 
 
 if __name__ == "__main__":

@@ -109,3 +109,117 @@ def test_weight_archive_roundtrip(tmp_path):
             assert torch.equal(a, b)
     with pytest.raises((RuntimeError, OSError)):      # no h5py in this image (or, with h5py, no such file)
         dataio.from_keras_h5(os.path.join(str(tmp_path), "missing.weights.h5"), m.conv_names)
+
+
+# ------------------------------------------------------------------------------------------------------------
+# Keras-3 `.weights.h5` interchange (Brats.py:732,611-622,933,1195) and the result pickle (Brats.py:1375,1427)
+# ------------------------------------------------------------------------------------------------------------
+GOLDEN = os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden")
+
+
+def _hip_names(n=8):
+    from oracle import supernet_oracle as O
+    return O, [s.name for s in O.unet_conv_specs("hippocampus", n, 3, 1)]
+
+
+def test_keras_h5_fixture_loads_into_the_model():
+    """The committed checkpoint (tests/golden/make_golden.py) -> from_keras_h5 -> load_weight_dict, every tensor equal
+    to the generator's weights; HWIO w_mu / raw w_sigma (Brats.py:54-63,107-116)."""
+    O, names = _hip_names()
+    path = os.path.join(GOLDEN, "keras3_hippocampus_n8.weights.h5")
+    with open(path, "rb") as f:
+        assert f.read(8) == b"\x89HDF\r\n\x1a\n"
+    model = S.Density_prop_with_pad_UNET(8, 3, variant="hippocampus")
+    model.build_with_input(1, "cpu")
+    w = dataio.from_keras_h5(path, model.conv_names, dataio.model_weight_shapes(model))
+    ref = O.make_weights("hippocampus", 8, 3, 1)
+    assert list(w) == names
+    for n in names:
+        assert torch.equal(w[n][0], ref[n][0]) and torch.equal(w[n][1], ref[n][1])
+    model.load_weight_dict(w)
+    assert torch.equal(model.up1_conv2x2.w_mu.detach(), ref["up1_conv2x2"][0])
+    assert torch.equal(model.conv_input.w_sigma1.detach(), ref["conv_input"][1])
+
+
+def test_keras_h5_auto_named_layers_use_numeric_suffix_order(tmp_path):
+    """groups named my_conv_intermediate, _1, _10, _11, _2 ... sort as text in the wrong order (conv2 / conv3
+    have the same shape and would swap silently).  The numeric suffix is the construction order of __init__."""
+    from supernet_b200 import h5min
+    O, names = _hip_names()
+    ref = O.make_weights("hippocampus", 8, 3, 1)
+    ds = {}
+    k = 0
+    for n in names:
+        if n == "conv_input":
+            g = "my_conv_input"
+        else:
+            g = "my_conv_intermediate" + (f"_{k}" if k else "")
+            k += 1
+        ds[f"/layers/{g}/vars/0"] = ref[n][0].numpy()
+        ds[f"/layers/{g}/vars/1"] = ref[n][1].numpy()
+    ds["/layers/my_max_pooling/vars/0"] = np.zeros(3, dtype=np.float32)       # a layer without a weight pair
+    ds["/vars/0"] = np.arange(4, dtype=np.int32)
+    path = str(tmp_path / "auto.weights.h5")
+    h5min.write_h5(path, ds)
+    assert sorted(f"my_conv_intermediate_{i}" for i in (1, 2, 10, 11))[1] == "my_conv_intermediate_10"   # the trap
+    w = dataio.from_keras_h5(path, names)
+    for n in names:
+        assert torch.equal(w[n][0], ref[n][0]) and torch.equal(w[n][1], ref[n][1]), n
+    # a shape that does not fit the model is an error, not a silent mis-load
+    bad = dict(ds)
+    bad["/layers/my_conv_intermediate_3/vars/0"] = np.zeros((3, 3, 8, 8), dtype=np.float32)
+    h5min.write_h5(str(tmp_path / "bad.weights.h5"), bad)
+    model = S.Density_prop_with_pad_UNET(8, 3, variant="hippocampus")
+    model.build_with_input(1, "cpu")
+    with pytest.raises(RuntimeError):
+        dataio.from_keras_h5(str(tmp_path / "bad.weights.h5"), names, dataio.model_weight_shapes(model))
+    with pytest.raises(RuntimeError):                      # a layer group is missing
+        dataio.from_keras_h5(path, names + ["conv_extra"])
+
+
+def test_h5min_round_trips_groups_dtypes_and_rejects_what_it_does_not_parse(tmp_path):
+    from supernet_b200 import h5min
+    g = np.random.default_rng(5)
+    ds = {f"/g{i:02d}/deep/er/x": g.random((i + 1, 3)).astype(np.float32) for i in range(21)}    # > 8 and > 16 links
+    ds["/f64"] = g.random((2, 3, 4))
+    ds["/i64"] = g.integers(-5, 5, size=7)
+    ds["/u8"] = g.integers(0, 255, size=(3, 3)).astype(np.uint8)
+    ds["/scalar"] = np.float32(2.5)
+    ds["/empty"] = np.zeros((0, 4), dtype=np.float32)
+    path = str(tmp_path / "t.h5")
+    h5min.write_h5(path, ds)
+    back = h5min.read_h5(path)
+    assert sorted(back) == sorted(ds)
+    for k_, v in ds.items():
+        assert back[k_].dtype == np.asarray(v).dtype and np.array_equal(back[k_], np.asarray(v)), k_
+    raw = bytearray(open(path, "rb").read())
+    with pytest.raises(h5min.H5FormatError):
+        h5min.H5Reader(bytes(raw[:4]) + b"XXXX" + bytes(raw[8:]))             # signature
+    v2 = bytearray(raw)
+    v2[8] = 2
+    with pytest.raises(h5min.H5FormatError):
+        h5min.H5Reader(bytes(v2))                                             # superblock version 2
+    # flip the layout class of one dataset to "chunked": the reader must refuse, not return garbage
+    i = raw.find(b"\x08\x00\x18\x00")                                      # a layout message header (type 8, 24 bytes)
+    assert i > 0 and raw[i + 8] == 3 and raw[i + 9] == 1
+    raw[i + 9] = 2
+    with pytest.raises(h5min.H5FormatError):
+        h5min.H5Reader(bytes(raw)).datasets()
+
+
+def test_result_pickle_has_the_reference_structure(tmp_path):
+    """pickle.dump([logits_, sigma_, x, y]) with image-shaped maps (Brats.py:1290-1298,1375,1427)."""
+    import pickle
+    p = torch.rand(3, 6 * 5, 4)
+    v = torch.rand(3, 6 * 5, 4)
+    x = torch.rand(3, 10, 9, 2)
+    y = torch.randint(0, 4, (3, 6, 5))
+    path = str(tmp_path / "uncertainty_info.pkl")
+    dataio.save_result_pickle(path, p, v, x, y, (6, 5))
+    with open(path, "rb") as f:
+        obj = pickle.load(f)
+    assert isinstance(obj, list) and len(obj) == 4 and all(isinstance(a, np.ndarray) for a in obj)
+    logits_, sigma_, xb, yb = dataio.load_result_pickle(path)
+    assert logits_.shape == (3, 6, 5, 4) and sigma_.shape == (3, 6, 5, 4)
+    assert np.array_equal(logits_.reshape(3, -1, 4), p.numpy()) and np.array_equal(xb, x.numpy())
+    assert np.array_equal(yb, y.numpy())
