@@ -10,8 +10,12 @@ golden vectors or saved outputs, and TensorFlow is not installable in this image
 the reference itself cannot be executed here.  This file is a line-by-line
 restatement of the reference *formulas*; it is pinned only by (i) two independent
 formulations that must agree (the "as written" patch-matmul form and the conv form),
-(ii) a Monte-Carlo check of the variance formula, (iii) structural identities and
-(iv) hand-computed tiny cases -- see tests/test_oracle.py.
+(ii) a Monte-Carlo check of the variance formula, (iii) structural identities,
+(iv) hand-computed tiny cases and (v) an INDEPENDENT NumPy restatement of the as-written
+forward (oracle/numpy_check.py: explicit index arithmetic, no torch) whose committed
+whole-network outputs (tests/golden/*_numpy_fp64.npz) both forms of this oracle must
+reproduce to 1e-12 -- see tests/test_oracle.py.  That is as close to pinned as an image
+without TensorFlow allows; it is still not a run of the reference.
 
 Everything is NHWC, weights HWIO ``[k,k,Cin,Cout]``, "sigma" means VARIANCE (as in the
 reference).  All functions are differentiable torch-CPU code so autograd provides the

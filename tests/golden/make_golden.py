@@ -1,5 +1,6 @@
-"""Regenerates the golden fixtures from the fp64 oracle (the TensorFlow reference cannot run in
-this image -- "parity unpinned", see oracle/supernet_oracle.py).  Run from the repo root:
+"""Regenerates the golden fixtures (the TensorFlow reference cannot run in this image -- "parity unpinned", see
+oracle/supernet_oracle.py): two from the fp64 torch oracle, two from the independent NumPy restatement
+(oracle/numpy_check.py) that the torch oracle is checked against, and one Keras-3 checkpoint.  Run from the repo root:
 
     python tests/golden/make_golden.py
 """
@@ -34,6 +35,18 @@ def main():
     m, vv = O.conv_intermediate_as_written(mu, var, w, ws)
     np.savez_compressed(os.path.join(HERE, "layers_fp64.npz"), mu=mu.numpy(), var=var.numpy(), w=w.numpy(),
                         ws=ws.numpy(), m_out=m.numpy(), v_out=vv.numpy())
+    # the SAME networks through the independent NumPy restatement (oracle/numpy_check.py: no torch arithmetic): these
+    # two files are what pins the torch oracle (tests/test_oracle.py)
+    from oracle import numpy_check as N
+    for variant, C, in_ch, alpha, fname in (("hippocampus", 3, 1, 1.0, "hippocampus_b2_numpy_fp64.npz"),
+                                            ("brats", 4, 4, O.BRATS_ALPHA, "brats_b1_numpy_fp64.npz")):
+        Wn = {k: (a.double().numpy(), b.double().numpy()) for k, (a, b) in O.make_weights(variant, 32, C, in_ch).items()}
+        xn = O.make_input(variant, 2 if variant == "hippocampus" else 1, alpha=alpha).double().numpy()
+        pn, vn, mfn, sfn = N.unet_forward(xn, Wn, variant)
+        idx = np.sort(np.random.default_rng(1).choice(pn.size, 2048, replace=False))
+        np.savez_compressed(os.path.join(HERE, fname), idx=idx, p=pn.reshape(-1)[idx], v=vn.reshape(-1)[idx],
+                            mf=mfn.reshape(-1)[idx], sf=sfn.reshape(-1)[idx], p_sum=float(pn.sum()),
+                            v_sum=float(vn.sum()), mf_abs_sum=float(np.abs(mfn).sum()), sf_sum=float(sfn.sum()))
     # a Keras-3 `.weights.h5` checkpoint in the reference model's layout (Brats.py:732): Hippocampus graph at
     # n_kernels = 8 (147 KB), attribute-named layer groups, written by the in-repo HDF5 writer (no h5py here)
     import supernet_b200  # noqa: F401

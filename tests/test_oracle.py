@@ -266,3 +266,58 @@ def test_forward_on_own_trajectory_is_the_identity():
     assert float(taps2["conv1"][0][tuple(idx)]) == 0.0
     g2, _ = orc.fgsm_gradient(x, y, trajectory=t2)
     assert O.rel_l2(g2, g0) > 0
+
+
+# ------------------------------------------------------------------------------------------------------------
+# the torch oracle against the independent NumPy restatement (oracle/numpy_check.py) and its committed output
+# ------------------------------------------------------------------------------------------------------------
+def _golden_np(name):
+    return np.load(os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden", name))
+
+
+@pytest.mark.parametrize("form", ["conv", "as_written"])
+@pytest.mark.parametrize("variant,C,in_ch,B,alpha,fname", [
+    ("hippocampus", 3, 1, 2, 1.0, "hippocampus_b2_numpy_fp64.npz"),
+    ("brats", 4, 4, 1, O.BRATS_ALPHA, "brats_b1_numpy_fp64.npz")])
+def test_torch_oracle_reproduces_the_numpy_restatement(variant, C, in_ch, B, alpha, fname, form):
+    """The fixtures were produced by NumPy index arithmetic that shares nothing with the torch oracle (different conv:
+    patches x matrix; pooling with TF's batch-inclusive flat arg-max index + flat gather; unpool op by op).  Both forms
+    of the torch oracle must land on them to 1e-12."""
+    if variant == "brats" and form == "as_written":
+        pytest.skip("BraTS as-written in fp64 needs ~2 GB of patch matrices; the conv form covers the graph")
+    z = _golden_np(fname)
+    p, v, mf, sf = O.UNetOracle(variant, 32, C, in_ch, torch.float64, form=form)(O.make_input(variant, B, alpha=alpha), True)
+    idx = torch.from_numpy(z["idx"])
+    for got, key in ((p, "p"), (v, "v"), (mf, "mf"), (sf, "sf")):
+        assert O.rel_l2(got.flatten()[idx], torch.from_numpy(z[key])) < 1e-12, key
+    assert abs(float(p.sum()) - float(z["p_sum"])) < 1e-9 * float(z["p_sum"])
+    assert abs(float(v.sum()) - float(z["v_sum"])) < 1e-9 * float(z["v_sum"])
+    assert abs(float(mf.abs().sum()) - float(z["mf_abs_sum"])) < 1e-9 * float(z["mf_abs_sum"])
+    assert abs(float(sf.sum()) - float(z["sf_sum"])) < 1e-9 * float(z["sf_sum"])
+
+
+def test_numpy_restatement_layers_against_torch_oracle_and_hand_cases():
+    """Layer by layer, including what the whole-network fixtures exercise only lightly: odd sizes and ties in the
+    pooling, the flat arg-max index formula, a hand-computed first conv."""
+    from oracle import numpy_check as N
+    g = np.random.default_rng(3)
+    mu, var = g.standard_normal((2, 7, 9, 5)), g.random((2, 7, 9, 5))
+    w, ws = g.standard_normal((3, 3, 5, 6)) * 0.1, g.uniform(-8, -2, 6)
+    a, b = N.conv_intermediate(mu, var, w, ws)
+    c, d = O.conv_intermediate_conv_form(*(torch.from_numpy(t) for t in (mu, var, w, ws)))
+    assert np.allclose(a, c.numpy(), rtol=0, atol=1e-13) and np.allclose(b, d.numpy(), rtol=0, atol=1e-13)
+    m = np.maximum(mu, 0)                                    # post-ReLU tensors have tied zeros
+    pm, pv = N.maxpooling(m, var)
+    qm, qv = O.maxpooling(torch.from_numpy(m), torch.from_numpy(var))
+    assert np.array_equal(pm, qm.numpy()) and np.array_equal(pv, qv.numpy())
+    _, arg = N.maxpool_with_argmax(m)
+    assert np.array_equal(m.reshape(-1)[arg], pm)           # include_batch_in_index=True: index into the whole batch
+    assert arg[1].min() >= 7 * 9 * 5                        # second image's indices lie beyond the first image
+    u = N.unpool(mu)
+    assert u.shape == (2, 15, 19, 5) and np.array_equal(u[:, 1::2, 1::2], mu) and float(np.abs(u).sum()) == float(np.abs(mu).sum())
+    # hand case: 1 pixel of output, x = ones(3x3x1): mean = sum(w), var = softplus(w_sigma) * 9
+    w1 = np.arange(9, dtype=np.float64).reshape(3, 3, 1, 1)
+    mo, vo = N.conv_input(np.ones((1, 3, 3, 1)), w1, np.array([0.0]))
+    assert float(mo) == 36.0 and abs(float(vo) - 9 * np.log(2.0)) < 1e-15
+    p, s = N.softmax_moments(np.zeros((1, 1, 1, 2)), np.array([1.0, 3.0]).reshape(1, 1, 1, 2))
+    assert np.allclose(p, 0.5) and np.allclose(s, 0.0625 * 4.0)        # J = [[.25,-.25],[-.25,.25]]: J^2 @ [1,3] = .25
