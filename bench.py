@@ -135,27 +135,66 @@ class ClockSampler:
                 "power_w_max": max(power) if power else None, "samples": len(sm), "reasons": sorted(reasons)}
 
 
-def cpu_baseline(seconds_budget: float = 15.0, form: str = "as_written"):
-    """The reference's CPU path restated (oracle, fp32, torch-CPU, all host threads) on a bounded sample of the
-    BraTS workload."""
+def _time_oracle(variant, batch, form, budget_s, n_labels, in_ch, alpha):
+    """slices/s of the fp32 torch-CPU oracle forward (bounded sample: as many batches as fit the budget, 2..20)."""
     from oracle import supernet_oracle as O
-    cores = os.cpu_count() or 1
-    torch.set_num_threads(cores)
-    oracle = O.UNetOracle("brats", N_KERNELS, N_LABELS, IN_CH, torch.float32, form=form)
-    x = O.make_input("brats", 1, alpha=O.BRATS_ALPHA)
+    oracle = O.UNetOracle(variant, N_KERNELS, n_labels, in_ch, torch.float32, form=form)
+    x = O.make_input(variant, batch, alpha=alpha)
     with torch.no_grad():
         oracle(x)                                  # warm-up
         t0 = time.perf_counter()
         oracle(x)
         one = time.perf_counter() - t0
-        n = max(2, min(64, int(seconds_budget / max(one, 1e-3))))
+        n = max(2, min(20, int(budget_s / max(one, 1e-3))))
         t0 = time.perf_counter()
         for _ in range(n):
             oracle(x)
         dt = time.perf_counter() - t0
-    return {"value": n / dt, "unit": UNIT, "cores": torch.get_num_threads(), "kind": "port",
-            "sample": f"{n} BraTS slices, batch 1, fp32 torch-CPU oracle ({form} form: the reference's op sequence "
-                      f"conv2d + extract_patches + 3 matmuls per layer)"}
+    return batch * n / dt, n
+
+
+def cpu_baseline():
+    """The reference's CPU path restated (oracle, fp32, torch-CPU, all host threads) on bounded samples:
+    BraTS batch 8 in the reference's own op sequence (the headline `value`) and in the best-case conv form, and
+    BASELINE.json configs[0] -- Hippocampus forward, batch 8 -- in both forms."""
+    from oracle import supernet_oracle as O
+    cores = os.cpu_count() or 1
+    torch.set_num_threads(cores)
+    v1, n1 = _time_oracle("brats", 1, "as_written", 8.0, N_LABELS, IN_CH, O.BRATS_ALPHA)
+    v8, n8 = _time_oracle("brats", 8, "as_written", 6.0, N_LABELS, IN_CH, O.BRATS_ALPHA)
+    v_cv, _ = _time_oracle("brats", 8, "conv", 4.0, N_LABELS, IN_CH, O.BRATS_ALPHA)
+    h_aw, _ = _time_oracle("hippocampus", 8, "as_written", 2.0, 3, 1, 1.0)
+    h_cv, _ = _time_oracle("hippocampus", 8, "conv", 2.0, 3, 1, 1.0)
+    # the reference's op sequence is fastest on the CPU at batch 1 (at batch 8 its 2 x 370 MB patch matrices per layer
+    # fall out of the caches): the headline baseline is the BETTER of the two
+    best, nb, bb = (v1, n1, 1) if v1 >= v8 else (v8, n8, 8)
+    return {"value": best, "unit": UNIT, "cores": torch.get_num_threads(), "kind": "port",
+            "sample": f"{nb} batches of {bb} BraTS slice(s), fp32 torch-CPU oracle, as_written form (the reference's op "
+                      f"sequence conv2d + extract_patches + 3 matmuls per layer); the better of batch 1 and batch 8",
+            "as_written_batch1": v1, "as_written_batch8": v8, "conv_form_batch8": v_cv,
+            "hippocampus_b8": {"config": "BASELINE.json configs[0]: Hippocampus forward, batch 8", "unit": UNIT,
+                               "as_written": h_aw, "conv_form": h_cv}}
+
+
+def hippocampus_b8_gpu(S, dev, steps=200):
+    """BASELINE.json configs[0] on the GPU path: Hippocampus forward, batch 8, FAST mode, CUDA-graph replay."""
+    from oracle import supernet_oracle as O
+    from supernet_b200.engine import InferenceEngine
+    model = S.Density_prop_with_pad_UNET(N_KERNELS, 3, variant="hippocampus", mode="fast")
+    model.load_weight_dict(O.make_weights("hippocampus", N_KERNELS, 3, 1), device=dev)
+    eng = InferenceEngine(model, 8, 64, 64, 1, dev, graph=True, keep_presoftmax=False)
+    eng.x_in.copy_(O.make_input("hippocampus", 8))
+    for _ in range(10):
+        eng.forward_resident()
+    torch.cuda.synchronize()
+    a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    a.record()
+    for _ in range(steps):
+        eng.forward_resident()
+    b.record()
+    torch.cuda.synchronize()
+    ms = a.elapsed_time(b) / steps
+    return {"ms_per_batch": round(ms, 4), "slices_per_s": round(8 / ms * 1e3, 1)}
 
 
 def aux_backward(model, B, dev, world=1, rank=0, steps=10, warmup=3):
@@ -242,8 +281,12 @@ def run_reference(args):
     from oracle import supernet_oracle as O
     cores = os.cpu_count() or 1
     torch.set_num_threads(cores)
+    # slices per step: 1.  The reference's op sequence is fastest on the CPU at batch 1 (measured: 5.4 slices/s at
+    # batch 1 against 1.5-2 at batch 8, whose patch matrices fall out of the caches), so this is the arm's best case;
+    # cpu_baseline in the b200 line reports batch 8 next to it.
+    RB = 1
     oracle = O.UNetOracle("brats", N_KERNELS, N_LABELS, IN_CH, torch.float32, form="as_written")
-    x = O.make_input("brats", 1, alpha=O.BRATS_ALPHA)
+    x = O.make_input("brats", RB, alpha=O.BRATS_ALPHA)
     with torch.no_grad():
         for _ in range(max(1, min(args.warmup, 3))):
             oracle(x)
@@ -252,8 +295,9 @@ def run_reference(args):
         for _ in range(steps):
             oracle(x)
         dt = time.perf_counter() - t0
-    v = steps / dt
-    sample = "1 BraTS slice per step (bounded sample of the batch), as-written op sequence, fp32 torch-CPU"
+    v = RB * steps / dt
+    sample = (f"{RB} BraTS slice per step (bounded sample of the batch-64 step; the CPU path's fastest batch size), "
+              f"as-written op sequence, fp32 torch-CPU, {torch.get_num_threads()} threads")
     print(json.dumps({
         "impl": "reference", "metric": METRIC, "value": v, "unit": UNIT, "n_gpus": args.gpus, "steps": steps,
         "warmup": args.warmup, "ms_per_step": 1e3 * dt / steps, "higher_is_better": True, "scaling": "weak",
@@ -409,18 +453,24 @@ def main():
                     other_bytes += r["bytes"] * B
             kernels.append(row)
         achieved = tc_flops / (tc_ms * 1e-3) / 1e12
-        traffic = None
-        tpath = os.path.join(ROOT, "profiles", "r01_traffic.json")
+        # dram__bytes_read + dram__bytes_write of the conv launches, from an ncu --set full capture of THIS build: the
+        # file carries the digest of the kernel sources it was captured on and is ignored when they have changed
+        traffic, traffic_note = None, "no ncu capture for this build (profiles/r02_traffic.json)"
+        tpath = os.path.join(ROOT, "profiles", "r02_traffic.json")
         if os.path.exists(tpath):
             with open(tpath) as f:
                 tj = json.load(f)
-            if tj.get("batch") == B:
-                traffic = tj["dram_bytes_per_step"]
+            if tj.get("batch") != B:
+                traffic_note = f"capture is for batch {tj.get('batch')}"
+            elif tj.get("build_digest") != S.build._digest():
+                traffic_note = "capture is from another build of the kernels (digest mismatch): refused"
+            else:
+                traffic, traffic_note = tj["dram_bytes_per_step"], tj.get("source")
         n_tc = sum(1 for nm in names if nm in tmap and nm not in ("conv_input", "conv_final"))
         roofline = {"kernel": f"conv_moments_halo_kernel ({n_tc} launches/step: every tcgen05 moment conv; achieved = "
                               "sum of algorithmic FLOPs / sum of CUDA-event launch times)", "bound": "tensor",
                     "achieved": round(achieved, 1), "peak": pk["tf_sustained"], "unit": "TFLOP/s",
-                    "frac": round(achieved / pk["tf_sustained"], 4), "traffic": traffic,
+                    "frac": round(achieved / pk["tf_sustained"], 4), "traffic": traffic, "traffic_note": traffic_note,
                     "algorithmic_bytes": round(sum(tmap[nm]["bytes"] for nm in names if nm in tmap and nm not in
                                                    ("conv_input", "conv_final")) * B),
                     "peak_source": f"{pk['source']} bf16 sustained", "share_of_step": round(tc_ms / sum(per), 3),
@@ -459,6 +509,8 @@ def main():
             out["aux"] = aux
         if not args.no_cpu_baseline and world == 1:
             out["cpu_baseline"] = cpu_baseline()
+            if args.mode == "fast":
+                out["cpu_baseline"]["hippocampus_b8"]["gpu_fast"] = hippocampus_b8_gpu(S, dev)
         print(json.dumps(out))
     if world > 1:
         dist.destroy_process_group()
