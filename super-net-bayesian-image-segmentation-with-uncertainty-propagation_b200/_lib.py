@@ -116,6 +116,16 @@ def ptr(t) -> C.c_void_p:
     return C.c_void_p(t.data_ptr())
 
 
+def check_device(t) -> None:
+    """Every launch goes to torch.cuda.current_stream() of the CURRENT device: a tensor that lives on another GPU would
+    be dereferenced there (illegal address, or silent peer access).  The engines enter torch.cuda.device(self.device)
+    themselves; direct callers of the ops must do the same."""
+    import torch
+    if t is not None and t.is_cuda and t.device.index != torch.cuda.current_device():
+        raise RuntimeError(f"tensor on {t.device}, but the current CUDA device is cuda:{torch.cuda.current_device()}: "
+                           f"wrap the call in `with torch.cuda.device(tensor.device):`")
+
+
 def stream_ptr() -> C.c_void_p:
     import torch
     return C.c_void_p(torch.cuda.current_stream().cuda_stream)

@@ -37,6 +37,14 @@
 
 namespace sn {
 
+// SN_HL_DBG knob experiments (profiles/r02_kwc_knobs.md) are compiled in only with -DSN_HL_KNOBS: the shipped kernels
+// carry none of the checks (they sit in the UMMA issue loop and the epilogue).
+#ifdef SN_HL_KNOBS
+#define HL_DBG(p) ((p).dbg)
+#else
+#define HL_DBG(p) 0
+#endif
+
 constexpr int HL_BM = 128;
 constexpr int HL_KC = 32;
 constexpr int HL_THREADS = 576;       // 18 warps: TMA, UMMA, 8 x q reduction, 8 x epilogue
@@ -380,7 +388,7 @@ __global__ void __launch_bounds__(hl_threads(KWC), 1) conv_moments_halo_kernel(c
               b0 = b_st + (uint32_t)slot * SLOT16;
             }
             const uint32_t a00 = a_st + (uint32_t)kh * row_shift16 + (uint32_t)kw * 4u;  // tap = row offset in the halo
-            if (leader && (!(p.dbg & 2) || tap == 0)) {
+            if (leader && (!(HL_DBG(p) & 2) || tap == 0)) {
 #pragma unroll
               for (int t = 0; t < G; ++t) {
                 const uint32_t a0 = a00 + (uint32_t)t * 3u * plane16;             // tile t of the pair
@@ -433,7 +441,7 @@ __global__ void __launch_bounds__(hl_threads(KWC), 1) conv_moments_halo_kernel(c
             while (cb >= p.cblk_s[src]) { cb = 0; ++src; }
           }
           ptx::mbar_wait(a_full(a_stage_i), a_par);
-          if (row < p.rows_box && !(p.dbg & 4)) {
+          if (row < p.rows_box && !(HL_DBG(p) & 4)) {
 #pragma unroll
            for (int t = 0; t < G; ++t) {
             float qa = 0.f, qb = 0.f, qc = 0.f, qd = 0.f;         // four chains for ILP
@@ -538,12 +546,12 @@ __global__ void __launch_bounds__(hl_threads(KWC), 1) conv_moments_halo_kernel(c
         const int gcol0 = nt_i * NT + half * NH;               // first column (parity group, channel) of this warp
         const int ox_i = tx * p.TWo + x, oy_i = ty * p.THo + y, ob = tb * p.TN + n;
         const bool valid = tc.store && x < p.TWo && y < p.THo && n < p.TN && ox_i < p.Wo && oy_i < p.Ho && ob < p.B &&
-                           !(p.dbg & 8);
+                           !(HL_DBG(p) & 8);
         if (!DGRAD && p.r_out != nullptr && half == 0 && nt_i == 0 && valid)
           p.r_out[((size_t)ob * p.Ho + oy_i) * p.Wo + ox_i] = r;
         ptx::mbar_wait(acc_full(as), par);
         ptx::tc_fence_after();
-        if (p.dbg & 1) {
+        if (HL_DBG(p) & 1) {
           ptx::tc_fence_before();
           __syncwarp();
           if (lane == 0) ptx::mbar_arrive(acc_empty(as));
@@ -775,7 +783,7 @@ __global__ void __launch_bounds__(hl_threads(KWC), 1) conv_moments_halo_kernel(c
               if (lane == 0) ptx::mbar_arrive(acc_empty(as));
               ptx::fence_proxy_async();                               // generic-proxy writes -> visible to the TMA
               ptx::named_barrier(pair_bar, 64);
-              if (half == 0 && lane == 0 && tc.store && oy_i < p.Ho && ob < p.B && !(p.dbg & 8)) {
+              if (half == 0 && lane == 0 && tc.store && oy_i < p.Ho && ob < p.B && !(HL_DBG(p) & 8)) {
                 ptx::tma_store_5d(&maps.d, stg, nt_i * NT, 0, tx * p.TWo, oy_i, ob);
                 ptx::bulk_commit_group();
               }

@@ -23,6 +23,18 @@ from .fastops import PackedView
 Tensor = torch.Tensor
 
 
+def _on_device(fn):
+    """Run an engine method with the engine's GPU as the current device: the C-ABI launches on the current device's
+    stream, so a model / input on cuda:1 must not be driven while cuda:0 is current."""
+    import functools
+
+    @functools.wraps(fn)
+    def wrapped(self, *a, **k):
+        with torch.cuda.device(self.device):
+            return fn(self, *a, **k)
+    return wrapped
+
+
 def _capture_graph(device, launch: Callable[[], None]) -> "torch.cuda.CUDAGraph":
     """Warm `launch` up on a side stream (lazy module loading, shared-memory attributes), then capture it.
     Garbage is collected BEFORE and the collector is paused DURING the capture: freeing an older engine (its CUDA
@@ -78,6 +90,7 @@ class InferenceEngine:
             w, ws = getattr(m, name).weights()
             self.prepared[name] = F.prepare_weights(w, ws, upconv=name.endswith("conv2x2"))
 
+    @_on_device
     def refresh_weights(self) -> None:
         """After a weight update: re-derive the bf16 operands IN PLACE (a captured graph keeps its pointers)."""
         m = self.model
@@ -100,6 +113,7 @@ class InferenceEngine:
         if self._weights_version != self._weights_stamp():
             self.refresh_weights()
 
+    @_on_device
     def _build(self) -> None:
         m = self.model
         B, H, W, Cin = self.shape
@@ -212,6 +226,7 @@ class InferenceEngine:
         for s in self._steps:
             s()
 
+    @_on_device
     def forward_resident(self) -> Tuple[Tensor, Tensor]:
         """Run the forward on whatever is in self.x_in; returns the engine-owned output tensors."""
         if not self.use_graph:
@@ -222,6 +237,7 @@ class InferenceEngine:
             self._graph.replay()
         return self.p, self.v
 
+    @_on_device
     def saved_activations(self):
         """layer name -> (mean, variance) fp32 NHWC of every conv output as this engine last computed it (post-ReLU
         where the layer has one; the interior of padded buffers).  What the layer-by-layer reference API would have
@@ -240,6 +256,7 @@ class InferenceEngine:
             out[name] = (t[..., 0, :] + t[..., 1, :], t[..., 2, :])
         return out
 
+    @_on_device
     def run(self, x: Tensor, return_presoftmax: bool = False):
         if not self.matches(x):
             raise RuntimeError(f"engine built for input {self.shape}, got {tuple(x.shape)}")
@@ -292,6 +309,7 @@ class GradientEngine(InferenceEngine):
             w, _ = getattr(m, name).weights()
             self.prepared_bwd[name] = F.prepare_weights_bwd(w, upconv=name.endswith("conv2x2"))
 
+    @_on_device
     def _build_backward(self) -> None:
         m = self.model
         B, H, W, Cin = self.shape
@@ -422,6 +440,7 @@ class GradientEngine(InferenceEngine):
         self.grad_buffers = gbuf
         self.n_launches_bwd = len(steps) + 2          # + the two NLL forward kernels
 
+    @_on_device
     def refresh_weights(self) -> None:
         """After an optimiser step: re-derive forward AND data-gradient operands in place."""
         super().refresh_weights()
@@ -463,6 +482,7 @@ class GradientEngine(InferenceEngine):
         gw, gws = self.grads["conv_input"]
         ops.conv_bwd_weight_raw(B, H, W, cin, w.shape[-1], k, self.x_in, None, gm32, gv32, rs0, w, ws, gw, gws)
 
+    @_on_device
     def loss_and_weight_gradients(self, x: Tensor, y_onehot: Tensor, clip: Tuple[float, float] = (1e-12, 1e3),
                                   kl_factor: float = 0.0):
         """train_on_batch's loss and gradients (Brats.py:572-578): loss = NLL(clip(var)) + kl_factor * 0.5 *
@@ -493,6 +513,7 @@ class GradientEngine(InferenceEngine):
         if self.train:
             self._regulariser()
 
+    @_on_device
     def loss_and_input_gradient_resident(self) -> Tuple[Tensor, Tensor]:
         """Forward, loss_scale * NLL and d(loss)/dx on whatever is in self.x_in / self.y_in; returns engine-owned
         (loss [1] = the un-scaled NLL, g_x)."""
@@ -504,6 +525,7 @@ class GradientEngine(InferenceEngine):
             self._graph_bwd.replay()
         return self.nll_loss, self.g_x
 
+    @_on_device
     def forward_then_input_gradient(self, x: Tensor, upstream) -> Tuple[Tensor, Tensor, Tensor]:
         """Forward, then d <g_p, p> + <g_v, v> / dx for upstream gradients chosen AFTER looking at the outputs:
         `upstream(p, v) -> (g_p, g_v or None)`, both [B, HW, C] device tensors.  This is create_saliency_map's shape
@@ -530,6 +552,7 @@ class GradientEngine(InferenceEngine):
             s_()
         return self.g_x, self.p, self.v
 
+    @_on_device
     def input_gradient(self, x: Tensor, y_onehot: Tensor, loss_scale: float = 0.5,
                        clip: Tuple[float, float] = (-1e4, 1e3)) -> Tuple[Tensor, Tensor]:
         """(loss, d loss / d x) with loss = loss_scale * nll_gaussian(y, p, clip(var)): the defaults are

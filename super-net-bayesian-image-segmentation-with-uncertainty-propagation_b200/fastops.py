@@ -30,6 +30,7 @@ class PackedView:
     def c_view(self) -> sn_packed_view:
         n, h, w, three, c = self.buf.shape
         assert three == 3 and self.buf.dtype == torch.bfloat16 and self.buf.is_contiguous()
+        _lib.check_device(self.buf)
         return sn_packed_view(self.buf.data_ptr(), n, h, w, c, self.y0, self.x0, self.c0, 0)
 
 

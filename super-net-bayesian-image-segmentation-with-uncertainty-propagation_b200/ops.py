@@ -24,6 +24,7 @@ def _req(t: Optional[Tensor], name: str) -> Optional[Tensor]:
         raise RuntimeError(f"{name}: expected a CUDA tensor (the moment path has no CPU fallback)")
     if t.dtype != torch.float32:
         raise RuntimeError(f"{name}: expected float32, got {t.dtype}")
+    _lib.check_device(t)
     return t.contiguous()
 
 

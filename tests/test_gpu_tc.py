@@ -386,3 +386,60 @@ def test_fast_engines_follow_inplace_weight_updates(S):
     with torch.no_grad():
         p3, v3 = model(x.cuda())
     assert torch.equal(p3, p0) and torch.equal(v3, v0)
+
+
+# ------------------------------------------------------------------------------------------------------------
+# compute-sanitizer is closed on the GPU pool ("runs under it have left GPUs needing a reset",
+# profiles/r02_sanitizer_closed.txt), so the two properties it would check are tested directly:
+#   * no write outside the destination window (canary-filled buffers around every window),
+#   * no data race that changes results (bit-identical outputs over repeated launches with other work in flight).
+# Protocol bugs (a barrier never completed) already trap through the bounded mbarrier wait of sn_sm100.cuh.
+# ------------------------------------------------------------------------------------------------------------
+GUARD_CASES = [
+    # B, H, W, cin, c1, cout, k, upconv, kwc
+    (2, 10, 12, 32, 0, 32, 3, False, None),
+    (2, 10, 12, 64, 0, 64, 3, False, None),
+    (40, 20, 20, 64, 0, 64, 3, False, None),      # streamed weights, two pixel tiles per weight slot
+    (1, 12, 12, 128, 0, 128, 3, False, None),
+    (2, 6, 6, 64, 0, 32, 2, True, None),
+    (2, 9, 36, 32, 0, 32, 3, False, True),        # kw-concatenated, TMA-store epilogue
+    (3, 11, 67, 32, 0, 32, 3, False, True),       # ... partial last tile row and tile column
+    (2, 9, 36, 32, 32, 32, 3, False, True),       # kw-concatenated, two sources
+    (2, 9, 40, 128, 0, 32, 3, False, True),       # kw-concatenated, streamed weights
+]
+
+
+@pytest.mark.parametrize("case", GUARD_CASES)
+def test_conv_writes_only_its_window_and_is_deterministic(S, case):
+    F = S.fastops
+    B, H, W, cin, c1, cout, k, upconv, kwc = case
+    g = torch.Generator().manual_seed(sum(int(v or 0) for v in case))
+    src0 = F.PackedView(F.pack_moments(dev(torch.randn(B, H, W, cin, generator=g)), dev(torch.rand(B, H, W, cin, generator=g))))
+    src1 = F.PackedView(F.pack_moments(dev(torch.randn(B, H, W, c1, generator=g)), dev(torch.rand(B, H, W, c1, generator=g)))) \
+        if c1 else None
+    w = torch.randn(k, k, cin + c1, cout, generator=g) * 0.1
+    ws = torch.empty(cout).uniform_(-6, -2, generator=g)
+    wp, s = F.prepare_weights(dev(w), dev(ws), upconv=upconv)
+    Ho, Wo = (2 * H, 2 * W) if upconv else (H - k + 1, W - k + 1)
+    CANARY = -7.0                                              # bf16-exact, never produced (variances are >= 0)
+    # the window sits inside a larger buffer: 2 rows above, 3 below, 3 columns left, 2 right, 32 channels on each side,
+    # and one spare image after the batch
+    big = torch.full((B + 1, Ho + 5, Wo + 5, 3, cout + 64), CANARY, device="cuda", dtype=torch.bfloat16)
+    dst = F.PackedView(big, 2, 3, 32)
+    outs = []
+    noise = torch.empty(64 << 20, device="cuda")
+    for rep in range(4):
+        big.fill_(CANARY)
+        noise.normal_()                                        # unrelated traffic in flight around the launch
+        F.conv_moments_tc(src0, cin, B, H, W, k, cout, wp, s, dst=dst, relu=not upconv, upconv=upconv, src1=src1,
+                          c1=c1, kwc=kwc)
+        noise.add_(1.0)
+        torch.cuda.synchronize()
+        win = big[:B, 2:2 + Ho, 3:3 + Wo, :, 32:32 + cout]
+        outs.append(win.clone())
+        assert bool((win != CANARY).all()), "part of the window was not written"
+        guard = big.clone()
+        guard[:B, 2:2 + Ho, 3:3 + Wo, :, 32:32 + cout] = CANARY
+        assert bool((guard == CANARY).all()), "a write landed outside the destination window"
+    for o in outs[1:]:
+        assert torch.equal(o.view(torch.int16), outs[0].view(torch.int16)), "results differ between identical launches"

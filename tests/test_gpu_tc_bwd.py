@@ -503,3 +503,37 @@ def test_fast_mode_other_width_uses_the_general_kernels(S):
     worst = max(rel(a.grad, b) for a, b in zip([q for c in model.convs() for q in c.weights()], rg))
     print("n_kernels 64: input gradient", rel(g, g_ref), "worst weight gradient", worst)
     assert worst < 1e-2, worst
+
+
+@pytest.mark.parametrize("case", [(2, 10, 12, 32, 32, 3, None), (2, 10, 12, 64, 64, 3, None), (2, 9, 34, 32, 64, 3, True),
+                                  (3, 36, 45, 32, 128, 3, True), (2, 6, 6, 64, 32, 2, None)])
+def test_dgrad_writes_only_its_window_and_is_deterministic(S, case):
+    """compute-sanitizer is closed on the GPU pool (profiles/r02_sanitizer_closed.txt): the data-gradient kernel's
+    writes are checked against canary-filled surroundings, and repeated launches must agree bit for bit."""
+    F = S.fastops
+    B, H, W, cin, cout, k, kwc = case
+    upconv = k == 2
+    Ho, Wo = (2 * H, 2 * W) if upconv else (H - k + 1, W - k + 1)
+    g = torch.Generator().manual_seed(sum(int(v or 0) for v in case))
+    saved = F.PackedView(F.pack_moments(dev(torch.randn(B, H, W, cin, generator=g).double()),
+                                        dev(torch.rand(B, H, W, cin, generator=g).double())))
+    g_out = F.PackedView(F.pack_moments(dev(torch.randn(B, Ho, Wo, cout, generator=g).double()),
+                                        dev(torch.randn(B, Ho, Wo, cout, generator=g).double())))
+    w = (torch.randn(k, k, cin, cout, generator=g) * 0.1).double()
+    ws = torch.empty(cout, dtype=torch.float64).uniform_(-6, -2, generator=g)
+    wt = F.prepare_weights_bwd(dev(w), upconv=upconv)
+    _, s = F.prepare_weights(dev(w), dev(ws), upconv=upconv)
+    CANARY = -7.0
+    big = torch.full((B + 1, H + 4, W + 5, 3, cin + 64), CANARY, device="cuda", dtype=torch.bfloat16)
+    outs = []
+    for rep in range(3):
+        big.fill_(CANARY)
+        F.conv_moments_bwd_data_tc(g_out, B, H, W, k, cout, wt, s, saved, F.PackedView(big, 1, 2, 32), cin, True,
+                                   upconv=upconv, kwc=kwc)
+        torch.cuda.synchronize()
+        win = big[:B, 1:1 + H, 2:2 + W, :, 32:32 + cin]
+        outs.append(win.clone())
+        guard = big.clone()
+        guard[:B, 1:1 + H, 2:2 + W, :, 32:32 + cin] = CANARY
+        assert bool((guard == CANARY).all()), "a write landed outside the gradient window"
+    assert all(torch.equal(o.view(torch.int16), outs[0].view(torch.int16)) for o in outs[1:])
