@@ -25,6 +25,8 @@ NVCC_FLAGS = [
     "-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo", "-O3", "-std=c++17",
     "-Xcompiler", "-fPIC,-Wall,-Wno-unused-function", "--expt-relaxed-constexpr",
 ]
+if os.environ.get("SN_BUILD_KNOBS") == "1":          # profiling builds only: compile the SN_HL_DBG knob checks in
+    NVCC_FLAGS.append("-DSN_HL_KNOBS")
 
 
 def _nvcc() -> str:

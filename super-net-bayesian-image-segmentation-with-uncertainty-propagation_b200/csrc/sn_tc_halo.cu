@@ -568,6 +568,7 @@ __global__ void __launch_bounds__(hl_threads(KWC), 1) conv_moments_halo_kernel(c
         const uint32_t stg = bar_base + 5120u + (uint32_t)(eset * 4 + q) * HL_STG_BUF;
         const uint32_t pair_bar = 1u + (uint32_t)(eset * 4 + q);
         auto stage32 = [&](int pl, const uint32_t (&w8)[8]) {      // this lane's 16 channels of plane pl
+          if (HL_DBG(p) & 16) return;
           const uint32_t L = (uint32_t)lane * 192u + (uint32_t)pl * 64u + (uint32_t)half * 32u;
           const uint32_t x4 = ((L >> 7) & 3u) << 4;                 // SWIZZLE_64B: bits [4,6) ^= bits [7,9)
           ptx::st_shared_v4(stg + (L ^ x4), w8[0], w8[1], w8[2], w8[3]);
@@ -575,7 +576,7 @@ __global__ void __launch_bounds__(hl_threads(KWC), 1) conv_moments_halo_kernel(c
         };
         if (tma_st) {
           if (half == 0 && lane == 0) ptx::bulk_wait_read0();       // the pair's previous store has left the buffer
-          ptx::named_barrier(pair_bar, 64);
+          if (!(HL_DBG(p) & 128)) ptx::named_barrier(pair_bar, 64);
         }
         // KWC: out[j] = D[j][kw = 0] + D[j+1][kw = 1] + D[j+2][kw = 2]; rows j+1, j+2 are the next TMEM lanes = the next
         // threads of this warp (R = 32: a quarter is one tile row; lanes 30, 31 wrap into junk and are never stored)
@@ -585,6 +586,11 @@ __global__ void __launch_bounds__(hl_threads(KWC), 1) conv_moments_halo_kernel(c
           ptx::tmem_ld16(taddr + NT, t1);
           ptx::tmem_ld16(taddr + 2 * NT, t2);
           ptx::tmem_ld_wait();
+          if (HL_DBG(p) & 32) {
+#pragma unroll
+            for (int j = 0; j < 16; ++j) a[j] = __float_as_uint(__uint_as_float(a[j]) + __uint_as_float(t1[j]) + __uint_as_float(t2[j]));
+            return;
+          }
 #pragma unroll
           for (int j = 0; j < 16; ++j)
             a[j] = __float_as_uint(__uint_as_float(a[j]) + __shfl_down_sync(0xffffffffu, __uint_as_float(t1[j]), 1) +
@@ -781,8 +787,8 @@ __global__ void __launch_bounds__(hl_threads(KWC), 1) conv_moments_halo_kernel(c
               ptx::tc_fence_before();
               __syncwarp();
               if (lane == 0) ptx::mbar_arrive(acc_empty(as));
-              ptx::fence_proxy_async();                               // generic-proxy writes -> visible to the TMA
-              ptx::named_barrier(pair_bar, 64);
+              if (!(HL_DBG(p) & 64)) ptx::fence_proxy_async();        // generic-proxy writes -> visible to the TMA
+              if (!(HL_DBG(p) & 128)) ptx::named_barrier(pair_bar, 64);
               if (half == 0 && lane == 0 && tc.store && oy_i < p.Ho && ob < p.B && !(HL_DBG(p) & 8)) {
                 ptx::tma_store_5d(&maps.d, stg, nt_i * NT, 0, tx * p.TWo, oy_i, ob);
                 ptx::bulk_commit_group();

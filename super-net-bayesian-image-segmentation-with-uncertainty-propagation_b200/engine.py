@@ -208,8 +208,10 @@ class InferenceEngine:
         # ---- head -----------------------------------------------------------------------------------
         self.out_hw = (h, w)
         C = m.n_labels
-        self.p = torch.empty((B, h * w, C), device=dev, dtype=torch.float32)
-        self.v = torch.empty_like(self.p)
+        # both output maps live in ONE buffer (p = pv[0], v = pv[1]): the host-facing pipeline moves them with a single
+        # device-to-host copy per batch
+        self.pv = torch.empty((2, B, h * w, C), device=dev, dtype=torch.float32)
+        self.p, self.v = self.pv[0], self.pv[1]
         self.pre_m = torch.empty_like(self.p)
         self.pre_v = torch.empty_like(self.p)
         wf, wsf = m.conv_final.weights()
@@ -584,8 +586,9 @@ class StreamingPipeline:
         self.streams = [torch.cuda.Stream(device=self.device) for _ in range(depth)]
         self.done = [torch.cuda.Event() for _ in range(depth)]
         e0 = self.engines[0]
-        self.p_host = [torch.empty(e0.p.shape, dtype=torch.float32).pin_memory() for _ in range(depth)]
-        self.v_host = [torch.empty(e0.p.shape, dtype=torch.float32).pin_memory() for _ in range(depth)]
+        self.pv_host = [torch.empty(e0.pv.shape, dtype=torch.float32).pin_memory() for _ in range(depth)]
+        self.p_host = [t[0] for t in self.pv_host]
+        self.v_host = [t[1] for t in self.pv_host]
         self._next = 0
         self._busy = [False] * depth
         for eng, st in zip(self.engines, self.streams):          # capture each graph on its own stream
@@ -609,8 +612,7 @@ class StreamingPipeline:
             eng.sync_weights()                   # operands follow in-place weight updates (every engine has its own)
             eng.x_in.copy_(x_host, non_blocking=True)
             p, v = eng.forward_resident()
-            self.p_host[slot].copy_(p, non_blocking=True)
-            self.v_host[slot].copy_(v, non_blocking=True)
+            self.pv_host[slot].copy_(eng.pv, non_blocking=True)      # both maps, one DMA
             self.done[slot].record(st)
         self._busy[slot] = True
         return slot
