@@ -48,8 +48,15 @@ namespace sn {
 constexpr int HL_BM = 128;
 constexpr int HL_KC = 32;
 constexpr int HL_THREADS = 576;       // 18 warps: TMA, UMMA, 8 x q reduction, 8 x epilogue
-constexpr int HL_THREADS_2SETS = 832; // 26 warps: a second set of 8 epilogue warps (kw-concatenated kernels)
-__host__ __device__ constexpr int hl_threads(bool kwc) { return kwc ? HL_THREADS_2SETS : HL_THREADS; }
+constexpr int HL_THREADS_2SETS = 832; // 26 warps: a second set of 8 epilogue warps
+// Two epilogue sets (on alternate tiles, set s draining TMEM stage s) where the epilogue is on the critical path: the
+// kw-concatenated kernels.  Tried and measured neutral for the forward kernels with two pixel tiles per weight slot
+// (G = 2; conv3 0.246 vs 0.240 ms): there the UMMA issuer does wait for the pair's epilogues (28 % of its samples on
+// acc_empty, tools/ncu_waits.py), but the layer is bound by shared-memory bandwidth -- every N <= 128 UMMA streams
+// both operands from shared memory at exactly 128 B/clk, and the TMA fills and the q reduction share that pipe
+// (profiles/r02_kwc_knobs.md section 6) -- so a second set only moves the wait.  `g == 2 && !dgrad` re-enables it.
+__host__ __device__ constexpr bool hl_two_sets(bool kwc, int g, bool dgrad) { return kwc; }
+__host__ __device__ constexpr int hl_threads(bool two_sets) { return two_sets ? HL_THREADS_2SETS : HL_THREADS; }
 constexpr int HL_MAX_BSLOTS = 36;
 constexpr int HL_MAX_ASTAGES = 4;
 constexpr int HL_SMEM = 232448;        // 227 KB: always requested so exactly one CTA owns an SM (and its TMEM)
@@ -158,7 +165,7 @@ __device__ __forceinline__ TileCoord decode_group_tile(int grp, int t, const HlP
 // The lane shift must stay inside one 32-lane TMEM quarter (a warp only reads its own quarter), so the halo box is
 // R = 32 columns wide: quarter = one output row of the tile, lanes 30 / 31 are the halo margin that is junk anyway.
 template <int NT, int KS, bool RESIDENT, bool DGRAD, int G = 1, bool KWC = false>
-__global__ void __launch_bounds__(hl_threads(KWC), 1) conv_moments_halo_kernel(const __grid_constant__ HlMaps maps,
+__global__ void __launch_bounds__(hl_threads(hl_two_sets(KWC, G, DGRAD)), 1) conv_moments_halo_kernel(const __grid_constant__ HlMaps maps,
                                                                           const HlP p) {
   static_assert(!KWC || (NT == 32 && KS == 3 && G == 1), "kw-concatenation: 32-column tiles of a 3x3 conv");
   constexpr int NB = KWC ? KS * NT : NT;                  // rows (GEMM N) of one weight plane of a slot
@@ -224,7 +231,8 @@ __global__ void __launch_bounds__(hl_threads(KWC), 1) conv_moments_halo_kernel(c
     ptx::tmem_alloc(tmem_slot, TMEM_COLS);
     ptx::tmem_relinquish();
   }
-  for (int i = threadIdx.x; i < p.s_len; i += hl_threads(KWC)) s_sm[i] = p.s[i];
+  constexpr bool TWO_SETS = hl_two_sets(KWC, G, DGRAD);
+  for (int i = threadIdx.x; i < p.s_len; i += hl_threads(TWO_SETS)) s_sm[i] = p.s[i];
   ptx::tc_fence_before();
   __syncthreads();
   ptx::tc_fence_after();
@@ -499,7 +507,7 @@ __global__ void __launch_bounds__(hl_threads(KWC), 1) conv_moments_halo_kernel(c
       // shuffles, converts, stores: ~500 instructions per tile at ~0.17 IPC) is the longest path per tile (ncu: the
       // issuer waits on acc_empty, the reduction warps on q_empty).  Two sets of eight warps take alternate tiles, set s
       // always draining accumulator stage s.
-      constexpr int ESETS = KWC ? 2 : 1;
+      constexpr int ESETS = TWO_SETS ? 2 : 1;
       const int eset = (warp - 10) >> 3;
       const int q = warp & 3;                   // TMEM lane quarter this warp may access
       const int half = ((warp - 10) >> 2) & 1;  // which half of the tile's NT columns this warp converts
@@ -521,6 +529,7 @@ __global__ void __launch_bounds__(hl_threads(KWC), 1) conv_moments_halo_kernel(c
           it.next(p);
           if (ESETS == 2 && (titer & 1) != eset) continue;     // the other set's tile
         } else {
+          if (ESETS == 2 && (titer & 1) != eset) continue;     // the other set's half of the pair
           tc = decode_group_tile((int)blockIdx.x + (titer >> 1) * (int)gridDim.x, titer & 1, p);
         }
         const int as = titer & 1;
@@ -700,13 +709,26 @@ __global__ void __launch_bounds__(hl_threads(KWC), 1) conv_moments_halo_kernel(c
               d_hi = p.dst + ((((size_t)ob * p.dh + oy + p.dy0) * p.dw + ox + p.dx0) * 3) * p.dc + p.dc0 + nch;
             }
           }
-          if constexpr (KWC) {
+          if constexpr (TWO_SETS) {
             // mean first, then variance (one 16-bit gate mask in between): half the live registers of the joint form,
             // which matters at the 72 registers per thread the two epilogue sets leave
             uint32_t gate = 0xFFFFu;
             {
               uint32_t am[16];
-              load_kwc16(lane_base + c0, am);
+              if constexpr (KWC) {
+                load_kwc16(lane_base + c0, am);
+              } else {
+                ptx::tmem_ld16(lane_base + c0, am);
+                if constexpr (CONCAT) {
+                  uint32_t am2[16];
+                  ptx::tmem_ld16(lane_base + NT + c0, am2);     // the hi x W_lo half of the mean
+                  ptx::tmem_ld_wait();
+#pragma unroll
+                  for (int j = 0; j < 16; ++j) am[j] = __float_as_uint(__uint_as_float(am[j]) + __uint_as_float(am2[j]));
+                } else {
+                  ptx::tmem_ld_wait();
+                }
+              }
               if (p.relu) {
                 gate = 0;
 #pragma unroll
@@ -748,7 +770,12 @@ __global__ void __launch_bounds__(hl_threads(KWC), 1) conv_moments_halo_kernel(c
             }
             {
               uint32_t av[16];
-              load_kwc16(lane_base + NB + c0, av);
+              if constexpr (KWC) {
+                load_kwc16(lane_base + NB + c0, av);
+              } else {
+                ptx::tmem_ld16(lane_base + (CONCAT ? 2 * NT : NT) + c0, av);
+                ptx::tmem_ld_wait();
+              }
 #pragma unroll
               for (int j4 = 0; j4 < 16; j4 += 4) {
                 const float4 s4 = *reinterpret_cast<const float4*>(s_sm + nch + j4);   // warp-uniform: broadcast
@@ -1024,7 +1051,7 @@ static int hl_launch3(const HlMaps& maps, const HlP& p, cudaStream_t st) {
   }();
   cudaLaunchConfig_t cfg{};
   cfg.gridDim = dim3((unsigned)grid);
-  cfg.blockDim = dim3(hl_threads(KWC));
+  cfg.blockDim = dim3(hl_threads(hl_two_sets(KWC, G, DGRAD)));
   cfg.dynamicSmemBytes = HL_SMEM;
   cfg.stream = st;
   cudaLaunchAttribute attr[1];
@@ -1136,14 +1163,14 @@ static int hl_plan(HlP& p, const HaloTiling& t, int keff, int ncols, int nt, int
   // every SM busy and the doubled A stages still leave >= 3 weight slots
   p.pix_tiles = p.tiles_x * p.tiles_y * p.tiles_b;
   p.total_groups = 0;
-  static const bool dual = [] {
+  static const int dual = [] {          // 0: off, 1: 64-column tiles (default), 2: 128-column tiles too (A/B)
     const char* e = getenv("SN_DUAL");
-    return e == nullptr || e[0] != '0';
+    return e == nullptr ? 1 : atoi(e);
   }();
   // (measured at batch 64: +11 % on the 64-column layers conv3 / up3_conv1, whose UMMA pipe idled waiting for weights;
   //  -10..25 % on the 128-column layers, where the pair's two epilogues can no longer hide behind the next tile's
   //  UMMAs -- so only N tiles of 64 columns use it)
-  if (dual && nt == 64 && !p.b_resident && (keff == 3 || keff == 1)) {
+  if (dual && (nt == 64 || (dual >= 2 && nt == 128)) && !p.b_resident && (keff == 3 || keff == 1)) {
     const long long groups = (long long)p.tiles_n * ((p.pix_tiles + 1) / 2);
     const int a_stage2 = 2 * a_stage;
     const int sb2 = (avail - 2 * a_stage2) / b_slot;
