@@ -6,7 +6,9 @@ import sys
 
 rep, launches, out = sys.argv[1:4]
 names = sys.argv[4].split(",") if len(sys.argv) > 4 else None
-raw = subprocess.run(["ncu", "-i", rep, "--page", "raw", "--csv"], capture_output=True, text=True).stdout
+# a report, or the csv of its raw page (`ncu -i rep --page raw --csv`, made on the GPU box when the report is too big)
+raw = open(rep).read() if rep.endswith(".csv") else \
+    subprocess.run(["ncu", "-i", rep, "--page", "raw", "--csv"], capture_output=True, text=True).stdout
 rows = list(csv.reader(raw.splitlines()))
 h = rows[0]
 cols = [("Kernel Name", "kernel"), ("launch__grid_size", "grid"), ("gpu__time_duration.sum", "us"),
