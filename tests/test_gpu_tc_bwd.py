@@ -429,16 +429,17 @@ def _elbo_grads_fast_vs_oracle(S, variant, C, in_ch, B, alpha, kl):
 def test_hippocampus_elbo_gradients_fast(S, C):
     errs, errs_bwd = _elbo_grads_fast_vs_oracle(S, "hippocampus", C, 1, 4, 1.0, 1e-3)
     assert max(errs.values()) < 1e-2, errs
-    assert max(errs_bwd.values()) < 1e-2, errs_bwd
+    assert max(errs_bwd.values()) < 5e-3, errs_bwd          # measured 0.9e-3 / 1.7e-3
 
 
 def test_brats_elbo_gradients_fast(S):
     errs, errs_bwd = _elbo_grads_fast_vs_oracle(S, "brats", 4, 4, 1, O.BRATS_ALPHA, 1e-5)
-    # SURVEY.md 8d's 1e-2 per tensor holds for the backward chain itself (gradients vs exact arithmetic on the FAST
-    # forward's trajectory).  Against the fp64 oracle's own trajectory the gate / arg-max decisions of the bf16x3
-    # forward add their sqrt(flipped fraction) on top (the input gradient of the same network: 9.2e-3, of which 7e-5
-    # is the backward's), which takes the worst tensor (one w_sigma) to 1.8e-2: bar 2e-2 there.
-    assert max(errs_bwd.values()) < 1e-2, errs_bwd
+    # The backward chain itself (gradients vs exact arithmetic on the FAST forward's trajectory) is well inside SURVEY.md
+    # 8d's 1e-2 per tensor: worst tensor 1.9e-3 (conv5.w_mu; single-bf16 wgrad operands), bar 5e-3.  Against the fp64
+    # oracle's own trajectory the gate / arg-max decisions of the bf16x3 forward add their sqrt(flipped fraction) on top
+    # (the input gradient of the same network: 9.2e-3, of which 7e-5 is the backward's), which takes the worst tensor
+    # (up4_conv2x2.w_sigma) to 1.8e-2: bar 2e-2 there.
+    assert max(errs_bwd.values()) < 5e-3, errs_bwd
     assert max(errs.values()) < 2e-2, errs
 
 
