@@ -28,6 +28,10 @@ import torch  # noqa: E402
 METRIC = "BraTS slices/sec (mean+var maps)"
 UNIT = "slices/s"
 N_KERNELS, N_LABELS, IN_CH, IN_HW, OUT_HW = 32, 4, 4, 204, 186
+# engines (own buffers, CUDA graph, stream) the host-to-host pipeline rotates through: with 3 the H2D of batch i+1 and
+# the D2H of batch i-1 never wait for a free slot (measured e2e / resident: 0.96-0.98 at depth 2, 0.98-0.99 at 3,
+# 1.00 at 4; profiles/r02_g21.txt)
+PIPE_DEPTH = int(os.environ.get("SN_PIPE_DEPTH", "3"))
 
 
 def peaks():
@@ -368,7 +372,7 @@ def main():
         eng.x_in.copy_(x_host, non_blocking=True)
         step = eng.forward_resident
         launches_per_step = eng.n_launches
-        pipe = StreamingPipeline(model, B, IN_HW, IN_HW, IN_CH, dev, depth=2)
+        pipe = StreamingPipeline(model, B, IN_HW, IN_HW, IN_CH, dev, depth=PIPE_DEPTH)
         p_host = pipe.p_host[0]
         join = pipe.join
 
@@ -498,7 +502,7 @@ def main():
             "e2e": {"value": round(e2e, 1), "unit": UNIT, "h2d_bytes_per_step": int(x_host.numel() * 4),
                     "d2h_bytes_per_step": int(2 * p_host.numel() * 4), "ms_per_step": round(ms_e2e / args.steps, 4),
                     "how": "StreamingPipeline.submit(): pinned host batch -> H2D -> CUDA-graph forward -> D2H of both "
-                           "maps, 2 engines round-robin so copies overlap the next batch's kernels"},
+                           f"maps (one D2H), {PIPE_DEPTH} engines round-robin so copies overlap the other batches' kernels"},
             "gpu_launches": (launches_per_step or 0) * args.steps,
             "clocks": clocks,
         }
