@@ -60,7 +60,7 @@ class sn_tc_wgrad_desc(C.Structure):
 
 SN_CONV_RELU = 1
 SN_TC_RELU, SN_TC_UPCONV, SN_TC_DST_F32, SN_TC_IM2COL, SN_TC_ROWS, SN_TC_EXACT = 1, 2, 4, 8, 16, 32
-SN_TC_KWC, SN_TC_NO_KWC = 64, 128
+SN_TC_KWC, SN_TC_NO_KWC, SN_TC_CTA2, SN_TC_NO_CTA2 = 64, 128, 256, 512
 
 
 def header_path() -> str:

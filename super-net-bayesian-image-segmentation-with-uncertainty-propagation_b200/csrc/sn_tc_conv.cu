@@ -468,8 +468,8 @@ int conv_moments_halo_dgrad_dispatch(const sn_tc_dgrad_desc* d, cudaStream_t str
 extern "C" int sn_conv_moments_bwd_data_tc(const sn_tc_dgrad_desc* d, sn_stream_t st) {
   SN_REQUIRE(d, SN_ERR_BAD_ARG, "dgrad_tc: null descriptor");
   const bool upconv = (d->flags & SN_TC_UPCONV) != 0;
-  SN_REQUIRE((d->flags & ~(SN_TC_UPCONV | SN_TC_KWC | SN_TC_NO_KWC)) == 0, SN_ERR_BAD_ARG,
-             "dgrad_tc: only SN_TC_UPCONV / SN_TC_KWC / SN_TC_NO_KWC are valid flags");
+  SN_REQUIRE((d->flags & ~(SN_TC_UPCONV | SN_TC_KWC | SN_TC_NO_KWC | SN_TC_CTA2 | SN_TC_NO_CTA2)) == 0, SN_ERR_BAD_ARG,
+             "dgrad_tc: only SN_TC_UPCONV / SN_TC_KWC / SN_TC_NO_KWC / SN_TC_CTA2 / SN_TC_NO_CTA2 are valid flags");
   SN_REQUIRE(d->batch > 0 && d->in_h > 0 && d->in_w > 0 && d->cout > 0, SN_ERR_BAD_ARG, "dgrad_tc: bad geometry");
   SN_REQUIRE(d->ksize >= 1 && d->ksize <= 3, SN_ERR_UNSUPPORTED, "dgrad_tc: kernel size %d", d->ksize);
   SN_REQUIRE(!upconv || d->ksize == 2, SN_ERR_BAD_ARG, "dgrad_tc: SN_TC_UPCONV needs ksize == 2");

@@ -59,6 +59,7 @@ __host__ __device__ constexpr bool hl_two_sets(bool kwc, int g, bool dgrad) { re
 __host__ __device__ constexpr int hl_threads(bool two_sets) { return two_sets ? HL_THREADS_2SETS : HL_THREADS; }
 constexpr int HL_MAX_BSLOTS = 36;
 constexpr int HL_MAX_ASTAGES = 4;
+constexpr int HL_CTA2_MAX_BSLOTS = 16;  // CTA pairs: the leader also keeps one "peer's half-slot landed" barrier per slot
 constexpr int HL_SMEM = 232448;        // 227 KB: always requested so exactly one CTA owns an SM (and its TMEM)
 
 struct HlMaps {
@@ -99,6 +100,7 @@ struct HlP {
   int csplit, gate[2];
   int v8;                  // every packed row segment the epilogue touches is 32-byte aligned: use 256-bit accesses
   int kwc;                 // kw-concatenated variant (see the kernel): R = 32, one weight slot per filter row
+  int cta2;                // CTA pair (cta_group::2) variant: M = 256 over two SMs, half of every weight slot per CTA
   int tma_store;           // forward KWC, packed destination: rows leave through shared memory + TMA tensor stores
   int dbg;                 // SN_HL_DBG knob experiments (profiling only; results are wrong when non-zero): 1 epilogue
                            // skips its work, 2 one UMMA group per tile, 4 reducers skip their loads, 8 no global stores
@@ -164,13 +166,23 @@ __device__ __forceinline__ TileCoord decode_group_tile(int grp, int t, const HlP
 // of math.  One A fetch for three taps cuts the UMMAs per (kh, K step) from 9 (414 cycles) to 4 of N = 96 (~224).
 // The lane shift must stay inside one 32-lane TMEM quarter (a warp only reads its own quarter), so the halo box is
 // R = 32 columns wide: quarter = one output row of the tile, lanes 30 / 31 are the halo margin that is junk anyway.
-template <int NT, int KS, bool RESIDENT, bool DGRAD, int G = 1, bool KWC = false>
+// CTA2 (NT = 128, streamed weights): two CTAs of a cluster -- the two SMs of a TPC -- work on two pixel tiles that
+// share one N tile, and every UMMA is a cta_group::2 instruction of M = 256: rows 0-127 are the leader CTA's halo tile,
+// rows 128-255 the peer's, and each CTA holds (and TMA-loads) only HALF of the weight slot (64 of the 128 rows of
+// B).  Why: at N = 128 a single-CTA UMMA streams 4 KB of A + 4 KB of B per 64 cycles = exactly the 128 B/clk of shared
+// memory, so the weight TMA fills (216 KB per channel block and tile) push the UMMA pipe down to ~70 % busy
+// (profiles/r02_kwc_knobs.md section 6).  A pair halves the B bytes each SM reads AND writes.
+// Protocol on top of the single-CTA one: the leader's issuer also waits for the peer's operands (pa_full / pb_full,
+// relayed by the peer's otherwise idle warp 1 with remote mbarrier arrives), its commits are multicast to both CTAs'
+// a_empty / b_empty / acc_full, and the peer's epilogue warps release the accumulator stage on the LEADER's acc_empty.
+template <int NT, int KS, bool RESIDENT, bool DGRAD, int G = 1, bool KWC = false, bool CTA2 = false>
 __global__ void __launch_bounds__(hl_threads(hl_two_sets(KWC, G, DGRAD)), 1) conv_moments_halo_kernel(const __grid_constant__ HlMaps maps,
                                                                           const HlP p) {
   static_assert(!KWC || (NT == 32 && KS == 3 && G == 1), "kw-concatenation: 32-column tiles of a 3x3 conv");
+  static_assert(!CTA2 || (NT == 128 && !RESIDENT && G == 1 && !KWC), "CTA pairs: 128-column tiles, streamed weights");
   constexpr int NB = KWC ? KS * NT : NT;                  // rows (GEMM N) of one weight plane of a slot
   constexpr int SLOTS_PER_CB = KWC ? KS : KS * KS;        // weight slots per 32-channel block: filter rows / taps
-  constexpr int B_PLANE = NB * HL_KC * 2;
+  constexpr int B_PLANE = (CTA2 ? NB / 2 : NB) * HL_KC * 2;   // CTA pair: this CTA's half of the plane
   constexpr int B_SLOT = 3 * B_PLANE;
   constexpr bool CONCAT = !KWC && NT <= 64;               // hi x [W_hi ; W_lo] as one UMMA of N = 2*NT
   constexpr int ACC_STAGE = KWC ? 2 * NB : (CONCAT ? 3 * NT : 2 * NT);     // TMEM columns per accumulator stage
@@ -191,6 +203,20 @@ __global__ void __launch_bounds__(hl_threads(hl_two_sets(KWC, G, DGRAD)), 1) con
   auto q_full = [&](int s) { return bar_base + 8u * (2 * HL_MAX_ASTAGES + 2 * HL_MAX_BSLOTS + 4 + s); };
   auto q_empty = [&](int s) { return bar_base + 8u * (2 * HL_MAX_ASTAGES + 2 * HL_MAX_BSLOTS + 6 + s); };
   const uint32_t tmem_slot = bar_base + 8u * (2 * HL_MAX_ASTAGES + 2 * HL_MAX_BSLOTS + 8);
+  // CTA pair, leader only: "the peer's A stage / weight half-slot has landed" (sb <= HL_CTA2_MAX_BSLOTS there)
+  auto pa_full = [&](int s) { return bar_base + 8u * (2 * HL_MAX_ASTAGES + 2 * HL_MAX_BSLOTS + 9 + s); };
+  auto pb_full = [&](int s) { return bar_base + 8u * (2 * HL_MAX_ASTAGES + 2 * HL_MAX_BSLOTS + 9 + HL_MAX_ASTAGES + s); };
+  const uint32_t crank = CTA2 ? ptx::cluster_ctarank() : 0u;
+  // CTA pairs poll (barriers there are completed from the other CTA; see mbar_wait_poll), everything else may park
+  auto WAIT = [](uint32_t bar, uint32_t parity) {
+    if constexpr (CTA2) ptx::mbar_wait_poll(bar, parity);
+    else ptx::mbar_wait(bar, parity);
+  };
+  // persistent walk: tiles (or tile pairs: G = 2 inside one CTA, CTA2 across the pair) u0, u0 + ustep, ...
+  constexpr bool GROUPED = G == 2 || CTA2;
+  const int u0 = CTA2 ? (int)(blockIdx.x >> 1) : (int)blockIdx.x;
+  const int ustep = CTA2 ? (int)(gridDim.x >> 1) : (int)gridDim.x;
+  const int n_units = GROUPED ? p.total_groups : p.total_tiles;
   const int bar_off = p.sa * a_stage + p.sb * B_SLOT;
   volatile uint32_t* tmem_slot_gen =
       reinterpret_cast<volatile uint32_t*>(smem_gen + bar_off + 8 * (2 * HL_MAX_ASTAGES + 2 * HL_MAX_BSLOTS + 8));
@@ -219,22 +245,32 @@ __global__ void __launch_bounds__(hl_threads(hl_two_sets(KWC, G, DGRAD)), 1) con
       ptx::mbar_init(b_full(s), 1);
       ptx::mbar_init(b_empty(s), 1);
     }
+    if constexpr (CTA2) {
+      for (int s = 0; s < p.sa; ++s) ptx::mbar_init(pa_full(s), 1);
+      for (int s = 0; s < p.sb; ++s) ptx::mbar_init(pb_full(s), 1);
+    }
     for (int s = 0; s < 2; ++s) {
       ptx::mbar_init(acc_full(s), 1);
-      ptx::mbar_init(acc_empty(s), 8);        // 8 epilogue warps
+      ptx::mbar_init(acc_empty(s), CTA2 ? 16 : 8);        // 8 epilogue warps (CTA pair: of both CTAs, on the leader)
       ptx::mbar_init(q_full(s), 8);           // 8 reducer warps
       ptx::mbar_init(q_empty(s), 8);          // 8 epilogue warps
     }
     ptx::fence_barrier_init();
   }
   if (warp == 1) {
-    ptx::tmem_alloc(tmem_slot, TMEM_COLS);
-    ptx::tmem_relinquish();
+    if constexpr (CTA2) {
+      ptx::tmem_alloc2(tmem_slot, TMEM_COLS);
+      ptx::tmem_relinquish2();
+    } else {
+      ptx::tmem_alloc(tmem_slot, TMEM_COLS);
+      ptx::tmem_relinquish();
+    }
   }
   constexpr bool TWO_SETS = hl_two_sets(KWC, G, DGRAD);
   for (int i = threadIdx.x; i < p.s_len; i += hl_threads(TWO_SETS)) s_sm[i] = p.s[i];
   ptx::tc_fence_before();
   __syncthreads();
+  if constexpr (CTA2) ptx::cluster_sync_all();      // both CTAs' barriers exist before any remote arrive / multicast commit
   ptx::tc_fence_after();
   const uint32_t tmem_base = *tmem_slot_gen;
   // Everything below that depends on the previous kernel of the stream -- activation tiles (TMA), saved activations
@@ -245,21 +281,19 @@ __global__ void __launch_bounds__(hl_threads(hl_two_sets(KWC, G, DGRAD)), 1) con
   if (warp == 0) {
     // ===================== TMA producer =====================
     if (lane == 0) {
-      // one weight slot: the three operand planes of tap `tap` (KWC: of filter row `tap`, its kw taps stacked along N)
+      // one weight slot = ONE TMA request: the weight tensor is mapped as (cin, n, tap, plane) and the box takes all three
+      // operand planes of tap `tap` (KWC: the three kw taps of filter row `tap` as well), landing as [plane][(kw)][n] rows
+      // -- exactly the slot layout.  (Three / nine requests per slot made the weight stream request-rate bound: ~250
+      // cycles per request whatever its size, profiles/r02_cta2.md.)
       auto load_b_slot = [&](uint32_t sb_addr, uint32_t bar, int cbt, int tap, int ncol0, int n0) {
-#pragma unroll
-        for (int pl = 0; pl < 3; ++pl) {
-          if constexpr (KWC) {
-#pragma unroll
-            for (int kw = 0; kw < KS; ++kw)
-              ptx::tma_load_3d(sb_addr + pl * B_PLANE + kw * (NT * HL_KC * 2), &maps.w, bar, cbt * HL_KC, n0,
-                               pl * p.taps_w + tap * KS + kw);
-          } else {
-            // regular conv: weights [3*taps][cout][cin], rows n0.. of tap `tap`; up-conv: [3][4*cout][cin], the N
-            // tile may span several parity groups (rows ncol0.. of the (parity, channel) axis)
-            ptx::tma_load_3d(sb_addr + pl * B_PLANE, &maps.w, bar, cbt * HL_KC, p.upconv ? ncol0 : n0,
-                             p.upconv ? pl : pl * p.taps_w + tap);
-          }
+        const int row = p.upconv ? ncol0 : n0;                      // up-conv: the (parity, channel) axis, one "tap"
+        const int t0 = p.upconv ? 0 : (KWC ? tap * KS : tap);
+        if constexpr (CTA2) {
+          // CTA pair: this CTA's 64 rows of the 128-row N tile, landing in its own shared memory but signalled on the
+          // LEADER's b_full, which expects both halves
+          ptx::tma_load_4d_pair(sb_addr, &maps.w, ptx::map_to_rank(bar, 0), cbt * HL_KC, row + (int)crank * (NT / 2), t0, 0);
+        } else {
+          ptx::tma_load_4d(sb_addr, &maps.w, bar, cbt * HL_KC, row, t0, 0);
         }
       };
       bool dep_waited = false;
@@ -278,10 +312,13 @@ __global__ void __launch_bounds__(hl_threads(hl_two_sets(KWC, G, DGRAD)), 1) con
             load_b_slot(b_base + slot * B_SLOT, b_full(slot), cbt, tap, ncol0, n0);
           }
       }
-      const int n_units = G == 1 ? p.total_tiles : p.total_groups;
-      for (int tile = blockIdx.x, titer = 0; tile < n_units; tile += gridDim.x, ++titer, it.next(p)) {
+      for (int tile = u0, titer = 0; tile < n_units; tile += ustep, ++titer, it.next(p)) {
         int nt_i, x0s[G], y0s[G], b0s[G];
-        if constexpr (G == 1) {
+        if constexpr (CTA2) {
+          const TileCoord c = decode_group_tile(tile, (int)crank, p);      // this CTA's half of the pair
+          nt_i = c.nt;
+          x0s[0] = c.tx * p.TWo - p.pad; y0s[0] = c.ty * p.THo - p.pad; b0s[0] = c.tb * p.TN;
+        } else if constexpr (G == 1) {
           nt_i = it.nt;
           x0s[0] = it.tx * p.TWo - p.pad; y0s[0] = it.ty * p.THo - p.pad; b0s[0] = it.tb * p.TN;
         } else {
@@ -306,7 +343,7 @@ __global__ void __launch_bounds__(hl_threads(hl_two_sets(KWC, G, DGRAD)), 1) con
             const int stage = ai % p.sa;
             const uint32_t parity = (uint32_t)(ai / p.sa) & 1u;
             ++ai;
-            ptx::mbar_wait(a_empty(stage), parity ^ 1u);
+            WAIT(a_empty(stage), parity ^ 1u);
             ptx::mbar_arrive_expect_tx(a_full(stage), (uint32_t)(G * 3 * p.rows_box * 64));
             const uint32_t sa_addr = smem_base + stage * a_stage;
 #pragma unroll
@@ -329,9 +366,9 @@ __global__ void __launch_bounds__(hl_threads(hl_two_sets(KWC, G, DGRAD)), 1) con
                 slot = bi % p.sb;
                 const uint32_t parity = (uint32_t)(bi / p.sb) & 1u;
                 ++bi;
-                ptx::mbar_wait(b_empty(slot), parity ^ 1u);
+                WAIT(b_empty(slot), parity ^ 1u);
               }
-              ptx::mbar_arrive_expect_tx(b_full(slot), (uint32_t)B_SLOT);
+              if (!CTA2 || crank == 0) ptx::mbar_arrive_expect_tx(b_full(slot), (uint32_t)(CTA2 ? 2 * B_SLOT : B_SLOT));
               load_b_slot(b_base + slot * B_SLOT, b_full(slot), cbt, tap, ncol0, n0);
             }
           }
@@ -349,7 +386,7 @@ __global__ void __launch_bounds__(hl_threads(hl_two_sets(KWC, G, DGRAD)), 1) con
       // All 32 lanes run this loop (uniform control flow keeps the descriptor arithmetic in the uniform datapath);
       // one elected lane issues the UMMAs and commits.  Taps and K steps are fully unrolled so every descriptor is
       // "per-stage base + immediate": the issuing thread must sustain one UMMA per ~45 cycles.
-      constexpr uint32_t idesc_n = ptx::idesc_bf16_f32(HL_BM, NB);
+      constexpr uint32_t idesc_n = ptx::idesc_bf16_f32(CTA2 ? 2 * HL_BM : HL_BM, NB);
       constexpr uint32_t idesc_2n = ptx::idesc_bf16_f32(HL_BM, CONCAT ? 2 * NT : NT);
       // descriptor = constant high word | (1 << 16 | address >> 4) in the low word (smem < 256 KB: 14 bits);
       // high word of smem_desc_kmajor<64>: SBO = 512 B >> 4 at bits [32,46), version 1 at bit 46, SW64 (4) at [61,64)
@@ -363,19 +400,31 @@ __global__ void __launch_bounds__(hl_threads(hl_two_sets(KWC, G, DGRAD)), 1) con
       constexpr uint32_t SLOT16 = B_SLOT >> 4, BPLANE16 = B_PLANE >> 4;
       int a_stage_i = 0, b_slot_i = 0;
       uint32_t a_par = 0, b_par = 0;
-      const int n_units = G == 1 ? p.total_tiles : p.total_groups;
-      for (int tile = blockIdx.x, uiter = 0; tile < n_units; tile += gridDim.x, ++uiter) {
+      if (CTA2 && crank != 0) {
+        // ---- peer CTA of a pair: no UMMA issue here; relay "my operands have landed" to the leader's barriers, in the
+        // order the leader consumes them (a refill of a stage / slot needs the leader's multicast commit first, so no
+        // phase can be skipped or signalled twice)
+        for (int tile = u0; tile < n_units; tile += ustep) {
+          for (int cbt = 0; cbt < cblk; ++cbt) {
+            WAIT(a_full(a_stage_i), a_par);
+            if (leader) ptx::mbar_arrive_remote(pa_full(a_stage_i), 0);
+            if (++a_stage_i == p.sa) { a_stage_i = 0; a_par ^= 1u; }
+          }
+        }
+      } else
+      for (int tile = u0, uiter = 0; tile < n_units; tile += ustep, ++uiter) {
         // unit = one tile (G = 1, accumulator stage alternates) or a pair of tiles (G = 2, stage = tile of the pair)
         const int titer = uiter * G;
 #pragma unroll
         for (int t = 0; t < G; ++t)
-          ptx::mbar_wait(acc_empty((titer + t) & 1), (((uint32_t)(titer + t) >> 1) & 1u) ^ 1u);
+          WAIT(acc_empty((titer + t) & 1), (((uint32_t)(titer + t) >> 1) & 1u) ^ 1u);
         const int as = titer & 1;
         const uint32_t acc_mu0 = tmem_base + as * ACC_STAGE;
         for (int cbt = 0; cbt < cblk; ++cbt) {
-          ptx::mbar_wait(a_full(a_stage_i), a_par);
+          WAIT(a_full(a_stage_i), a_par);
+          if constexpr (CTA2) WAIT(pa_full(a_stage_i), a_par);
           if (RESIDENT && titer == 0) {
-            for (int tap = 0; tap < SLOTS_PER_CB; ++tap) ptx::mbar_wait(b_full(cbt * SLOTS_PER_CB + tap), 0);
+            for (int tap = 0; tap < SLOTS_PER_CB; ++tap) WAIT(b_full(cbt * SLOTS_PER_CB + tap), 0);
           }
           ptx::tc_fence_after();
           const uint32_t a_st = a_lo_base + a_stage_i * stage16;
@@ -390,7 +439,7 @@ __global__ void __launch_bounds__(hl_threads(hl_two_sets(KWC, G, DGRAD)), 1) con
               b0 = b_st + (uint32_t)tap * SLOT16;
             } else {
               slot = b_slot_i;
-              ptx::mbar_wait(b_full(slot), b_par);
+              WAIT(b_full(slot), b_par);
               ptx::tc_fence_after();
               if (++b_slot_i == p.sb) { b_slot_i = 0; b_par ^= 1u; }
               b0 = b_st + (uint32_t)slot * SLOT16;
@@ -409,23 +458,37 @@ __global__ void __launch_bounds__(hl_threads(hl_two_sets(KWC, G, DGRAD)), 1) con
                   if constexpr (CONCAT) {
                     ptx::umma_bf16(acc_mu, desc(a0 + k16), desc(b0 + k16), idesc_2n, acc);               // hi x [Whi;Wlo]
                     ptx::umma_bf16(acc_mu, desc(a0 + plane16 + k16), desc(b0 + k16), idesc_n, 1u);      // lo x Whi
+                  } else if constexpr (CTA2) {
+                    ptx::umma2_bf16(acc_mu, desc(a0 + k16), desc(b0 + k16), idesc_n, acc);
+                    ptx::umma2_bf16(acc_mu, desc(a0 + plane16 + k16), desc(b0 + k16), idesc_n, 1u);
+                    ptx::umma2_bf16(acc_mu, desc(a0 + k16), desc(b0 + BPLANE16 + k16), idesc_n, 1u);
                   } else {
                     ptx::umma_bf16(acc_mu, desc(a0 + k16), desc(b0 + k16), idesc_n, acc);
                     ptx::umma_bf16(acc_mu, desc(a0 + plane16 + k16), desc(b0 + k16), idesc_n, 1u);
                     ptx::umma_bf16(acc_mu, desc(a0 + k16), desc(b0 + BPLANE16 + k16), idesc_n, 1u);
                   }
-                  ptx::umma_bf16(acc_var, desc(a0 + 2 * plane16 + k16), desc(b0 + 2 * BPLANE16 + k16), idesc_n, acc);
+                  if constexpr (CTA2)
+                    ptx::umma2_bf16(acc_var, desc(a0 + 2 * plane16 + k16), desc(b0 + 2 * BPLANE16 + k16), idesc_n, acc);
+                  else
+                    ptx::umma_bf16(acc_var, desc(a0 + 2 * plane16 + k16), desc(b0 + 2 * BPLANE16 + k16), idesc_n, acc);
                 }
               }
             }
-            if (leader && !RESIDENT) ptx::umma_commit(b_empty(slot));
+            if (leader && !RESIDENT) {
+              if constexpr (CTA2) ptx::umma2_commit(b_empty(slot)); else ptx::umma_commit(b_empty(slot));
+            }
           }
-          if (leader) ptx::umma_commit(a_empty(a_stage_i));
+          if (leader) {
+            if constexpr (CTA2) ptx::umma2_commit(a_empty(a_stage_i)); else ptx::umma_commit(a_empty(a_stage_i));
+          }
           if (++a_stage_i == p.sa) { a_stage_i = 0; a_par ^= 1u; }
         }
         if (leader) {
 #pragma unroll
-          for (int t = 0; t < G; ++t) ptx::umma_commit(acc_full((titer + t) & 1));
+          for (int t = 0; t < G; ++t) {
+            if constexpr (CTA2) ptx::umma2_commit(acc_full((titer + t) & 1));
+            else ptx::umma_commit(acc_full((titer + t) & 1));
+          }
         }
       }
     }
@@ -438,8 +501,7 @@ __global__ void __launch_bounds__(hl_threads(hl_two_sets(KWC, G, DGRAD)), 1) con
       const int row = (warp - 2) * 32 + lane;
       int a_stage_i = 0;
       uint32_t a_par = 0;
-      const int n_units = G == 1 ? p.total_tiles : p.total_groups;
-      for (int tile = blockIdx.x, uiter = 0; tile < n_units; tile += gridDim.x, ++uiter) {
+      for (int tile = u0, uiter = 0; tile < n_units; tile += ustep, ++uiter) {
         float qsum[G];
 #pragma unroll
         for (int t = 0; t < G; ++t) qsum[t] = 0.f;
@@ -448,7 +510,7 @@ __global__ void __launch_bounds__(hl_threads(hl_two_sets(KWC, G, DGRAD)), 1) con
           if constexpr (DGRAD) {
             while (cb >= p.cblk_s[src]) { cb = 0; ++src; }
           }
-          ptx::mbar_wait(a_full(a_stage_i), a_par);
+          WAIT(a_full(a_stage_i), a_par);
           if (row < p.rows_box && !(HL_DBG(p) & 4)) {
 #pragma unroll
            for (int t = 0; t < G; ++t) {
@@ -495,7 +557,7 @@ __global__ void __launch_bounds__(hl_threads(hl_two_sets(KWC, G, DGRAD)), 1) con
         for (int t = 0; t < G; ++t) {
           const int titer = uiter * G + t;
           const int qs = titer & 1;
-          ptx::mbar_wait(q_empty(qs), (((uint32_t)titer >> 1) & 1u) ^ 1u);
+          WAIT(q_empty(qs), (((uint32_t)titer >> 1) & 1u) ^ 1u);
           qbuf[qs * 256 + row] = qsum[t];                      // rows >= rows_box hold 0
           __syncwarp();
           if (lane == 0) ptx::mbar_arrive(q_full(qs));
@@ -520,11 +582,13 @@ __global__ void __launch_bounds__(hl_threads(hl_two_sets(KWC, G, DGRAD)), 1) con
       TileIt it;
       it.init(blockIdx.x, gridDim.x, p);
       // G = 2: the "tiles" of this CTA are the halves of its tile pairs, in order (stage = half of the pair)
-      const int n_tiles_cta = G == 1 ? (p.total_tiles > (int)blockIdx.x ? (p.total_tiles - 1 - (int)blockIdx.x) / (int)gridDim.x + 1 : 0)
-                                     : 2 * (p.total_groups > (int)blockIdx.x ? (p.total_groups - 1 - (int)blockIdx.x) / (int)gridDim.x + 1 : 0);
+      const int n_units_cta = n_units > u0 ? (n_units - 1 - u0) / ustep + 1 : 0;
+      const int n_tiles_cta = G * n_units_cta;
       for (int titer = 0; titer < n_tiles_cta; ++titer) {
         TileCoord tc;
-        if constexpr (G == 1) {
+        if constexpr (CTA2) {
+          tc = decode_group_tile(u0 + titer * ustep, (int)crank, p);       // this CTA's half of the pair
+        } else if constexpr (G == 1) {
           tc.nt = it.nt; tc.tx = it.tx; tc.ty = it.ty; tc.tb = it.tb; tc.store = true;
           it.next(p);
           if (ESETS == 2 && (titer & 1) != eset) continue;     // the other set's tile
@@ -534,7 +598,12 @@ __global__ void __launch_bounds__(hl_threads(hl_two_sets(KWC, G, DGRAD)), 1) con
         }
         const int as = titer & 1;
         const uint32_t par = ((uint32_t)titer >> 1) & 1u;
-        ptx::mbar_wait(q_full(as), par);
+        // this warp's TMEM reads of stage `as` are done (CTA pair: the issuer lives in the leader CTA)
+        auto release_acc = [&]() {
+          if (CTA2 && crank != 0) ptx::mbar_arrive_remote(acc_empty(as), 0);
+          else ptx::mbar_arrive(acc_empty(as));
+        };
+        WAIT(q_full(as), par);
         const float* myq = qbuf + as * 256;
         float qv[taps];
 #pragma unroll
@@ -558,12 +627,12 @@ __global__ void __launch_bounds__(hl_threads(hl_two_sets(KWC, G, DGRAD)), 1) con
                            !(HL_DBG(p) & 8);
         if (!DGRAD && p.r_out != nullptr && half == 0 && nt_i == 0 && valid)
           p.r_out[((size_t)ob * p.Ho + oy_i) * p.Wo + ox_i] = r;
-        ptx::mbar_wait(acc_full(as), par);
+        WAIT(acc_full(as), par);
         ptx::tc_fence_after();
         if (HL_DBG(p) & 1) {
           ptx::tc_fence_before();
           __syncwarp();
-          if (lane == 0) ptx::mbar_arrive(acc_empty(as));
+          if (lane == 0) release_acc();
           continue;
         }
         const uint32_t lane_base = tmem_base + ((uint32_t)(q * 32) << 16) + as * ACC_STAGE + half * NH;
@@ -813,7 +882,7 @@ __global__ void __launch_bounds__(hl_threads(hl_two_sets(KWC, G, DGRAD)), 1) con
               // before the store handshake
               ptx::tc_fence_before();
               __syncwarp();
-              if (lane == 0) ptx::mbar_arrive(acc_empty(as));
+              if (lane == 0) release_acc();
               if (!(HL_DBG(p) & 64)) ptx::fence_proxy_async();        // generic-proxy writes -> visible to the TMA
               if (!(HL_DBG(p) & 128)) ptx::named_barrier(pair_bar, 64);
               if (half == 0 && lane == 0 && tc.store && oy_i < p.Ho && ob < p.B && !(HL_DBG(p) & 8)) {
@@ -881,7 +950,7 @@ __global__ void __launch_bounds__(hl_threads(hl_two_sets(KWC, G, DGRAD)), 1) con
         if (!tma_st) {
           ptx::tc_fence_before();
           __syncwarp();
-          if (lane == 0) ptx::mbar_arrive(acc_empty(as));    // this warp's TMEM reads of stage `as` are done
+          if (lane == 0) release_acc();
         }
       }
       if (KWC && !DGRAD && p.tma_store && half == 0 && lane == 0) ptx::bulk_wait_read0();   // staging must outlive the reads
@@ -890,7 +959,12 @@ __global__ void __launch_bounds__(hl_threads(hl_two_sets(KWC, G, DGRAD)), 1) con
 
   ptx::tc_fence_before();
   __syncthreads();
-  if (warp == 1) ptx::tmem_dealloc(tmem_base, TMEM_COLS);
+  if constexpr (CTA2) {
+    ptx::cluster_sync_all();          // the peer's shared memory / TMEM must outlive the leader's last UMMA and remote arrive
+    if (warp == 1) ptx::tmem_dealloc2(tmem_base, TMEM_COLS);
+  } else {
+    if (warp == 1) ptx::tmem_dealloc(tmem_base, TMEM_COLS);
+  }
 }
 
 // ---------------------------------------------------------------------------------------------------------
@@ -1022,29 +1096,59 @@ static int hl_make_dst_map(CUtensorMap* out, const sn_packed_view& v, int cout, 
   return SN_OK;
 }
 
-static int hl_make_weight_map(CUtensorMap* out, const void* w_packed, int taps, int cout, int cin, int nt) {
-  cuuint64_t dims[3] = {(cuuint64_t)cin, (cuuint64_t)cout, (cuuint64_t)(3 * taps)};
-  cuuint64_t strides[2] = {(cuuint64_t)cin * 2, (cuuint64_t)cin * cout * 2};
-  cuuint32_t box[3] = {HL_KC, (cuuint32_t)nt, 1};
-  cuuint32_t estr[3] = {1, 1, 1};
-  CUresult r = hl_encode_tiled()(out, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 3, const_cast<void*>(w_packed), dims, strides,
+// Prepared weights [3 planes][taps][n][cin] as a 4-D tensor (cin, n, tap, plane); one box = the three planes of
+// `box_taps` consecutive taps x `box_n` rows x 32 channels.
+static int hl_make_weight_map(CUtensorMap* out, const void* w_packed, int taps, int cout, int cin, int box_n,
+                              int box_taps = 1) {
+  cuuint64_t dims[4] = {(cuuint64_t)cin, (cuuint64_t)cout, (cuuint64_t)taps, 3};
+  cuuint64_t strides[3] = {(cuuint64_t)cin * 2, (cuuint64_t)cin * cout * 2, (cuuint64_t)taps * cin * cout * 2};
+  cuuint32_t box[4] = {HL_KC, (cuuint32_t)box_n, (cuuint32_t)box_taps, 3};
+  cuuint32_t estr[4] = {1, 1, 1, 1};
+  CUresult r = hl_encode_tiled()(out, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 4, const_cast<void*>(w_packed), dims, strides,
                                  box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_64B,
                                  CU_TENSOR_MAP_L2_PROMOTION_L2_128B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
   if (r != CUDA_SUCCESS) return fail(SN_ERR_DRIVER, "cuTensorMapEncodeTiled(weights) failed (%d)", (int)r);
   return SN_OK;
 }
 
-template <int NT, int KS, bool RESIDENT, bool DGRAD, int G = 1, bool KWC = false>
+template <int NT, int KS, bool RESIDENT, bool DGRAD, int G = 1, bool KWC = false, bool CTA2 = false>
 static int hl_launch3(const HlMaps& maps, const HlP& p, cudaStream_t st) {
   static std::once_flag once;
   static cudaError_t attr_err = cudaSuccess;
   std::call_once(once, [] {
-    attr_err = cudaFuncSetAttribute(conv_moments_halo_kernel<NT, KS, RESIDENT, DGRAD, G, KWC>,
+    attr_err = cudaFuncSetAttribute(conv_moments_halo_kernel<NT, KS, RESIDENT, DGRAD, G, KWC, CTA2>,
                                     cudaFuncAttributeMaxDynamicSharedMemorySize, HL_SMEM);
   });
   if (attr_err != cudaSuccess) return fail(SN_ERR_LAUNCH, "conv_halo: cannot reserve %d B of shared memory", HL_SMEM);
-  const int units = G == 1 ? p.total_tiles : p.total_groups;
+  const int units = (G == 1 && !CTA2) ? p.total_tiles : p.total_groups;
   int grid = units < num_sms() ? units : num_sms();
+  if (CTA2) {
+    // one cluster of two CTAs per tile pair; the persistent walk assumes every cluster is resident at once, so the grid
+    // is what the device can co-schedule (GPC boundaries can leave it below num_sms / 2)
+    static int max_clusters = 0;
+    static std::once_flag once_c;
+    std::call_once(once_c, [] {
+      cudaLaunchConfig_t q{};
+      q.gridDim = dim3((unsigned)(num_sms() & ~1));
+      q.blockDim = dim3(hl_threads(hl_two_sets(KWC, G, DGRAD)));
+      q.dynamicSmemBytes = HL_SMEM;
+      cudaLaunchAttribute a[1];
+      a[0].id = cudaLaunchAttributeClusterDimension;
+      a[0].val.clusterDim.x = 2;
+      a[0].val.clusterDim.y = 1;
+      a[0].val.clusterDim.z = 1;
+      q.attrs = a;
+      q.numAttrs = 1;
+      int n = 0;
+      if (cudaOccupancyMaxActiveClusters(&n, conv_moments_halo_kernel<NT, KS, RESIDENT, DGRAD, G, KWC, CTA2>, &q) ==
+              cudaSuccess && n > 0)
+        max_clusters = n;
+      else
+        max_clusters = num_sms() / 2;
+      if (getenv("SN_CTA2_VERBOSE")) fprintf(stderr, "conv_halo CTA pairs: %d clusters co-resident\n", max_clusters);
+    });
+    grid = 2 * (units < max_clusters ? units : max_clusters);
+  }
   static const bool pdl = [] {
     const char* e = getenv("SN_PDL");
     return e == nullptr || e[0] != '0';
@@ -1054,18 +1158,43 @@ static int hl_launch3(const HlMaps& maps, const HlP& p, cudaStream_t st) {
   cfg.blockDim = dim3(hl_threads(hl_two_sets(KWC, G, DGRAD)));
   cfg.dynamicSmemBytes = HL_SMEM;
   cfg.stream = st;
-  cudaLaunchAttribute attr[1];
-  attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
-  attr[0].val.programmaticStreamSerializationAllowed = 1;
+  cudaLaunchAttribute attr[2];
+  int na = 0;
+#ifdef SN_HL_KNOBS
+  static const bool fake_cluster = getenv("SN_FAKE_CLUSTER") != nullptr;      // single-CTA kernel launched as clusters of 2
+#else
+  constexpr bool fake_cluster = false;
+#endif
+  if (CTA2 || (fake_cluster && grid % 2 == 0)) {
+    attr[na].id = cudaLaunchAttributeClusterDimension;
+    attr[na].val.clusterDim.x = 2;
+    attr[na].val.clusterDim.y = 1;
+    attr[na].val.clusterDim.z = 1;
+    ++na;
+  }
+  if (pdl) {
+    attr[na].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+    attr[na].val.programmaticStreamSerializationAllowed = 1;
+    ++na;
+  }
   cfg.attrs = attr;
-  cfg.numAttrs = pdl ? 1 : 0;
-  cudaError_t e = cudaLaunchKernelEx(&cfg, conv_moments_halo_kernel<NT, KS, RESIDENT, DGRAD, G, KWC>, maps, p);
+  cfg.numAttrs = na;
+  cudaError_t e = cudaLaunchKernelEx(&cfg, conv_moments_halo_kernel<NT, KS, RESIDENT, DGRAD, G, KWC, CTA2>, maps, p);
   if (e != cudaSuccess) return fail(SN_ERR_LAUNCH, "conv_halo launch: %s", cudaGetErrorString(e));
   return check_launch(DGRAD ? "conv_moments_halo_dgrad" : "conv_moments_halo");
 }
 
 template <int NT>
 static int hl_launch(const HlMaps& maps, const HlP& p, cudaStream_t st) {
+  if constexpr (NT == 128) {
+    if (p.cta2) {
+      switch (p.ksize) {
+        case 1: return hl_launch3<128, 1, false, false, 1, false, true>(maps, p, st);
+        case 2: return hl_launch3<128, 2, false, false, 1, false, true>(maps, p, st);
+        default: return hl_launch3<128, 3, false, false, 1, false, true>(maps, p, st);
+      }
+    }
+  }
   if constexpr (NT == 32) {
     if (p.kwc) {
       return p.b_resident ? hl_launch3<32, 3, true, false, 1, true>(maps, p, st)
@@ -1090,6 +1219,15 @@ static int hl_launch(const HlMaps& maps, const HlP& p, cudaStream_t st) {
 // output parities become four K-concatenated sources).
 template <int NT>
 static int hl_launch_dgrad(const HlMaps& maps, const HlP& p, cudaStream_t st) {
+  if constexpr (NT == 128) {
+    if (p.cta2) {
+      switch (p.ksize) {
+        case 1: return hl_launch3<128, 1, false, true, 1, false, true>(maps, p, st);
+        case 2: return hl_launch3<128, 2, false, true, 1, false, true>(maps, p, st);
+        default: return hl_launch3<128, 3, false, true, 1, false, true>(maps, p, st);
+      }
+    }
+  }
   if constexpr (NT == 32) {
     if (p.kwc) {
       return p.b_resident ? hl_launch3<32, 3, true, true, 1, true>(maps, p, st)
@@ -1117,9 +1255,10 @@ static bool hl_view_v8(const sn_packed_view& v) {
 
 // Tile geometry + shared-memory plan shared by the forward and the data-gradient dispatch.
 static int hl_plan(HlP& p, const HaloTiling& t, int keff, int ncols, int nt, int cblk, bool kwc = false,
-                   bool tma_store = false) {
+                   bool tma_store = false, int cta2_mode = 1) {
   p.kwc = kwc ? 1 : 0;
   p.tma_store = tma_store ? 1 : 0;
+  p.cta2 = 0;
   {
     static const int dbg = [] {
       const char* e = getenv("SN_HL_DBG");
@@ -1163,6 +1302,38 @@ static int hl_plan(HlP& p, const HaloTiling& t, int keff, int ncols, int nt, int
   // every SM busy and the doubled A stages still leave >= 3 weight slots
   p.pix_tiles = p.tiles_x * p.tiles_y * p.tiles_b;
   p.total_groups = 0;
+  // CTA pairs for the 128-column layers with streamed weights: two pixel tiles of one N tile on the two SMs of a TPC,
+  // M = 256 UMMAs, half of every weight slot per SM.  Needs enough tile pairs to fill the clusters (74 on B200).
+  // cta2_mode: 0 never, 1 the library's choice, 2 whenever the shape allows (tests)
+  {
+    static const int env_mode = [] {
+      const char* e = getenv("SN_CTA2");
+      return e == nullptr ? 1 : atoi(e);
+    }();
+    const int mode = cta2_mode == 1 ? env_mode : cta2_mode;
+    const long long pairs = (long long)p.tiles_n * ((p.pix_tiles + 1) / 2);
+    // (not for k = 1 / up-convs by default: one tap per channel block is too little UMMA work per handshake -- measured
+    //  +15...20 % on the three 2x2 up-convs -- while the 3x3 layers gain 3...12 %, profiles/r02_cta2.md)
+    if (mode != 0 && nt == 128 && !p.b_resident && !kwc &&
+        (mode == 2 || (keff >= 2 && 4 * pairs >= 3 * (num_sms() / 2)))) {
+      const int b_half = b_slot / 2;
+      int sa = 3;
+      if (3 * a_stage + 4 * b_half > avail) sa = 2;
+      int sb = (avail - sa * a_stage) / b_half;
+      if (sb > HL_CTA2_MAX_BSLOTS) sb = HL_CTA2_MAX_BSLOTS;
+#ifdef SN_HL_KNOBS
+      if (const char* e = getenv("SN_CTA2_SA")) { sa = atoi(e); sb = (avail - sa * a_stage) / b_half; if (sb > HL_CTA2_MAX_BSLOTS) sb = HL_CTA2_MAX_BSLOTS; }
+      if (const char* e = getenv("SN_CTA2_SB")) { if (atoi(e) < sb) sb = atoi(e); }
+#endif
+      if (sb >= 3) {
+        p.cta2 = 1;
+        p.sa = sa;
+        p.sb = sb;
+        p.total_groups = (int)pairs;
+        return SN_OK;
+      }
+    }
+  }
   static const int dual = [] {          // 0: off, 1: 64-column tiles (default), 2: 128-column tiles too (A/B)
     const char* e = getenv("SN_DUAL");
     return e == nullptr ? 1 : atoi(e);
@@ -1219,7 +1390,8 @@ int conv_moments_halo_dispatch(const sn_tc_conv_desc* d, cudaStream_t stream) {
     HlP probe{};
     if ((rc = hl_plan(probe, t, keff, ncols, nt, cblk, kwc, true)) || !probe.b_resident || probe.sa < 2) tma_store = false;
   }
-  if ((rc = hl_plan(p, t, keff, ncols, nt, cblk, kwc, tma_store))) return rc;
+  const int cta2_mode = (d->flags & SN_TC_NO_CTA2) ? 0 : ((d->flags & SN_TC_CTA2) ? 2 : 1);
+  if ((rc = hl_plan(p, t, keff, ncols, nt, cblk, kwc, tma_store, cta2_mode))) return rc;
   p.taps_w = taps_w;
   p.cblk_s[0] = d->src_c[0] / HL_KC; p.cblk_s[1] = d->src_c[1] / HL_KC;
   p.Ho = Ho; p.Wo = Wo; p.B = d->batch;
@@ -1245,7 +1417,8 @@ int conv_moments_halo_dispatch(const sn_tc_conv_desc* d, cudaStream_t stream) {
   }
   for (int pl = 0; pl < 3; ++pl) maps.a[2][pl] = maps.a[3][pl] = maps.a[0][pl];     // unused
   // regular: [3*taps][cout][cin]; up-conv: [3][4*cout][cin] (same memory, parity and channel fused into one axis)
-  if ((rc = hl_make_weight_map(&maps.w, d->w_packed, upconv ? 1 : taps_w, upconv ? ncols : d->cout, cin, nt)))
+  if ((rc = hl_make_weight_map(&maps.w, d->w_packed, upconv ? 1 : taps_w, upconv ? ncols : d->cout, cin,
+                               p.cta2 ? nt / 2 : nt, p.kwc ? 3 : 1)))
     return rc;
   maps.d = maps.w;
   if (p.tma_store && (rc = hl_make_dst_map(&maps.d, d->dst, d->cout, out_h, out_w, d->batch, t.TWo))) return rc;
@@ -1289,7 +1462,8 @@ int conv_moments_halo_dgrad_dispatch(const sn_tc_dgrad_desc* d, cudaStream_t str
 
   HlP p{};
   int rc;
-  if ((rc = hl_plan(p, t, keff, ncols, nt, cblk, kwc))) return rc;
+  const int cta2_mode = (d->flags & SN_TC_NO_CTA2) ? 0 : ((d->flags & SN_TC_CTA2) ? 2 : 1);
+  if ((rc = hl_plan(p, t, keff, ncols, nt, cblk, kwc, false, cta2_mode))) return rc;
   p.taps_w = keff * keff;
   for (int s = 0; s < nsrc; ++s) p.cblk_s[s] = d->cout / HL_KC;
   p.pad = pad;
@@ -1318,7 +1492,9 @@ int conv_moments_halo_dgrad_dispatch(const sn_tc_dgrad_desc* d, cudaStream_t str
         return rc;
   }
   // transposed weights [3][taps][N = cin][K = nsrc * cout]
-  if ((rc = hl_make_weight_map(&maps.w, d->wt_packed, keff * keff, ncols, nsrc * d->cout, nt))) return rc;
+  if ((rc = hl_make_weight_map(&maps.w, d->wt_packed, keff * keff, ncols, nsrc * d->cout, p.cta2 ? nt / 2 : nt,
+                               p.kwc ? 3 : 1)))
+    return rc;
   maps.d = maps.w;          // unused
   switch (nt) {
     case 128: return hl_launch_dgrad<128>(maps, p, stream);

@@ -13,7 +13,8 @@ from typing import Optional, Tuple
 import torch
 
 from . import _lib
-from ._lib import (SN_TC_DST_F32, SN_TC_EXACT, SN_TC_IM2COL, SN_TC_KWC, SN_TC_NO_KWC, SN_TC_RELU, SN_TC_ROWS,
+from ._lib import (SN_TC_CTA2, SN_TC_DST_F32, SN_TC_EXACT, SN_TC_IM2COL, SN_TC_KWC, SN_TC_NO_CTA2, SN_TC_NO_KWC, SN_TC_RELU,
+                   SN_TC_ROWS,
                    SN_TC_UPCONV, check, ptr, sn_packed_view, sn_tc_conv_desc,
                    sn_tc_dgrad_desc, sn_tc_wgrad_desc, stream_ptr)
 
@@ -84,15 +85,17 @@ def conv_moments_tc(src0: PackedView, c0: int, batch: int, in_h: int, in_w: int,
                     w_packed: Tensor, s: Tensor, dst: Optional[PackedView] = None, relu: bool = False,
                     upconv: bool = False, src1: Optional[PackedView] = None, c1: int = 0,
                     dst_f32: Optional[Tuple[Tensor, Tensor]] = None, im2col: bool = False,
-                    rsum_out: Optional[Tensor] = None, kwc: Optional[bool] = None) -> None:
-    """kwc: None = the library's choice, True / False force / forbid the kw-concatenated halo kernel (SN_TC_KWC)."""
+                    rsum_out: Optional[Tensor] = None, kwc: Optional[bool] = None, cta2: Optional[bool] = None) -> None:
+    """kwc / cta2: None = the library's choice, True / False force / forbid the kw-concatenated halo kernel
+    (SN_TC_KWC) / the CTA-pair variant (SN_TC_CTA2)."""
     d = sn_tc_conv_desc()
     d.src[0] = src0.c_view()
     d.src[1] = (src1 if src1 is not None else src0).c_view()
     d.src_c[0], d.src_c[1] = c0, c1
     d.batch, d.in_h, d.in_w, d.ksize, d.cout = batch, in_h, in_w, ksize, cout
     d.flags = ((SN_TC_RELU if relu else 0) | (SN_TC_UPCONV if upconv else 0) | (SN_TC_DST_F32 if dst_f32 else 0) |
-               (SN_TC_IM2COL if im2col else 0) | (SN_TC_KWC if kwc else (SN_TC_NO_KWC if kwc is False else 0)))
+               (SN_TC_IM2COL if im2col else 0) | (SN_TC_KWC if kwc else (SN_TC_NO_KWC if kwc is False else 0)) |
+               (SN_TC_CTA2 if cta2 else (SN_TC_NO_CTA2 if cta2 is False else 0)))
     d.w_packed = w_packed.data_ptr()
     d.s = s.data_ptr()
     if rsum_out is not None:
@@ -146,7 +149,8 @@ def prepare_weights_bwd(w_mu: Tensor, upconv: bool = False, out: Optional[Tensor
 def conv_moments_bwd_data_tc(g_out: PackedView, batch: int, in_h: int, in_w: int, ksize: int, cout: int,
                              wt_packed: Tensor, s: Tensor, in0: PackedView, g_in0: PackedView, c0: int, gate0: bool,
                              in1: Optional[PackedView] = None, g_in1: Optional[PackedView] = None, c1: int = 0,
-                             gate1: bool = False, upconv: bool = False, kwc: Optional[bool] = None) -> None:
+                             gate1: bool = False, upconv: bool = False, kwc: Optional[bool] = None,
+                             cta2: Optional[bool] = None) -> None:
     d = sn_tc_dgrad_desc()
     d.g_out = g_out.c_view()
     d.in_[0], d.g_in[0] = in0.c_view(), g_in0.c_view()
@@ -155,7 +159,8 @@ def conv_moments_bwd_data_tc(g_out: PackedView, batch: int, in_h: int, in_w: int
     d.in_c[0], d.in_c[1] = c0, c1
     d.gate[0], d.gate[1] = int(gate0), int(gate1)
     d.batch, d.in_h, d.in_w, d.ksize, d.cout = batch, in_h, in_w, ksize, cout
-    d.flags = (SN_TC_UPCONV if upconv else 0) | (SN_TC_KWC if kwc else (SN_TC_NO_KWC if kwc is False else 0))
+    d.flags = ((SN_TC_UPCONV if upconv else 0) | (SN_TC_KWC if kwc else (SN_TC_NO_KWC if kwc is False else 0)) |
+               (SN_TC_CTA2 if cta2 else (SN_TC_NO_CTA2 if cta2 is False else 0)))
     d.wt_packed = wt_packed.data_ptr()
     d.s = s.data_ptr()
     check(_lib.load().sn_conv_moments_bwd_data_tc(C.byref(d), stream_ptr()), "conv_moments_bwd_data_tc")

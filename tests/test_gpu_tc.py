@@ -86,14 +86,19 @@ def _kwc_eligible(case):
 
 @pytest.mark.parametrize("case", TC_CASES)
 @pytest.mark.parametrize("relu", [False, True])
-@pytest.mark.parametrize("im2col", [False, True, "kwc", "nokwc"], ids=["halo", "im2col", "kwc", "nokwc"])
+@pytest.mark.parametrize("im2col", [False, True, "kwc", "nokwc", "cta2", "nocta2"],
+                         ids=["halo", "im2col", "kwc", "nokwc", "cta2", "nocta2"])
 def test_conv_tc_f32_dst(S, case, relu, im2col):
     F = S.fastops
-    kwc = None
-    if isinstance(im2col, str):            # the two halo variants, forced (SN_TC_KWC / SN_TC_NO_KWC)
+    kwc = cta2 = None
+    if im2col in ("kwc", "nokwc"):         # the two halo variants, forced (SN_TC_KWC / SN_TC_NO_KWC)
         if not _kwc_eligible(case):
             pytest.skip("shape not eligible for the kw-concatenated kernel")
         kwc, im2col = im2col == "kwc", False
+    elif im2col in ("cta2", "nocta2"):     # CTA pairs (cta_group::2) forced / forbidden
+        if case[4] % 128 != 0:
+            pytest.skip("CTA pairs need 128-column tiles")
+        cta2, im2col = im2col == "cta2", False
     B, H, W, cin, cout, k = case
     mu, var, w, ws = rand_layer(B, H, W, cin, cout, k, seed=sum(case))
     m_ref, v_ref = O.conv_intermediate_conv_form(mu, var, w, ws)
@@ -104,7 +109,7 @@ def test_conv_tc_f32_dst(S, case, relu, im2col):
     Ho, Wo = H - k + 1, W - k + 1
     m = torch.full((B, Ho, Wo, cout), float("nan"), device="cuda")
     v = torch.full((B, Ho, Wo, cout), float("nan"), device="cuda")
-    F.conv_moments_tc(src, cin, B, H, W, k, cout, wp, s, relu=relu, dst_f32=(m, v), im2col=im2col, kwc=kwc)
+    F.conv_moments_tc(src, cin, B, H, W, k, cout, wp, s, relu=relu, dst_f32=(m, v), im2col=im2col, kwc=kwc, cta2=cta2)
     torch.cuda.synchronize()
     assert bool(torch.isfinite(m).all()) and bool(torch.isfinite(v).all())
     assert rel(m, m_ref) < MEAN_TOL, rel(m, m_ref)
@@ -443,3 +448,46 @@ def test_conv_writes_only_its_window_and_is_deterministic(S, case):
         assert bool((guard == CANARY).all()), "a write landed outside the destination window"
     for o in outs[1:]:
         assert torch.equal(o.view(torch.int16), outs[0].view(torch.int16)), "results differ between identical launches"
+
+
+CTA2_CASES = [
+    # B, H, W, cin, c1, cout, k, upconv
+    (3, 20, 20, 128, 0, 128, 3, False),     # 3 pixel tiles per image, 9 in all: the last pair repeats a tile, unsaved
+    (2, 9, 9, 256, 0, 256, 3, False),       # two N tiles
+    (64, 24, 24, 128, 0, 128, 3, False),    # several tile pairs per cluster
+    (5, 12, 12, 128, 0, 128, 1, False),     # 1x1
+    (2, 5, 5, 256, 0, 128, 2, True),        # up-conv: N = 4 x 128
+    (2, 10, 10, 128, 128, 128, 3, False),   # two sources
+    (1, 6, 6, 512, 0, 512, 3, False),       # one pixel tile, four N tiles: every pair is a tile and its unsaved copy
+]
+
+
+@pytest.mark.parametrize("case", CTA2_CASES)
+def test_conv_tc_cta_pair_is_bit_identical_and_stays_in_its_window(S, case):
+    """The CTA-pair variant (cta_group::2 UMMAs of M = 256 over two pixel tiles, half of every weight slot per SM)
+    accumulates every output row in the same order as the single-CTA kernel: the packed results must be bit-identical,
+    inside canary-filled surroundings, and repeatable."""
+    F = S.fastops
+    B, H, W, cin, c1, cout, k, upconv = case
+    g = torch.Generator().manual_seed(sum(int(v) for v in case))
+    src0 = F.PackedView(F.pack_moments(dev(torch.randn(B, H, W, cin, generator=g)), dev(torch.rand(B, H, W, cin, generator=g))))
+    src1 = F.PackedView(F.pack_moments(dev(torch.randn(B, H, W, c1, generator=g)), dev(torch.rand(B, H, W, c1, generator=g)))) \
+        if c1 else None
+    w = torch.randn(k, k, cin + c1, cout, generator=g) * 0.1
+    ws = torch.empty(cout).uniform_(-6, -2, generator=g)
+    wp, s = F.prepare_weights(dev(w), dev(ws), upconv=upconv)
+    Ho, Wo = (2 * H, 2 * W) if upconv else (H - k + 1, W - k + 1)
+    CANARY = -7.0
+    outs = {}
+    for cta2 in (False, True, True):
+        big = torch.full((B + 1, Ho + 5, Wo + 5, 3, cout + 64), CANARY, device="cuda", dtype=torch.bfloat16)
+        F.conv_moments_tc(src0, cin, B, H, W, k, cout, wp, s, dst=F.PackedView(big, 2, 3, 32), relu=not upconv,
+                          upconv=upconv, src1=src1, c1=c1, cta2=cta2)
+        torch.cuda.synchronize()
+        win = big[:B, 2:2 + Ho, 3:3 + Wo, :, 32:32 + cout].clone()
+        assert bool((win != CANARY).all()), "part of the window was not written"
+        big[:B, 2:2 + Ho, 3:3 + Wo, :, 32:32 + cout] = CANARY
+        assert bool((big == CANARY).all()), "a write landed outside the destination window"
+        outs.setdefault(cta2, []).append(win.view(torch.int16))
+    assert torch.equal(outs[True][0], outs[True][1]), "CTA-pair results differ between identical launches"
+    assert torch.equal(outs[True][0], outs[False][0]), "CTA-pair result differs from the single-CTA kernel"

@@ -538,3 +538,32 @@ def test_dgrad_writes_only_its_window_and_is_deterministic(S, case):
         guard[:B, 1:1 + H, 2:2 + W, :, 32:32 + cin] = CANARY
         assert bool((guard == CANARY).all()), "a write landed outside the gradient window"
     assert all(torch.equal(o.view(torch.int16), outs[0].view(torch.int16)) for o in outs[1:])
+
+
+@pytest.mark.parametrize("case", [(3, 20, 20, 128, 128, 3), (20, 24, 24, 128, 128, 3), (2, 9, 9, 256, 128, 3),
+                                  (2, 5, 5, 128, 256, 2)])
+def test_dgrad_cta_pair_is_bit_identical(S, case):
+    """Data gradient through the CTA-pair variant (N = cin = 128-column tiles): bit-identical to the single-CTA kernel."""
+    F = S.fastops
+    B, H, W, cin, cout, k = case
+    upconv = k == 2
+    Ho, Wo = (2 * H, 2 * W) if upconv else (H - k + 1, W - k + 1)
+    g = torch.Generator().manual_seed(sum(case))
+    saved = F.PackedView(F.pack_moments(dev(torch.randn(B, H, W, cin, generator=g).double()),
+                                        dev(torch.rand(B, H, W, cin, generator=g).double())))
+    g_out = F.PackedView(F.pack_moments(dev(torch.randn(B, Ho, Wo, cout, generator=g).double()),
+                                        dev(torch.randn(B, Ho, Wo, cout, generator=g).double())))
+    w = (torch.randn(k, k, cin, cout, generator=g) * 0.1).double()
+    ws = torch.empty(cout, dtype=torch.float64).uniform_(-6, -2, generator=g)
+    wt = F.prepare_weights_bwd(dev(w), upconv=upconv)
+    _, s = F.prepare_weights(dev(w), dev(ws), upconv=upconv)
+    outs = []
+    for cta2 in (False, True):
+        g_in = F.packed_empty(B, H, W, cin, "cuda")
+        g_in.fill_(float("nan"))
+        F.conv_moments_bwd_data_tc(g_out, B, H, W, k, cout, wt, s, saved, F.PackedView(g_in), cin, True, upconv=upconv,
+                                   cta2=cta2)
+        torch.cuda.synchronize()
+        assert bool(torch.isfinite(g_in.float()).all())
+        outs.append(g_in.view(torch.int16))
+    assert torch.equal(outs[0], outs[1])

@@ -12,7 +12,9 @@ import tempfile
 
 rep, lib = sys.argv[1:3]
 top = int(sys.argv[3]) if len(sys.argv) > 3 else 40
-raw = subprocess.run(["ncu", "-i", rep, "--page", "source", "--csv"], capture_output=True, text=True).stdout
+# a report, or the csv of its source page (`ncu -i rep --page source --csv`, made on the GPU box)
+raw = open(rep).read() if rep.endswith(".csv") else \
+    subprocess.run(["ncu", "-i", rep, "--page", "source", "--csv"], capture_output=True, text=True).stdout
 rows = list(csv.reader(raw.splitlines()))
 kernel = rows[0][1]
 h = rows[1]

@@ -9,7 +9,9 @@ import sys
 import tempfile
 
 rep, lib = sys.argv[1:3]
-raw = subprocess.run(["ncu", "-i", rep, "--page", "source", "--csv"], capture_output=True, text=True).stdout
+# a report, or the csv of its source page (`ncu -i rep --page source --csv`, made on the GPU box)
+raw = open(rep).read() if rep.endswith(".csv") else \
+    subprocess.run(["ncu", "-i", rep, "--page", "source", "--csv"], capture_output=True, text=True).stdout
 rows = list(csv.reader(raw.splitlines()))
 kernel = rows[0][1]
 h = rows[1]
@@ -58,7 +60,7 @@ print(f"# {kernel}")
 total_s = sum(s for _, _, s, _ in sass)
 print(f"# stall samples total {total_s}")
 print("| addr | first tries | retries | samples near | nearest non-wrapper source line |\n|---|---|---|---|---|")
-idx = [i for i, (a, n, s, t) in enumerate(sass) if "TRYWAIT" in t and n > 0]
+idx = [i for i, (a, n, s, t) in enumerate(sass) if "PHASECHK" in t and n > 0]
 k = 0
 while k < len(idx):
     i = idx[k]
