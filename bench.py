@@ -443,6 +443,12 @@ def main():
         kernels = []
         tc_ms, tc_flops, other_ms, other_bytes = 0.0, 0.0, 0.0, 0.0
         tmap = {r["name"]: r for r in table}
+        for nm in names:
+            if nm.endswith("+conv_final"):
+                # the last 3x3 conv with conv_final + softmax in its epilogue (sn_conv_moments_fwd_tc_head): the conv's
+                # FLOPs; bytes = its packed input + the fp32 maps (its own 32-channel output is never written)
+                r, f = tmap[nm.split("+")[0]], tmap["conv_final"]
+                tmap[nm] = dict(r, name=nm, bytes=r["bytes"] - r["hout"] ** 2 * r["cout"] * 6 + f["hout"] ** 2 * f["cout"] * 8)
         for nm, t in zip(names, per):
             row = {"name": nm, "ms": round(t, 4)}
             if nm in tmap:

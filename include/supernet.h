@@ -208,6 +208,30 @@ typedef struct sn_tc_conv_desc {
 } sn_tc_conv_desc;
 int sn_conv_moments_fwd_tc(const sn_tc_conv_desc* d, sn_stream_t st);
 
+/* The network's LAST 3x3 convolution fused with conv_final (k = 1, Brats.py:367,454) and mysoftmax (Brats.py:269-283):
+ * Density_prop_with_pad_UNET.call ends `up4_conv2 -> ReLU -> conv_final -> softmax` (Brats.py:451-455,
+ * Hippocampus.py:417-421), and the 32 channels of a pixel that the conv's epilogue has just produced are all conv_final
+ * needs -- so the epilogue finishes the forward and sn_final_conv_softmax_packed is not launched.
+ *   - d: as for sn_conv_moments_fwd_tc, restricted to what sn_tc_head_fusable() accepts (ksize 3, SN_TC_RELU, one packed
+ *     32-channel source, cout 32, no SN_TC_UPCONV / DST_F32 / IM2COL / KWC, rsum_out NULL); d->dst.base may be NULL: the
+ *     32-channel tensor is then never written (inference), otherwise it is stored as usual (32-byte aligned window);
+ *   - h: conv_final's raw parameters (w_mu fp32 [32][n_labels], w_sigma [n_labels], 2 <= n_labels <= 5) and the outputs
+ *     of sn_final_conv_softmax_packed: fp32 [batch*Ho*Wo, n_labels] probabilities / variances, optional pre-softmax
+ *     moments (both or neither).
+ * Results are bit-identical to sn_conv_moments_fwd_tc followed by sn_final_conv_softmax_packed: the head reads the
+ * bf16-rounded (hi, lo, var) values the conv would have stored and runs the same per-pixel chain in channel order. */
+typedef struct sn_tc_head_desc {
+  int32_t n_labels;
+  const float* w_mu;
+  const float* w_sigma;
+  float* p_out;
+  float* var_out;
+  float* presoftmax_mu;
+  float* presoftmax_var;
+} sn_tc_head_desc;
+int sn_tc_head_fusable(const sn_tc_conv_desc* d, int32_t n_labels);   /* 1 / 0; no launch, no error state */
+int sn_conv_moments_fwd_tc_head(const sn_tc_conv_desc* d, const sn_tc_head_desc* h, sn_stream_t st);
+
 /* myConv_input.call (Brats.py:65-76) (+ ReLU with SN_TC_RELU) on fp32 NHWC x (cin <= 8), written as a packed window.
  * k = 3, cout = 32, cin in {1, 4} runs on the tensor cores (bf16 hi/lo image and weights, ~1e-5 relative); with
  * SN_TC_EXACT the fp32 CUDA-core kernel is used instead: the gradient engine wants this layer's ReLU gates -- the

@@ -42,6 +42,11 @@ class sn_tc_conv_desc(C.Structure):
                 ("dst", sn_packed_view), ("dst_mu", C.c_void_p), ("dst_var", C.c_void_p), ("rsum_out", C.c_void_p)]
 
 
+class sn_tc_head_desc(C.Structure):
+    _fields_ = [("n_labels", C.c_int32), ("w_mu", C.c_void_p), ("w_sigma", C.c_void_p), ("p_out", C.c_void_p),
+                ("var_out", C.c_void_p), ("presoftmax_mu", C.c_void_p), ("presoftmax_var", C.c_void_p)]
+
+
 class sn_tc_dgrad_desc(C.Structure):
     _fields_ = [("g_out", sn_packed_view), ("in_", sn_packed_view * 2), ("g_in", sn_packed_view * 2),
                 ("in_c", C.c_int32 * 2), ("gate", C.c_int32 * 2),

@@ -462,10 +462,10 @@ __global__ void __launch_bounds__(FT_THREADS) first_conv_tc_kernel(int B, int H,
     parity ^= 1u;
     ptx::tc_fence_after();
     // ---- epilogue: thread = pixel row = TMEM lane
-    uint8_t* o = contiguous ? stage + tid * FT_ROWB
+    uint8_t* o = contiguous == 1 ? stage + tid * FT_ROWB
                             : reinterpret_cast<uint8_t*>(
                                   out + ((((size_t)b * dst.h + yo + dst.y0) * dst.w + xo + dst.x0) * 3) * dst.c + dst.c0);
-    const int plane_b = contiguous ? COUT * 2 : dst.c * 2;
+    const int plane_b = contiguous == 1 ? COUT * 2 : dst.c * 2;
     const uint32_t lane_base = tmem + ((uint32_t)(warp * 32) << 16);
 #pragma unroll
     for (int c0 = 0; c0 < COUT; c0 += 16) {
@@ -485,7 +485,22 @@ __global__ void __launch_bounds__(FT_THREADS) first_conv_tc_kernel(int B, int H,
         mu[j] = m;
         var[j] = v;
       }
-      if (live || contiguous) {
+      if (contiguous == 2) {
+        // direct 256-bit stores: a lane writes its 16 channels of a plane as ONE full 32-byte sector (STG.E.ENL2.256,
+        // what the halo kernel's epilogue does) -- no staging pass, no copy-out loop, one block-wide barrier less
+        if (live) {
+          uint32_t hi[8], lo[8], vr[8];
+#pragma unroll
+          for (int j = 0; j < 8; ++j) {
+            hi[j] = pk2(mu[2 * j], mu[2 * j + 1]);
+            lo[j] = pk2(mu[2 * j] - blo(hi[j]), mu[2 * j + 1] - bhi(hi[j]));
+            vr[j] = pk2(var[2 * j], var[2 * j + 1]);
+          }
+          ptx::st_global_v8(o + c0 * 2, hi);
+          ptx::st_global_v8(o + plane_b + c0 * 2, lo);
+          ptx::st_global_v8(o + 2 * plane_b + c0 * 2, vr);
+        }
+      } else if (live || contiguous) {
 #pragma unroll
         for (int h8 = 0; h8 < 16; h8 += 8) {
           float m8[8], v8[8];
@@ -501,7 +516,7 @@ __global__ void __launch_bounds__(FT_THREADS) first_conv_tc_kernel(int B, int H,
     }
     ptx::tc_fence_before();
     __syncthreads();                       // TMEM reads done (next tile's UMMAs may overwrite); stage complete
-    if (contiguous) {
+    if (contiguous == 1) {
       const size_t remain = total - tile0;
       const int chunks = (int)(remain < 128 ? remain : 128) * 12;
       uint4* g = reinterpret_cast<uint4*>(out + tile0 * 3 * COUT);
@@ -743,39 +758,11 @@ __global__ void __launch_bounds__(128) final_conv_softmax_kernel(sn_packed_view 
         unpack8(*reinterpret_cast<const uint4*>(s8 + plane_b + c8 * 2), l);
         unpack8(*reinterpret_cast<const uint4*>(s8 + 2 * plane_b + c8 * 2), vv);
 #pragma unroll
-        for (int e = 0; e < 8; ++e) {
-          const float mu = h[e] + l[e];
-          r += fmaf(mu, mu, vv[e]);
-#pragma unroll
-          for (int j = 0; j < C; ++j) {
-            m[j] = fmaf(mu, sw[(c8 + e) * C + j], m[j]);
-            v[j] = fmaf(vv[e], sw2[(c8 + e) * C + j], v[j]);
-          }
-        }
+        for (int e = 0; e < 8; ++e)
+          head_accumulate<C>(h[e] + l[e], vv[e], sw + (c8 + e) * C, sw2 + (c8 + e) * C, m, v, r);
       }
-      float mx = -INFINITY;
-#pragma unroll
-      for (int j = 0; j < C; ++j) {
-        v[j] = fmaxf(fmaf(ss[j], r, v[j]), 0.f);
-        mx = fmaxf(mx, m[j]);
-      }
-      float p[C], sum = 0.f;
-#pragma unroll
-      for (int j = 0; j < C; ++j) { p[j] = expf(m[j] - mx); sum += p[j]; }
-      const float inv = 1.f / sum;
-#pragma unroll
-      for (int j = 0; j < C; ++j) p[j] *= inv;
-      float vo[C];
-#pragma unroll
-      for (int a = 0; a < C; ++a) {
-        float acc = 0.f;   // sum_j (p_a (delta_aj - p_j))^2 v_j : non-negative terms only
-#pragma unroll
-        for (int j = 0; j < C; ++j) {
-          const float J = p[a] * ((a == j ? 1.f : 0.f) - p[j]);
-          acc = fmaf(J * J, v[j], acc);
-        }
-        vo[a] = acc;
-      }
+      float p[C], vo[C];
+      head_finish<C>(m, v, r, ss, p, vo);
       if constexpr (C == 4) {
         reinterpret_cast<float4*>(p_out)[i] = make_float4(p[0], p[1], p[2], p[3]);
         reinterpret_cast<float4*>(v_out)[i] = make_float4(vo[0], vo[1], vo[2], vo[3]);
@@ -884,7 +871,14 @@ int sn_first_conv_fwd_packed(int32_t batch, int32_t in_h, int32_t in_w, int32_t 
     const size_t tiles = (pixels + 127) / 128;
     const size_t cap = (size_t)num_sms() * FT_CTAS_PER_SM;
     const int grid = (int)(tiles < cap ? tiles : cap);
-    const int contiguous = dst->y0 == 0 && dst->x0 == 0 && dst->c0 == 0 && dst->h == Ho && dst->w == Wo && dst->c == cout;
+    int contiguous = dst->y0 == 0 && dst->x0 == 0 && dst->c0 == 0 && dst->h == Ho && dst->w == Wo && dst->c == cout;
+    // 2: every (pixel, plane, 16-channel chunk) segment of the destination is 32-byte aligned -> direct 256-bit stores
+    static const bool first_v8 = [] {
+      const char* e = getenv("SN_FIRST_V8");
+      return e == nullptr || e[0] != '0';
+    }();
+    if (first_v8 && (reinterpret_cast<uintptr_t>(dst->base) & 31u) == 0 && dst->c % 16 == 0 && dst->c0 % 16 == 0)
+      contiguous = 2;
     if (cin == 4)
       first_conv_tc_kernel<4><<<grid, FT_THREADS, FT_SMEM, as_stream(st)>>>(batch, in_h, in_w, x, w_mu, w_sigma, *dst,
                                                                             relu, contiguous);

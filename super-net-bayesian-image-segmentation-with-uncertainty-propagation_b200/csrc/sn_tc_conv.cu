@@ -385,13 +385,15 @@ static int launch_tc(const TcMaps& maps, const TcP& p, int n_tiles, cudaStream_t
   return check_launch("conv_moments_tc");
 }
 
-int conv_moments_halo_dispatch(const sn_tc_conv_desc* d, cudaStream_t stream);   // sn_tc_halo.cu
+int conv_moments_halo_dispatch(const sn_tc_conv_desc* d, cudaStream_t stream, const sn_tc_head_desc* head);   // sn_tc_halo.cu
 
 }  // namespace sn
 
 using namespace sn;
 
-extern "C" int sn_conv_moments_fwd_tc(const sn_tc_conv_desc* d, sn_stream_t st) {
+// Argument checks shared by sn_conv_moments_fwd_tc and sn_conv_moments_fwd_tc_head (dst_optional: the fused head may
+// run without a packed destination for the 32-channel tensor).
+static int conv_tc_validate(const sn_tc_conv_desc* d, bool dst_optional) {
   SN_REQUIRE(d, SN_ERR_BAD_ARG, "conv_tc: null descriptor");
   const bool upconv = (d->flags & SN_TC_UPCONV) != 0;
   const bool dst_f32 = (d->flags & SN_TC_DST_F32) != 0;
@@ -420,11 +422,37 @@ extern "C" int sn_conv_moments_fwd_tc(const sn_tc_conv_desc* d, sn_stream_t st) 
   if (dst_f32) {
     SN_REQUIRE(d->dst_mu && d->dst_var && aligned16(d->dst_mu) && aligned16(d->dst_var), SN_ERR_BAD_ARG,
                "conv_tc: fp32 destinations missing/misaligned");
-  } else {
+  } else if (!(dst_optional && d->dst.base == nullptr)) {
     if ((rc = check_view(d->dst, d->batch, out_h, out_w, d->cout, "conv_tc dst"))) return rc;
   }
+  return SN_OK;
+}
 
-  if (!(d->flags & SN_TC_IM2COL)) return conv_moments_halo_dispatch(d, as_stream(st));
+extern "C" int sn_conv_moments_fwd_tc_head(const sn_tc_conv_desc* d, const sn_tc_head_desc* h, sn_stream_t st) {
+  int rc;
+  if ((rc = conv_tc_validate(d, true))) return rc;
+  SN_REQUIRE(h, SN_ERR_BAD_ARG, "conv_tc_head: null head descriptor");
+  SN_REQUIRE(sn_tc_head_fusable(d, h->n_labels), SN_ERR_UNSUPPORTED,
+             "conv_tc_head: this layer / label count cannot end in the fused head (sn_tc_head_fusable)");
+  SN_REQUIRE(h->w_mu && h->w_sigma && h->p_out && h->var_out, SN_ERR_BAD_ARG, "conv_tc_head: null weights / outputs");
+  SN_REQUIRE((h->presoftmax_mu == nullptr) == (h->presoftmax_var == nullptr), SN_ERR_BAD_ARG,
+             "conv_tc_head: presoftmax_mu and presoftmax_var go together");
+  SN_REQUIRE(aligned16(h->p_out) && aligned16(h->var_out) && aligned16(h->presoftmax_mu) && aligned16(h->presoftmax_var),
+             SN_ERR_BAD_ARG, "conv_tc_head: outputs must be 16-byte aligned");
+  return conv_moments_halo_dispatch(d, as_stream(st), h);
+}
+
+extern "C" int sn_conv_moments_fwd_tc(const sn_tc_conv_desc* d, sn_stream_t st) {
+  int rc;
+  if ((rc = conv_tc_validate(d, false))) return rc;
+  const bool upconv = (d->flags & SN_TC_UPCONV) != 0;
+  const bool dst_f32 = (d->flags & SN_TC_DST_F32) != 0;
+  const int keff = upconv ? 1 : d->ksize;
+  const int Ho = d->in_h - keff + 1, Wo = d->in_w - keff + 1;
+  const int out_h = upconv ? 2 * d->in_h : Ho, out_w = upconv ? 2 * d->in_w : Wo;
+  const long long m_total = (long long)d->batch * Ho * Wo;
+
+  if (!(d->flags & SN_TC_IM2COL)) return conv_moments_halo_dispatch(d, as_stream(st), nullptr);
   SN_REQUIRE(d->rsum_out == nullptr, SN_ERR_UNSUPPORTED, "conv_tc: rsum_out needs the halo kernel (no SN_TC_IM2COL)");
 
   const int nt = d->cout % 128 == 0 ? 128 : (d->cout % 64 == 0 ? 64 : 32);

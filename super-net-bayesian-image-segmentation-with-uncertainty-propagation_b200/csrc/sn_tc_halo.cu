@@ -67,6 +67,7 @@ struct HlMaps {
   CUtensorMap w;
   CUtensorMap d;           // destination window (c, plane, x, y, n) for the TMA-store epilogue
 };
+constexpr int HL_HEAD_SMEM = 16384;   // fused head: W, W^2, s of conv_final + the partial-sum exchange of the warp pairs
 constexpr int HL_STG_BUF = 6144;      // staging buffer of one (epilogue set, tile row): 30 pixels x 3 planes x 32 channels
 
 struct HlView {            // a window of a packed buffer, device side
@@ -102,6 +103,12 @@ struct HlP {
   int kwc;                 // kw-concatenated variant (see the kernel): R = 32, one weight slot per filter row
   int cta2;                // CTA pair (cta_group::2) variant: M = 256 over two SMs, half of every weight slot per CTA
   int tma_store;           // forward KWC, packed destination: rows leave through shared memory + TMA tensor stores
+  // fused head (template HEAD = n_labels > 0): conv_final + mysoftmax in the epilogue of the last 32-channel conv
+  const float* head_w;     // conv_final w_mu, fp32 [32][n_labels]
+  const float* head_ws;    // conv_final raw w_sigma [n_labels]
+  float *head_p, *head_v;  // fp32 [B*Ho*Wo][n_labels] softmax probabilities / their variances
+  float *head_pre_mu, *head_pre_var;   // optional pre-softmax moments
+  int head_labels;         // host side only: which HEAD instantiation to launch (0: none)
   int dbg;                 // SN_HL_DBG knob experiments (profiling only; results are wrong when non-zero): 1 epilogue
                            // skips its work, 2 one UMMA group per tile, 4 reducers skip their loads, 8 no global stores
 };
@@ -111,6 +118,40 @@ __device__ __forceinline__ float hl_hi(uint32_t v) { return __uint_as_float(v & 
 __device__ __forceinline__ uint32_t hl_pack2(float a, float b) {
   __nv_bfloat162 t = __floats2bfloat162_rn(a, b);
   return *reinterpret_cast<uint32_t*>(&t);
+}
+// Mixed-precision arithmetic of sm_100 (PTX fma/add.rn.f32.bf16 = FHFMA.BF16 / FHADD.BF16 in SASS): the bf16 operands
+// are read straight from a half of a 32-bit register, the accumulator is fp32 -- no shift / mask to unpack first.  The
+// CUDA-core side of the 32/64-channel layers is issue-bound (profiles/r02_kwc_knobs.md), so instructions are the currency.
+//   hl_fma2(a, b, c0, c1):  c0 += a.lo * b.lo,  c1 += a.hi * b.hi        (products of two bf16 are exact in fp32)
+//   hl_add2(a, c0, c1):     c0 += a.lo,         c1 += a.hi
+//   hl_resid2(hi, a0, a1):  bf16x2(a0 - hi.lo, a1 - hi.hi), the "lo" plane of a hi/lo split (same value as the
+//                           unpack + FADD form: one rounding of an exactly representable difference)
+//   hl_sum2(h, l, m0, m1):  m0 = h.lo + l.lo, m1 = h.hi + l.hi in fp32
+__device__ __forceinline__ void hl_fma2(uint32_t a, uint32_t b, float& c0, float& c1) {
+  asm("{\n\t.reg .b16 al, ah, bl, bh;\n\t"
+      "mov.b32 {al, ah}, %2;\n\tmov.b32 {bl, bh}, %3;\n\t"
+      "fma.rn.f32.bf16 %0, al, bl, %0;\n\tfma.rn.f32.bf16 %1, ah, bh, %1;\n\t}"
+      : "+f"(c0), "+f"(c1) : "r"(a), "r"(b));
+}
+__device__ __forceinline__ void hl_add2(uint32_t a, float& c0, float& c1) {
+  asm("{\n\t.reg .b16 al, ah;\n\t"
+      "mov.b32 {al, ah}, %2;\n\t"
+      "add.rn.f32.bf16 %0, al, %0;\n\tadd.rn.f32.bf16 %1, ah, %1;\n\t}"
+      : "+f"(c0), "+f"(c1) : "r"(a));
+}
+__device__ __forceinline__ uint32_t hl_resid2(uint32_t hi, float a0, float a1) {
+  uint32_t lo;
+  asm("{\n\t.reg .b16 x, y, m1;\n\t.reg .f32 r0, r1;\n\t"
+      "mov.b32 {x, y}, %1;\n\tmov.b16 m1, 0xBF80;\n\t"            // bf16(-1)
+      "fma.rn.f32.bf16 r0, x, m1, %2;\n\tfma.rn.f32.bf16 r1, y, m1, %3;\n\t"
+      "cvt.rn.bf16x2.f32 %0, r1, r0;\n\t}"
+      : "=r"(lo) : "r"(hi), "f"(a0), "f"(a1));
+  return lo;
+}
+__device__ __forceinline__ void hl_sum2(uint32_t h, uint32_t l, float& m0, float& m1) {
+  m0 = hl_lo(h);
+  m1 = hl_hi(h);
+  hl_add2(l, m0, m1);
 }
 
 // Mixed-radix walk over (n-tile, x-tile, y-tile, image-tile) in steps of gridDim.x: no divisions per tile.
@@ -175,9 +216,19 @@ __device__ __forceinline__ TileCoord decode_group_tile(int grp, int t, const HlP
 // Protocol on top of the single-CTA one: the leader's issuer also waits for the peer's operands (pa_full / pb_full,
 // relayed by the peer's otherwise idle warp 1 with remote mbarrier arrives), its commits are multicast to both CTAs'
 // a_empty / b_empty / acc_full, and the peer's epilogue warps release the accumulator stage on the LEADER's acc_empty.
-template <int NT, int KS, bool RESIDENT, bool DGRAD, int G = 1, bool KWC = false, bool CTA2 = false>
+// HEAD = n_labels > 0 (NT = 32, resident weights, one tile per accumulator stage; the network's LAST 3x3 conv): the
+// epilogue goes on with conv_final (k = 1, Brats.py:367,454) and mysoftmax (Brats.py:269-283) on the 32 channels it has
+// just produced, so the forward ends here -- no final_conv_softmax launch, and the 32-channel tensor is not written
+// unless a destination is given.  The two warps of a TMEM lane quarter own channels 0-15 / 16-31 of the same pixels:
+// the first runs the per-pixel chain (sn_common.cuh: head_accumulate) over its channels, hands its 2*HEAD+1 partial sums
+// to the second through shared memory, the second continues the SAME chain over channels 16-31 and finishes.  Channel
+// order and arithmetic are those of final_conv_softmax_kernel on the bf16-rounded values the unfused path would have
+// stored, so fused and unfused forwards agree bit for bit.
+template <int NT, int KS, bool RESIDENT, bool DGRAD, int G = 1, bool KWC = false, bool CTA2 = false, int HEAD = 0>
 __global__ void __launch_bounds__(hl_threads(hl_two_sets(KWC, G, DGRAD)), 1) conv_moments_halo_kernel(const __grid_constant__ HlMaps maps,
                                                                           const HlP p) {
+  static_assert(HEAD == 0 || (NT == 32 && RESIDENT && !DGRAD && G == 1 && !KWC && !CTA2 && HEAD <= 5),
+                "fused head: last 32-channel conv, tap-shift kernel");
   static_assert(!KWC || (NT == 32 && KS == 3 && G == 1), "kw-concatenation: 32-column tiles of a 3x3 conv");
   static_assert(!CTA2 || (NT == 128 && !RESIDENT && G == 1 && !KWC), "CTA pairs: 128-column tiles, streamed weights");
   constexpr int NB = KWC ? KS * NT : NT;                  // rows (GEMM N) of one weight plane of a slot
@@ -222,6 +273,11 @@ __global__ void __launch_bounds__(hl_threads(hl_two_sets(KWC, G, DGRAD)), 1) con
       reinterpret_cast<volatile uint32_t*>(smem_gen + bar_off + 8 * (2 * HL_MAX_ASTAGES + 2 * HL_MAX_BSLOTS + 8));
   float* qbuf = reinterpret_cast<float*>(smem_gen + bar_off + 1024);     // [2 stages][256]
   float* s_sm = qbuf + 512;                                              // softplus(w_sigma) [cout <= 512]
+  // fused head: W [32][HEAD], W^2 [32][HEAD], s [8], then the exchange array [2*HEAD+1][128 rows]
+  float* head_w = s_sm + 512;
+  float* head_w2 = head_w + 32 * (HEAD > 0 ? HEAD : 1);
+  float* head_s = head_w2 + 32 * (HEAD > 0 ? HEAD : 1);
+  float* head_ex = head_s + 8;
 
   const int warp = __shfl_sync(0xffffffffu, (int)(threadIdx.x >> 5), 0);   // provably warp-uniform
   const int lane = threadIdx.x & 31;
@@ -268,6 +324,14 @@ __global__ void __launch_bounds__(hl_threads(hl_two_sets(KWC, G, DGRAD)), 1) con
   }
   constexpr bool TWO_SETS = hl_two_sets(KWC, G, DGRAD);
   for (int i = threadIdx.x; i < p.s_len; i += hl_threads(TWO_SETS)) s_sm[i] = p.s[i];
+  if constexpr (HEAD > 0) {
+    for (int i = threadIdx.x; i < 32 * HEAD; i += hl_threads(TWO_SETS)) {
+      const float v = p.head_w[i];
+      head_w[i] = v;
+      head_w2[i] = v * v;
+    }
+    if (threadIdx.x < HEAD) head_s[threadIdx.x] = softplus_f(p.head_ws[threadIdx.x]);
+  }
   ptx::tc_fence_before();
   __syncthreads();
   if constexpr (CTA2) ptx::cluster_sync_all();      // both CTAs' barriers exist before any remote arrive / multicast commit
@@ -514,7 +578,8 @@ __global__ void __launch_bounds__(hl_threads(hl_two_sets(KWC, G, DGRAD)), 1) con
           if (row < p.rows_box && !(HL_DBG(p) & 4)) {
 #pragma unroll
            for (int t = 0; t < G; ++t) {
-            float qa = 0.f, qb = 0.f, qc = 0.f, qd = 0.f;         // four chains for ILP
+            float qa = 0.f, qb = 0.f, qc = 0.f, qd = 0.f;         // independent chains for ILP
+            float qe = 0.f, qf = 0.f;                             // forward only: sum of hi * lo
             const uint8_t* ar = smem_gen + a_stage_i * a_stage + t * 3 * p.a_plane + row * 64;
 #pragma unroll
             for (int j = 0; j < 4; ++j) {
@@ -535,18 +600,17 @@ __global__ void __launch_bounds__(hl_threads(hl_two_sets(KWC, G, DGRAD)), 1) con
                 const uint4 vv4 = *reinterpret_cast<const uint4*>(ar + 2 * p.a_plane + ch);
                 const uint32_t hh[4] = {hh4.x, hh4.y, hh4.z, hh4.w}, ll[4] = {ll4.x, ll4.y, ll4.z, ll4.w},
                                vv[4] = {vv4.x, vv4.y, vv4.z, vv4.w};
+                // mu^2 = (hi + lo)^2 = hi^2 + 2 hi lo (+ lo^2 <= 2^-18 hi^2, dropped: far below the bf16 variance operands
+                // this term is added to); six mixed-precision instructions per channel pair instead of fourteen
 #pragma unroll
                 for (int e = 0; e < 4; ++e) {
-                  const float m_a = hl_lo(hh[e]) + hl_lo(ll[e]);
-                  const float m_b = hl_hi(hh[e]) + hl_hi(ll[e]);
-                  qa = fmaf(m_a, m_a, qa);
-                  qb = fmaf(m_b, m_b, qb);
-                  qc += hl_lo(vv[e]);
-                  qd += hl_hi(vv[e]);
+                  hl_fma2(hh[e], hh[e], qa, qb);
+                  hl_fma2(hh[e], ll[e], qe, qf);
+                  hl_add2(vv[e], qc, qd);
                 }
               }
             }
-            qsum[t] += (qa + qb) + (qc + qd);
+            qsum[t] += ((qa + qb) + (qc + qd)) + 2.f * (qe + qf);
            }
           }
           __syncwarp();
@@ -726,7 +790,8 @@ __global__ void __launch_bounds__(hl_threads(hl_two_sets(KWC, G, DGRAD)), 1) con
             uint32_t hi[8], lo[8], vr[8];
 #pragma unroll
             for (int j = 0; j < 8; ++j) {
-              const float m0 = hl_lo(shw[j]) + hl_lo(slw[j]), m1 = hl_hi(shw[j]) + hl_hi(slw[j]);
+              float m0, m1;
+              hl_sum2(shw[j], slw[j], m0, m1);
               float a0 = fmaf(m0, r2, __uint_as_float(am[2 * j])), a1 = fmaf(m1, r2, __uint_as_float(am[2 * j + 1]));
               float v0 = __uint_as_float(av[2 * j]) + r, v1 = __uint_as_float(av[2 * j + 1]) + r;
               if (gate) {
@@ -734,7 +799,7 @@ __global__ void __launch_bounds__(hl_threads(hl_two_sets(KWC, G, DGRAD)), 1) con
                 if (!(m1 > 0.f)) { a1 = 0.f; v1 = 0.f; }
               }
               hi[j] = hl_pack2(a0, a1);
-              lo[j] = hl_pack2(a0 - hl_lo(hi[j]), a1 - hl_hi(hi[j]));
+              lo[j] = hl_resid2(hi[j], a0, a1);
               vr[j] = hl_pack2(v0, v1);
             }
             if (valid) {
@@ -774,7 +839,7 @@ __global__ void __launch_bounds__(hl_threads(hl_two_sets(KWC, G, DGRAD)), 1) con
               const size_t o = (((size_t)ob * p.out_h + oy) * p.out_w + ox) * p.cout + nch;
               f_mu = p.dst_mu + o;
               f_var = p.dst_var + o;
-            } else {
+            } else if (HEAD == 0 || p.dst != nullptr) {
               d_hi = p.dst + ((((size_t)ob * p.dh + oy + p.dy0) * p.dw + ox + p.dx0) * 3) * p.dc + p.dc0 + nch;
             }
           }
@@ -818,7 +883,7 @@ __global__ void __launch_bounds__(hl_threads(hl_two_sets(KWC, G, DGRAD)), 1) con
                   for (int j = 0; j < 8; ++j) {
                     const float a0 = __uint_as_float(am[2 * j]), a1 = __uint_as_float(am[2 * j + 1]);
                     hi[j] = hl_pack2(a0, a1);
-                    lo[j] = hl_pack2(a0 - hl_lo(hi[j]), a1 - hl_hi(hi[j]));
+                    lo[j] = hl_resid2(hi[j], a0, a1);
                   }
                   if (tma_st) {
                     stage32(0, hi);
@@ -912,6 +977,86 @@ __global__ void __launch_bounds__(hl_threads(hl_two_sets(KWC, G, DGRAD)), 1) con
               var[j] = vj;
             }
           }
+          if constexpr (HEAD > 0) {
+            // ---- fused conv_final + softmax (see the kernel's header comment); NH == 16: the only chunk of this warp
+            uint32_t hi[8], lo[8], vr[8];
+#pragma unroll
+            for (int j = 0; j < 8; ++j) {
+              const float a0 = mu[2 * j], a1 = mu[2 * j + 1];
+              hi[j] = hl_pack2(a0, a1);
+              lo[j] = hl_resid2(hi[j], a0, a1);
+              vr[j] = hl_pack2(var[2 * j], var[2 * j + 1]);
+            }
+            if (valid && d_hi != nullptr) {          // optional: the 32-channel tensor itself (packed destination)
+              ptx::st_global_v8(d_hi, hi);
+              ptx::st_global_v8(d_hi + p.dc, lo);
+              ptx::st_global_v8(d_hi + 2 * p.dc, vr);
+            }
+            // hand-over of the channel 0-15 partial sums: ONE exchange row per pixel, strict ping-pong between the two
+            // warps of a quarter (named barriers `full` / `free`), so the first warp runs at most one tile ahead and
+            // works on tile t+1 while the second finishes tile t.  Both release the accumulator stage right away: their
+            // columns are in registers.
+            float* ex = head_ex + row;                                // [k][row]: consecutive lanes, consecutive words
+            const uint32_t bar_full = 1u + (uint32_t)q, bar_free = 5u + (uint32_t)q;
+            ptx::tc_fence_before();
+            __syncwarp();
+            if (lane == 0) release_acc();
+            float hm[HEAD], hv[HEAD], hr;
+            if (half == 0) {
+#pragma unroll
+              for (int k = 0; k < HEAD; ++k) hm[k] = hv[k] = 0.f;
+              hr = 0.f;
+            } else {
+              ptx::named_barrier(bar_full, 64);                       // the channel 0-15 partial sums have landed
+#pragma unroll
+              for (int k = 0; k < HEAD; ++k) { hm[k] = ex[k * HL_BM]; hv[k] = ex[(HEAD + k) * HL_BM]; }
+              hr = ex[2 * HEAD * HL_BM];
+              if (titer + 1 < n_tiles_cta) {                          // (the last tile has no successor to admit)
+                __threadfence_block();
+                ptx::named_barrier_arrive(bar_free, 64);
+              }
+            }
+            const float* hw = head_w + (half * NH) * HEAD;
+            const float* hw2 = head_w2 + (half * NH) * HEAD;
+#pragma unroll
+            for (int j = 0; j < 8; ++j) {
+              // the values final_conv_softmax_kernel would read back: mean = hi + lo, variance = bf16
+              float m0, m1;
+              hl_sum2(hi[j], lo[j], m0, m1);
+              head_accumulate<HEAD>(m0, hl_lo(vr[j]), hw + (2 * j) * HEAD, hw2 + (2 * j) * HEAD, hm, hv, hr);
+              head_accumulate<HEAD>(m1, hl_hi(vr[j]), hw + (2 * j + 1) * HEAD, hw2 + (2 * j + 1) * HEAD, hm, hv, hr);
+            }
+            if (half == 0) {
+              if (titer > 0) ptx::named_barrier(bar_free, 64);        // the previous tile's sums have been taken
+#pragma unroll
+              for (int k = 0; k < HEAD; ++k) { ex[k * HL_BM] = hm[k]; ex[(HEAD + k) * HL_BM] = hv[k]; }
+              ex[2 * HEAD * HL_BM] = hr;
+              __threadfence_block();
+              ptx::named_barrier_arrive(bar_full, 64);
+            } else {
+              float pj[HEAD], vo[HEAD];
+              head_finish<HEAD>(hm, hv, hr, head_s, pj, vo);
+              if (valid) {
+                const size_t i = ((size_t)ob * p.Ho + oy_i) * p.Wo + ox_i;
+                if constexpr (HEAD == 4) {
+                  reinterpret_cast<float4*>(p.head_p)[i] = make_float4(pj[0], pj[1], pj[2], pj[3]);
+                  reinterpret_cast<float4*>(p.head_v)[i] = make_float4(vo[0], vo[1], vo[2], vo[3]);
+                  if (p.head_pre_mu) {
+                    reinterpret_cast<float4*>(p.head_pre_mu)[i] = make_float4(hm[0], hm[1], hm[2], hm[3]);
+                    reinterpret_cast<float4*>(p.head_pre_var)[i] = make_float4(hv[0], hv[1], hv[2], hv[3]);
+                  }
+                } else {
+#pragma unroll
+                  for (int a = 0; a < HEAD; ++a) { p.head_p[i * HEAD + a] = pj[a]; p.head_v[i * HEAD + a] = vo[a]; }
+                  if (p.head_pre_mu) {
+#pragma unroll
+                    for (int a = 0; a < HEAD; ++a) { p.head_pre_mu[i * HEAD + a] = hm[a]; p.head_pre_var[i * HEAD + a] = hv[a]; }
+                  }
+                }
+              }
+            }
+            continue;
+          }
           if (valid) {
             if (p.dst_f32) {
 #pragma unroll
@@ -925,7 +1070,7 @@ __global__ void __launch_bounds__(hl_threads(hl_two_sets(KWC, G, DGRAD)), 1) con
               for (int j = 0; j < 8; ++j) {
                 const float a0 = mu[2 * j], a1 = mu[2 * j + 1];
                 hi[j] = hl_pack2(a0, a1);                                   // one packed convert
-                lo[j] = hl_pack2(a0 - hl_lo(hi[j]), a1 - hl_hi(hi[j]));
+                lo[j] = hl_resid2(hi[j], a0, a1);
                 vr[j] = hl_pack2(var[2 * j], var[2 * j + 1]);
               }
               if (p.v8) {
@@ -947,7 +1092,7 @@ __global__ void __launch_bounds__(hl_threads(hl_two_sets(KWC, G, DGRAD)), 1) con
           }
         }
         }
-        if (!tma_st) {
+        if (!tma_st && HEAD == 0) {
           ptx::tc_fence_before();
           __syncwarp();
           if (lane == 0) release_acc();
@@ -1111,12 +1256,12 @@ static int hl_make_weight_map(CUtensorMap* out, const void* w_packed, int taps, 
   return SN_OK;
 }
 
-template <int NT, int KS, bool RESIDENT, bool DGRAD, int G = 1, bool KWC = false, bool CTA2 = false>
+template <int NT, int KS, bool RESIDENT, bool DGRAD, int G = 1, bool KWC = false, bool CTA2 = false, int HEAD = 0>
 static int hl_launch3(const HlMaps& maps, const HlP& p, cudaStream_t st) {
   static std::once_flag once;
   static cudaError_t attr_err = cudaSuccess;
   std::call_once(once, [] {
-    attr_err = cudaFuncSetAttribute(conv_moments_halo_kernel<NT, KS, RESIDENT, DGRAD, G, KWC, CTA2>,
+    attr_err = cudaFuncSetAttribute(conv_moments_halo_kernel<NT, KS, RESIDENT, DGRAD, G, KWC, CTA2, HEAD>,
                                     cudaFuncAttributeMaxDynamicSharedMemorySize, HL_SMEM);
   });
   if (attr_err != cudaSuccess) return fail(SN_ERR_LAUNCH, "conv_halo: cannot reserve %d B of shared memory", HL_SMEM);
@@ -1140,7 +1285,7 @@ static int hl_launch3(const HlMaps& maps, const HlP& p, cudaStream_t st) {
       q.attrs = a;
       q.numAttrs = 1;
       int n = 0;
-      if (cudaOccupancyMaxActiveClusters(&n, conv_moments_halo_kernel<NT, KS, RESIDENT, DGRAD, G, KWC, CTA2>, &q) ==
+      if (cudaOccupancyMaxActiveClusters(&n, conv_moments_halo_kernel<NT, KS, RESIDENT, DGRAD, G, KWC, CTA2, HEAD>, &q) ==
               cudaSuccess && n > 0)
         max_clusters = n;
       else
@@ -1179,7 +1324,7 @@ static int hl_launch3(const HlMaps& maps, const HlP& p, cudaStream_t st) {
   }
   cfg.attrs = attr;
   cfg.numAttrs = na;
-  cudaError_t e = cudaLaunchKernelEx(&cfg, conv_moments_halo_kernel<NT, KS, RESIDENT, DGRAD, G, KWC, CTA2>, maps, p);
+  cudaError_t e = cudaLaunchKernelEx(&cfg, conv_moments_halo_kernel<NT, KS, RESIDENT, DGRAD, G, KWC, CTA2, HEAD>, maps, p);
   if (e != cudaSuccess) return fail(SN_ERR_LAUNCH, "conv_halo launch: %s", cudaGetErrorString(e));
   return check_launch(DGRAD ? "conv_moments_halo_dgrad" : "conv_moments_halo");
 }
@@ -1196,6 +1341,14 @@ static int hl_launch(const HlMaps& maps, const HlP& p, cudaStream_t st) {
     }
   }
   if constexpr (NT == 32) {
+    if (p.head_labels) {               // fused conv_final + softmax (hl_head_fusable() has checked the variant)
+      switch (p.head_labels) {
+        case 2: return hl_launch3<32, 3, true, false, 1, false, false, 2>(maps, p, st);
+        case 3: return hl_launch3<32, 3, true, false, 1, false, false, 3>(maps, p, st);
+        case 4: return hl_launch3<32, 3, true, false, 1, false, false, 4>(maps, p, st);
+        default: return hl_launch3<32, 3, true, false, 1, false, false, 5>(maps, p, st);
+      }
+    }
     if (p.kwc) {
       return p.b_resident ? hl_launch3<32, 3, true, false, 1, true>(maps, p, st)
                           : hl_launch3<32, 3, false, false, 1, true>(maps, p, st);
@@ -1255,7 +1408,7 @@ static bool hl_view_v8(const sn_packed_view& v) {
 
 // Tile geometry + shared-memory plan shared by the forward and the data-gradient dispatch.
 static int hl_plan(HlP& p, const HaloTiling& t, int keff, int ncols, int nt, int cblk, bool kwc = false,
-                   bool tma_store = false, int cta2_mode = 1) {
+                   bool tma_store = false, int cta2_mode = 1, bool head = false) {
   p.kwc = kwc ? 1 : 0;
   p.tma_store = tma_store ? 1 : 0;
   p.cta2 = 0;
@@ -1280,8 +1433,8 @@ static int hl_plan(HlP& p, const HaloTiling& t, int keff, int ncols, int nt, int
   p.a_plane = ((rows_need * 64 + 1023) / 1024) * 1024;
   p.ksize = keff;
   // shared-memory plan: [A stages][B slots][1 KB barriers][2 KB q buffers][2 KB s], 1 KB alignment slack
-  // (+ 8 staging buffers behind s when the epilogue stores through TMA)
-  const int avail = HL_SMEM - 1024 - 1024 - 2048 - 2048 - (tma_store ? 8 * HL_STG_BUF : 0);
+  // (+ 8 staging buffers behind s when the epilogue stores through TMA, or the fused head's 16 KB)
+  const int avail = HL_SMEM - 1024 - 1024 - 2048 - 2048 - (tma_store ? 8 * HL_STG_BUF : 0) - (head ? HL_HEAD_SMEM : 0);
   const int a_stage = 3 * p.a_plane;
   const int b_slot = 3 * (kwc ? keff * nt : nt) * HL_KC * 2;
   const int resident_slots = cblk * (kwc ? keff : keff * keff);
@@ -1354,8 +1507,16 @@ static int hl_plan(HlP& p, const HaloTiling& t, int keff, int ncols, int nt, int
   return SN_OK;
 }
 
-// Called by sn_conv_moments_fwd_tc (sn_tc_conv.cu) after argument validation.
-int conv_moments_halo_dispatch(const sn_tc_conv_desc* d, cudaStream_t stream) {
+// Which layers can end in the fused head: 3x3, ReLU, one 32-channel source, 32 output channels, packed (or no)
+// destination, 2-5 labels -- the shape of up4_conv2 -> conv_final in both reference graphs (Brats.py:453-455).
+static bool hl_head_shape_ok(const sn_tc_conv_desc* d, int n_labels) {
+  return d->ksize == 3 && d->cout == 32 && d->src_c[0] == 32 && d->src_c[1] == 0 && n_labels >= 2 && n_labels <= 5 &&
+         (d->flags & SN_TC_RELU) && !(d->flags & (SN_TC_UPCONV | SN_TC_DST_F32 | SN_TC_IM2COL | SN_TC_KWC)) &&
+         d->rsum_out == nullptr;
+}
+
+// Called by sn_conv_moments_fwd_tc / sn_conv_moments_fwd_tc_head (sn_tc_conv.cu) after argument validation.
+int conv_moments_halo_dispatch(const sn_tc_conv_desc* d, cudaStream_t stream, const sn_tc_head_desc* head) {
   SN_REQUIRE(hl_encode_tiled() != nullptr, SN_ERR_DRIVER, "conv_halo: cuTensorMapEncodeTiled unavailable");
   const bool upconv = (d->flags & SN_TC_UPCONV) != 0;
   const bool dst_f32 = (d->flags & SN_TC_DST_F32) != 0;
@@ -1373,7 +1534,10 @@ int conv_moments_halo_dispatch(const sn_tc_conv_desc* d, cudaStream_t stream) {
   SN_REQUIRE(t.eff > 0, SN_ERR_UNSUPPORTED, "conv_halo: no tiling for %dx%d k=%d", d->in_h, d->in_w, keff);
   SN_REQUIRE(d->cout <= 512, SN_ERR_UNSUPPORTED, "conv_halo: cout %d > 512", d->cout);
   bool kwc = false;
-  if (nt == 32 && keff == 3 && !upconv) {
+  if (head != nullptr) {
+    SN_REQUIRE(hl_head_shape_ok(d, head->n_labels), SN_ERR_UNSUPPORTED,
+               "conv_tc_head: needs a 3x3 ReLU conv 32 -> 32 on one packed source and 2..5 labels (sn_tc_head_fusable)");
+  } else if (nt == 32 && keff == 3 && !upconv) {
     const HaloTiling tk = kwc_tiling(d->batch, d->in_h, d->in_w);
     if (kwc_wanted(d->flags, nt, keff, d->in_w, cblk, t, tk)) { t = tk; kwc = true; }
   }
@@ -1391,7 +1555,14 @@ int conv_moments_halo_dispatch(const sn_tc_conv_desc* d, cudaStream_t stream) {
     if ((rc = hl_plan(probe, t, keff, ncols, nt, cblk, kwc, true)) || !probe.b_resident || probe.sa < 2) tma_store = false;
   }
   const int cta2_mode = (d->flags & SN_TC_NO_CTA2) ? 0 : ((d->flags & SN_TC_CTA2) ? 2 : 1);
-  if ((rc = hl_plan(p, t, keff, ncols, nt, cblk, kwc, tma_store, cta2_mode))) return rc;
+  if ((rc = hl_plan(p, t, keff, ncols, nt, cblk, kwc, tma_store, cta2_mode, head != nullptr))) return rc;
+  if (head != nullptr) {
+    SN_REQUIRE(p.b_resident && p.sa >= 2, SN_ERR_UNSUPPORTED, "conv_tc_head: shared-memory plan failed");
+    p.head_labels = head->n_labels;
+    p.head_w = head->w_mu; p.head_ws = head->w_sigma;
+    p.head_p = head->p_out; p.head_v = head->var_out;
+    p.head_pre_mu = head->presoftmax_mu; p.head_pre_var = head->presoftmax_var;
+  }
   p.taps_w = taps_w;
   p.cblk_s[0] = d->src_c[0] / HL_KC; p.cblk_s[1] = d->src_c[1] / HL_KC;
   p.Ho = Ho; p.Wo = Wo; p.B = d->batch;
@@ -1407,6 +1578,8 @@ int conv_moments_halo_dispatch(const sn_tc_conv_desc* d, cudaStream_t stream) {
     return e == nullptr || e[0] != '0';
   }();
   p.v8 = use_v8 && !dst_f32 && hl_view_v8(d->dst) ? 1 : 0;
+  if (head != nullptr && p.dst != nullptr)
+    SN_REQUIRE(p.v8, SN_ERR_UNSUPPORTED, "conv_tc_head: the optional packed destination must be 32-byte aligned");
 
   HlMaps maps;
   for (int s = 0; s < 2; ++s) {
@@ -1504,3 +1677,7 @@ int conv_moments_halo_dgrad_dispatch(const sn_tc_dgrad_desc* d, cudaStream_t str
 }
 
 }  // namespace sn
+
+extern "C" int sn_tc_head_fusable(const sn_tc_conv_desc* d, int32_t n_labels) {
+  return d != nullptr && sn::hl_head_shape_ok(d, n_labels) ? 1 : 0;
+}

@@ -15,6 +15,8 @@ from __future__ import annotations
 
 from typing import Callable, List, Optional, Tuple
 
+import os
+
 import torch
 
 from . import fastops as F
@@ -61,8 +63,12 @@ def _capture_graph(device, launch: Callable[[], None]) -> "torch.cuda.CUDAGraph"
 
 class InferenceEngine:
     def __init__(self, model, batch: int, in_h: int, in_w: int, in_c: int, device, graph: bool = True,
-                 keep_presoftmax: bool = True):
+                 keep_presoftmax: bool = True, fuse_head: Optional[bool] = None):
+        """fuse_head: end the forward inside the last 3x3 conv's epilogue (sn_conv_moments_fwd_tc_head: conv_final +
+        softmax there, the last 32-channel tensor never written; bit-identical outputs).  None = whenever the shape
+        allows and nothing needs that tensor (a GradientEngine does: it passes False); SN_FUSE_HEAD=0 turns it off."""
         self.model = model
+        self.fuse_head = fuse_head
         self.keep_presoftmax = keep_presoftmax
         self.shape = (batch, in_h, in_w, in_c)
         self.device = torch.device(device)
@@ -202,26 +208,53 @@ class InferenceEngine:
             self.skip_window[enc.data_ptr()] = (oy, ox, h, w)            # where the decoder reads the skip tensor
             h, w = h + 2, w + 2
             c2n = getattr(m, f"up{d}_conv2").kernel_num
+            if d == L and self._want_fused_head(c1n, c2n):
+                break                                                    # the head step below runs this conv as well
             out = new(h - 2, w - 2, c2n)
             conv(f"up{d}_conv2", PackedView(mid), c1n, h, w, 3, PackedView(out), True)
             cur, c, h, w = out, c2n, h - 2, w - 2
         # ---- head -----------------------------------------------------------------------------------
-        self.out_hw = (h, w)
         C = m.n_labels
+        wf, wsf = m.conv_final.weights()
+        pre = lambda: (self.pre_m, self.pre_v) if self.keep_presoftmax else (None, None)
+        if self.head_fused:
+            # up{L}_conv2 + ReLU + conv_final + softmax in ONE launch; its 32-channel output is never written
+            name = f"up{L}_conv2"
+            wp, s = self.prepared[name]
+            oh, ow = h - 2, w - 2
+            self._alloc_outputs(B, oh, ow, C, dev)
+            self.step_names.append(name + "+conv_final")
+            self.records.append(dict(kind="conv+head", name=name, src0=PackedView(mid), c0=c1n, h=h, w=w, k=3, cout=c2n))
+            steps.append(lambda src=PackedView(mid), hh=h, ww=w: F.conv_moments_tc_head(
+                src, B, hh, ww, wp, s, wf, wsf, self.p, self.v, *pre()))
+            h, w = oh, ow
+        else:
+            self._alloc_outputs(B, h, w, C, dev)
+            last, lc = cur, c
+            self.step_names.append("conv_final")
+            self.records.append(dict(kind="head", src=PackedView(last), h=h, w=w, c=lc))
+            steps.append(lambda: F.final_conv_softmax_packed(PackedView(last), B, h, w, lc, wf, wsf, self.p, self.v,
+                                                             *pre()))
+        self.out_hw = (h, w)
+        self.n_launches = len(steps)
+
+    def _want_fused_head(self, cin: int, cout: int) -> bool:
+        want = self.fuse_head
+        if want is None:
+            want = os.environ.get("SN_FUSE_HEAD", "1") != "0" and not getattr(self, "want_rsum", False)
+        self.head_fused = bool(want) and F.tc_head_fusable(cin, 0, cout, 3, True, self.model.n_labels)
+        if self.fuse_head and not self.head_fused:
+            raise RuntimeError("fuse_head=True, but the last conv of this model cannot end in the fused head "
+                               "(needs 32 -> 32 channels, k = 3, 2..5 labels)")
+        return self.head_fused
+
+    def _alloc_outputs(self, B: int, h: int, w: int, C: int, dev) -> None:
         # both output maps live in ONE buffer (p = pv[0], v = pv[1]): the host-facing pipeline moves them with a single
         # device-to-host copy per batch
         self.pv = torch.empty((2, B, h * w, C), device=dev, dtype=torch.float32)
         self.p, self.v = self.pv[0], self.pv[1]
         self.pre_m = torch.empty_like(self.p)
         self.pre_v = torch.empty_like(self.p)
-        wf, wsf = m.conv_final.weights()
-        last, lc = cur, c
-        self.step_names.append("conv_final")
-        self.records.append(dict(kind="head", src=PackedView(last), h=h, w=w, c=lc))
-        pre = (self.pre_m, self.pre_v) if self.keep_presoftmax else (None, None)
-        steps.append(lambda: F.final_conv_softmax_packed(PackedView(last), B, h, w, lc, wf, wsf, self.p, self.v,
-                                                         pre[0], pre[1]))
-        self.n_launches = len(steps)
 
     # ------------------------------------------------------------------------------------------------
     def _launch_all(self) -> None:
@@ -292,7 +325,7 @@ class GradientEngine(InferenceEngine):
         self.want_rsum = train
         self.train = train
         self.exact_first_conv = True
-        super().__init__(model, batch, in_h, in_w, in_c, device, graph=False, keep_presoftmax=False)
+        super().__init__(model, batch, in_h, in_w, in_c, device, graph=False, keep_presoftmax=False, fuse_head=False)
         self.use_graph_bwd = graph
         self._graph_bwd: Optional[torch.cuda.CUDAGraph] = None
         self._bwd_steps: List[Callable[[], None]] = []

@@ -16,7 +16,7 @@ from . import _lib
 from ._lib import (SN_TC_CTA2, SN_TC_DST_F32, SN_TC_EXACT, SN_TC_IM2COL, SN_TC_KWC, SN_TC_NO_CTA2, SN_TC_NO_KWC, SN_TC_RELU,
                    SN_TC_ROWS,
                    SN_TC_UPCONV, check, ptr, sn_packed_view, sn_tc_conv_desc,
-                   sn_tc_dgrad_desc, sn_tc_wgrad_desc, stream_ptr)
+                   sn_tc_dgrad_desc, sn_tc_head_desc, sn_tc_wgrad_desc, stream_ptr)
 
 Tensor = torch.Tensor
 
@@ -105,6 +105,48 @@ def conv_moments_tc(src0: PackedView, c0: int, batch: int, in_h: int, in_w: int,
     else:
         d.dst = dst.c_view()
     check(_lib.load().sn_conv_moments_fwd_tc(C.byref(d), stream_ptr()), "conv_moments_fwd_tc")
+
+
+def _head_conv_desc(src: PackedView, batch: int, in_h: int, in_w: int, w_packed: Tensor, s: Tensor,
+                    dst: Optional[PackedView]) -> sn_tc_conv_desc:
+    d = sn_tc_conv_desc()
+    d.src[0] = src.c_view()
+    d.src[1] = d.src[0]
+    d.src_c[0], d.src_c[1] = 32, 0
+    d.batch, d.in_h, d.in_w, d.ksize, d.cout = batch, in_h, in_w, 3, 32
+    d.flags = SN_TC_RELU
+    d.w_packed = w_packed.data_ptr()
+    d.s = s.data_ptr()
+    if dst is not None:
+        d.dst = dst.c_view()
+    return d
+
+
+def tc_head_fusable(cin: int, cin1: int, cout: int, ksize: int, relu: bool, n_labels: int) -> bool:
+    """Can a conv of this shape end in the fused conv_final + softmax head (sn_tc_head_fusable)?"""
+    d = sn_tc_conv_desc()
+    d.src_c[0], d.src_c[1] = cin, cin1
+    d.batch, d.in_h, d.in_w, d.ksize, d.cout = 1, ksize, ksize, ksize, cout
+    d.flags = SN_TC_RELU if relu else 0
+    return bool(_lib.load().sn_tc_head_fusable(C.byref(d), n_labels))
+
+
+def conv_moments_tc_head(src: PackedView, batch: int, in_h: int, in_w: int, w_packed: Tensor, s: Tensor,
+                         w_final: Tensor, ws_final: Tensor, p_out: Tensor, var_out: Tensor,
+                         pre_mu: Optional[Tensor] = None, pre_var: Optional[Tensor] = None,
+                         dst: Optional[PackedView] = None) -> None:
+    """The last 3x3 conv (32 -> 32, ReLU) + conv_final + mysoftmax in one launch (sn_conv_moments_fwd_tc_head);
+    dst=None: the 32-channel tensor is not written."""
+    d = _head_conv_desc(src, batch, in_h, in_w, w_packed, s, dst)
+    h = sn_tc_head_desc()
+    h.n_labels = w_final.shape[-1]
+    h.w_mu, h.w_sigma = w_final.data_ptr(), ws_final.data_ptr()
+    h.p_out, h.var_out = p_out.data_ptr(), var_out.data_ptr()
+    if pre_mu is not None:
+        h.presoftmax_mu, h.presoftmax_var = pre_mu.data_ptr(), pre_var.data_ptr()
+    for t in (w_final, ws_final, p_out, var_out, pre_mu, pre_var):
+        _lib.check_device(t)
+    check(_lib.load().sn_conv_moments_fwd_tc_head(C.byref(d), C.byref(h), stream_ptr()), "conv_moments_fwd_tc_head")
 
 
 def first_conv_packed(x: Tensor, w_mu: Tensor, w_sigma: Tensor, dst: PackedView, relu: bool = True,

@@ -491,3 +491,95 @@ def test_conv_tc_cta_pair_is_bit_identical_and_stays_in_its_window(S, case):
         outs.setdefault(cta2, []).append(win.view(torch.int16))
     assert torch.equal(outs[True][0], outs[True][1]), "CTA-pair results differ between identical launches"
     assert torch.equal(outs[True][0], outs[False][0]), "CTA-pair result differs from the single-CTA kernel"
+
+
+# ------------------------------------------------------------------------------------------------------------
+# fused head: the last 3x3 conv + conv_final + mysoftmax in one launch (sn_conv_moments_fwd_tc_head,
+# Brats.py:451-455) must reproduce the two-kernel path bit for bit
+# ------------------------------------------------------------------------------------------------------------
+@pytest.mark.parametrize("variant,C,in_ch,B,alpha", [("hippocampus", 3, 1, 3, 1.0), ("hippocampus", 2, 1, 2, 1.0),
+                                                     ("brats", 4, 4, 1, O.BRATS_ALPHA), ("brats", 5, 4, 1, O.BRATS_ALPHA)])
+def test_fused_head_engine_is_bit_identical_to_two_kernels(S, variant, C, in_ch, B, alpha):
+    from supernet_b200.engine import InferenceEngine
+    w32 = O.make_weights(variant, 32, C, in_ch)
+    model = S.Density_prop_with_pad_UNET(32, C, variant=variant, mode="fast").load_weight_dict(w32, device="cuda")
+    x = dev(O.make_input(variant, B, alpha=alpha))
+    two = InferenceEngine(model, B, x.shape[1], x.shape[2], in_ch, "cuda", graph=False, fuse_head=False)
+    one = InferenceEngine(model, B, x.shape[1], x.shape[2], in_ch, "cuda", graph=True, fuse_head=True)
+    auto = InferenceEngine(model, B, x.shape[1], x.shape[2], in_ch, "cuda", graph=False, keep_presoftmax=False)
+    assert one.head_fused and auto.head_fused and not two.head_fused
+    assert one.n_launches == two.n_launches - 1 and one.step_names[-1].endswith("+conv_final")
+    for e in (two, one, auto):
+        e.x_in.copy_(x)
+        e.forward_resident()
+    one.forward_resident()                      # graph replay
+    torch.cuda.synchronize()
+    assert bool(torch.isfinite(one.p).all()) and float(one.p.sum(-1).min()) > 0.999
+    for name in ("p", "v", "pre_m", "pre_v"):
+        assert torch.equal(getattr(one, name), getattr(two, name)), name
+    assert torch.equal(auto.p, two.p) and torch.equal(auto.v, two.v)
+
+
+@pytest.mark.parametrize("C", [2, 3, 4, 5])
+@pytest.mark.parametrize("shape", [(2, 21, 45), (1, 64, 64), (3, 9, 130)])
+def test_conv_tc_head_op(S, C, shape):
+    """Direct call: with a destination window the 32-channel tensor is also stored (bit-identical to the plain conv, nothing
+    outside the window touched); without one only the fp32 maps are written."""
+    F = S.fastops
+    B, H, W = shape
+    mu, var, w, ws = rand_layer(B, H, W, 32, 32, 3, seed=11 + C)
+    g = torch.Generator().manual_seed(7 + C)
+    wf = dev(torch.randn(1, 1, 32, C, generator=g) * 0.05)
+    wsf = dev(torch.empty(C).uniform_(-6, -2, generator=g))
+    src = F.pack_moments(dev(mu), dev(var))
+    wp, s = F.prepare_weights(dev(w), dev(ws))
+    Ho, Wo = H - 2, W - 2
+    ref = F.packed_empty(B, Ho, Wo, 32, "cuda")
+    F.conv_moments_tc(F.PackedView(src), 32, B, H, W, 3, 32, wp, s, dst=F.PackedView(ref), relu=True, kwc=False)
+    outs_ref = [torch.empty(B, Ho * Wo, C, device="cuda") for _ in range(4)]
+    F.final_conv_softmax_packed(F.PackedView(ref), B, Ho, Wo, 32, wf, wsf, *outs_ref)
+    # (a) no destination, no pre-softmax outputs
+    pa, va = torch.empty_like(outs_ref[0]), torch.empty_like(outs_ref[0])
+    F.conv_moments_tc_head(F.PackedView(src), B, H, W, wp, s, wf, wsf, pa, va)
+    # (b) destination = a window of a canary-filled buffer, with pre-softmax outputs
+    canary = torch.full((B, Ho + 3, Wo + 4, 3, 32), -7.0, device="cuda", dtype=torch.bfloat16)
+    big = canary.clone()
+    outs = [torch.full_like(outs_ref[0], float("nan")) for _ in range(4)]
+    for _ in range(2):                           # repeated launches: same bits
+        F.conv_moments_tc_head(F.PackedView(src), B, H, W, wp, s, wf, wsf, *outs, dst=F.PackedView(big, 1, 2, 0))
+    torch.cuda.synchronize()
+    assert torch.equal(pa, outs_ref[0]) and torch.equal(va, outs_ref[1])
+    for o, r in zip(outs, outs_ref):
+        assert torch.equal(o, r)
+    assert torch.equal(big[:, 1:1 + Ho, 2:2 + Wo], ref)
+    mask = torch.ones_like(big, dtype=torch.bool)
+    mask[:, 1:1 + Ho, 2:2 + Wo] = False
+    assert torch.equal(big[mask], canary[mask])
+    # the oracle, for the record (per-layer bars of this file; the head on top is fp32 arithmetic)
+    m_o, v_o = O.relu(*O.conv_intermediate_conv_form(mu, var, w, ws))
+    p_o, vo_o, _, _ = _oracle_head(m_o, v_o, wf.double().cpu(), wsf.double().cpu())
+    assert rel(outs[0].reshape(p_o.shape), p_o) < 1e-3 and rel(outs[1].reshape(vo_o.shape), vo_o) < 1e-2
+
+
+def _oracle_head(mu, var, wf, wsf):
+    m, v = O.conv_intermediate_conv_form(mu, var, wf, wsf)
+    p, vo = O.softmax_as_written(m, v)
+    return p, vo, m, v
+
+
+def test_conv_tc_head_rejects_what_it_cannot_fuse(S):
+    F = S.fastops
+    assert F.tc_head_fusable(32, 0, 32, 3, True, 4) and F.tc_head_fusable(32, 0, 32, 3, True, 2)
+    assert not F.tc_head_fusable(64, 0, 32, 3, True, 4)        # two channel blocks
+    assert not F.tc_head_fusable(32, 32, 32, 3, True, 4)       # concat input
+    assert not F.tc_head_fusable(32, 0, 64, 3, True, 4)        # 64 output channels
+    assert not F.tc_head_fusable(32, 0, 32, 1, True, 4)        # 1x1
+    assert not F.tc_head_fusable(32, 0, 32, 3, False, 4)       # conv_final must read a post-ReLU tensor
+    assert not F.tc_head_fusable(32, 0, 32, 3, True, 6)        # more labels than the fused head is built for
+    from supernet_b200.engine import InferenceEngine
+    w64 = O.make_weights("hippocampus", 64, 3, 1)
+    model = S.Density_prop_with_pad_UNET(64, 3, variant="hippocampus", mode="fast").load_weight_dict(w64, device="cuda")
+    eng = InferenceEngine(model, 1, 64, 64, 1, "cuda", graph=False)        # n_kernels 64: falls back to two kernels
+    assert not eng.head_fused and eng.step_names[-1] == "conv_final"
+    with pytest.raises(RuntimeError, match="cannot end in the fused head"):
+        InferenceEngine(model, 1, 64, 64, 1, "cuda", graph=False, fuse_head=True)

@@ -38,6 +38,7 @@ def test_struct_layouts_match_header():
     # backward descriptors (ABI v2): g_out + in[2] + g_in[2] views, 4 + 6 ints, 2 pointers / g_out + in[2], 2 + 6 ints, 6 pointers
     assert C.sizeof(L.sn_tc_dgrad_desc) == 5 * 40 + 4 * 4 + 6 * 4 + 2 * 8
     assert C.sizeof(L.sn_tc_wgrad_desc) == 3 * 40 + 2 * 4 + 6 * 4 + 6 * 8
+    assert C.sizeof(L.sn_tc_head_desc) == 8 + 6 * 8                                          # n_labels (+ pad), 6 pointers
 
 
 def test_argument_validation_needs_no_device():
@@ -56,6 +57,15 @@ def test_argument_validation_needs_no_device():
     t.batch, t.in_h, t.in_w, t.ksize, t.cout = 1, 8, 8, 3, 32
     t.src_c[0] = 16                                                                          # not a multiple of 32
     assert lib.sn_conv_moments_fwd_tc(C.byref(t), None) == -2
+    # fused head: shape query and argument checks (no launch)
+    t.src_c[0], t.flags = 32, S._lib.SN_TC_RELU
+    assert lib.sn_tc_head_fusable(C.byref(t), 4) == 1 and lib.sn_tc_head_fusable(C.byref(t), 6) == 0
+    assert lib.sn_tc_head_fusable(None, 4) == 0
+    t.cout = 64
+    assert lib.sn_tc_head_fusable(C.byref(t), 4) == 0
+    hd = S._lib.sn_tc_head_desc()
+    hd.n_labels = 4
+    assert lib.sn_conv_moments_fwd_tc_head(None, C.byref(hd), None) == -1
     g = S._lib.sn_tc_dgrad_desc()
     g.batch, g.in_h, g.in_w, g.ksize, g.cout = 1, 8, 8, 3, 32
     g.in_c[0] = 48                                                                           # not a multiple of 32
