@@ -667,6 +667,15 @@ __global__ void __launch_bounds__(hl_threads(hl_two_sets(KWC, G, DGRAD)), 1) con
           if (CTA2 && crank != 0) ptx::mbar_arrive_remote(acc_empty(as), 0);
           else ptx::mbar_arrive(acc_empty(as));
         };
+        // The accumulator stage goes back to the issuer as soon as this warp's LAST TMEM load has returned -- the math,
+        // conversions and stores of that chunk run on registers.  (With two pixel tiles per weight slot the issuer needs
+        // BOTH stages back before the next pair: 28 % of its stall samples were this wait, tools/ncu_waits.py.)
+        constexpr bool EARLY_REL = DGRAD || !TWO_SETS;
+        auto early_release = [&]() {
+          ptx::tc_fence_before();
+          __syncwarp();
+          if (lane == 0) release_acc();
+        };
         WAIT(q_full(as), par);
         const float* myq = qbuf + as * 256;
         float qv[taps];
@@ -785,6 +794,7 @@ __global__ void __launch_bounds__(hl_threads(hl_two_sets(KWC, G, DGRAD)), 1) con
             }
             uint32_t am[16], av[16];
             load_acc16(c0, am, av);
+            if (c0 + 16 >= NH) early_release();
             const bool gate = p.gate[seg] != 0;
             const float r2 = 2.f * r;
             uint32_t hi[8], lo[8], vr[8];
@@ -959,6 +969,7 @@ __global__ void __launch_bounds__(hl_threads(hl_two_sets(KWC, G, DGRAD)), 1) con
           }
           uint32_t am[16], av[16];
           load_acc16(c0, am, av);
+          if (c0 + 16 >= NH) early_release();
           float mu[16], var[16];
 #pragma unroll
           for (int j4 = 0; j4 < 16; j4 += 4) {
@@ -994,13 +1005,9 @@ __global__ void __launch_bounds__(hl_threads(hl_two_sets(KWC, G, DGRAD)), 1) con
             }
             // hand-over of the channel 0-15 partial sums: ONE exchange row per pixel, strict ping-pong between the two
             // warps of a quarter (named barriers `full` / `free`), so the first warp runs at most one tile ahead and
-            // works on tile t+1 while the second finishes tile t.  Both release the accumulator stage right away: their
-            // columns are in registers.
+            // works on tile t+1 while the second finishes tile t.  (Both have released the accumulator stage already.)
             float* ex = head_ex + row;                                // [k][row]: consecutive lanes, consecutive words
             const uint32_t bar_full = 1u + (uint32_t)q, bar_free = 5u + (uint32_t)q;
-            ptx::tc_fence_before();
-            __syncwarp();
-            if (lane == 0) release_acc();
             float hm[HEAD], hv[HEAD], hr;
             if (half == 0) {
 #pragma unroll
@@ -1092,7 +1099,7 @@ __global__ void __launch_bounds__(hl_threads(hl_two_sets(KWC, G, DGRAD)), 1) con
           }
         }
         }
-        if (!tma_st && HEAD == 0) {
+        if (!tma_st && !EARLY_REL) {
           ptx::tc_fence_before();
           __syncwarp();
           if (lane == 0) release_acc();
