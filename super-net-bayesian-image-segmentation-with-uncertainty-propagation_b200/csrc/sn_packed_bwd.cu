@@ -828,18 +828,31 @@ __global__ void __launch_bounds__(256) final_conv_wgrad_kernel(sn_packed_view in
 #pragma unroll
     for (int j = 0; j < C; ++j) ad[j] += __shfl_xor_sync(0xffffffffu, ad[j], o);
   }
+  // reduce over the block's warps in shared memory, then ONE atomic per (block, output): with one atomic per warp the
+  // kernel ended in ~1.2 M atomics on nine cache lines (B200, batch 64: 485 us for 505 MB of input)
+  constexpr int NOUT = 2 * 32 * C + C;
+  __shared__ float red[8][NOUT];
+  const int warp = threadIdx.x >> 5;
   if (psub == 0) {
 #pragma unroll
     for (int e = 0; e < 8; ++e)
 #pragma unroll
       for (int j = 0; j < C; ++j) {
-        atomicAdd(p_mu + (size_t)(chunk * 8 + e) * C + j, am[e][j]);
-        atomicAdd(p_var + (size_t)(chunk * 8 + e) * C + j, av[e][j]);
+        red[warp][(chunk * 8 + e) * C + j] = am[e][j];
+        red[warp][32 * C + (chunk * 8 + e) * C + j] = av[e][j];
       }
     if (chunk == 0) {
 #pragma unroll
-      for (int j = 0; j < C; ++j) atomicAdd(ds + j, ad[j]);
+      for (int j = 0; j < C; ++j) red[warp][64 * C + j] = ad[j];
     }
+  }
+  __syncthreads();
+  for (int o = threadIdx.x; o < NOUT; o += blockDim.x) {
+    float t = 0.f;
+#pragma unroll
+    for (int w = 0; w < 8; ++w) t += red[w][o];
+    float* dst = o < 32 * C ? p_mu + o : (o < 64 * C ? p_var + (o - 32 * C) : ds + (o - 64 * C));
+    atomicAdd(dst, t);
   }
 }
 
@@ -1051,7 +1064,7 @@ int sn_final_conv_bwd_weight_packed(const sn_packed_view* in, int32_t batch, int
   if (cudaMemsetAsync(wsf, 0, (2 * n_w + n_labels) * sizeof(float), s) != cudaSuccess)
     return fail(SN_ERR_LAUNCH, "final_conv_wgrad: memset failed");
   const size_t total = (size_t)batch * in_h * in_w;
-  const int grid = ew_grid((total + 7) / 8 * 32, 256, 4);
+  const int grid = ew_grid((total + 7) / 8 * 32, 256, 2);     // 256 threads x ~114 registers: two blocks per SM
 #define SN_FCW(CC)                                                                                                  \
   case CC:                                                                                                          \
     final_conv_wgrad_kernel<CC><<<grid, 256, 0, s>>>(*in, batch, in_h, in_w, g_logit_mu, g_logit_var, rsum, wsf,    \

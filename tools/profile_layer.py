@@ -1,5 +1,5 @@
 """Run one FAST-mode conv layer (BraTS shapes) alone, L2 flushed before each launch; prints CUDA-event times.
-usage: profile_layer.py <layer> <batch> [im2col]"""
+usage: profile_layer.py <layer> <batch> [im2col|rsum]"""
 import os
 import sys
 
@@ -18,6 +18,7 @@ LAYERS = {  # name: (H, cin0, cin1, cout, k, upconv)
 name = sys.argv[1]
 B = int(sys.argv[2])
 im2col = len(sys.argv) > 3 and sys.argv[3] == "im2col"
+want_rsum = len(sys.argv) > 3 and sys.argv[3] == "rsum"        # training forward: also emit the rank-1 statistic
 H, c0, c1, cout, k, up = LAYERS[name]
 g = torch.Generator(device="cuda").manual_seed(0)
 src0 = torch.randn((B, H, H, 3, c0), device="cuda", generator=g).bfloat16().abs()
@@ -28,11 +29,12 @@ wp, s = F.prepare_weights(w, ws, upconv=up)
 Ho = 2 * H if up else H - k + 1
 out = F.packed_empty(B, Ho, Ho, cout, "cuda")
 flush = torch.empty(512 << 20, dtype=torch.uint8, device="cuda")
+rs = torch.empty((B, H, H) if up else (B, Ho, Ho), device="cuda") if want_rsum else None
 
 
 def run():
     F.conv_moments_tc(F.PackedView(src0), c0, B, H, H, k, cout, wp, s, dst=F.PackedView(out), relu=not up, upconv=up,
-                      src1=F.PackedView(src1) if c1 else None, c1=c1, im2col=im2col)
+                      src1=F.PackedView(src1) if c1 else None, c1=c1, im2col=im2col, rsum_out=rs)
 
 
 run()
