@@ -618,6 +618,13 @@ class StreamingPipeline:
                         for _ in range(depth)]
         self.streams = [torch.cuda.Stream(device=self.device) for _ in range(depth)]
         self.done = [torch.cuda.Event() for _ in range(depth)]
+        # One forward at a time: slot i's graph waits for the graph submitted before it.  Every conv kernel is persistent
+        # and owns all 148 SMs, so two graphs on independent streams only interleave kernel by kernel -- which breaks the
+        # programmatic-dependent-launch chaining inside a graph and halves the L2 reuse between a layer and the next --
+        # while the copies (separate DMA engines) are what the extra streams are for.  SN_PIPE_SERIAL=0: old behaviour.
+        self.serial = os.environ.get("SN_PIPE_SERIAL", "1") != "0"
+        self.computed = [torch.cuda.Event() for _ in range(depth)]
+        self._last: Optional[int] = None
         e0 = self.engines[0]
         self.pv_host = [torch.empty(e0.pv.shape, dtype=torch.float32).pin_memory() for _ in range(depth)]
         self.p_host = [t[0] for t in self.pv_host]
@@ -644,10 +651,14 @@ class StreamingPipeline:
         with torch.cuda.stream(st):
             eng.sync_weights()                   # operands follow in-place weight updates (every engine has its own)
             eng.x_in.copy_(x_host, non_blocking=True)
+            if self.serial and self._last is not None and self._last != slot:
+                st.wait_event(self.computed[self._last])
             p, v = eng.forward_resident()
+            self.computed[slot].record(st)
             self.pv_host[slot].copy_(eng.pv, non_blocking=True)      # both maps, one DMA
             self.done[slot].record(st)
         self._busy[slot] = True
+        self._last = slot
         return slot
 
     def result(self, slot: int) -> Tuple[Tensor, Tensor]:
