@@ -91,6 +91,25 @@ def conv_table(variant="brats", n=N_KERNELS, C=N_LABELS, in_ch=IN_CH, H=IN_HW):
     return rows
 
 
+def _per_launch_bound(names, per_ms, tmap, B, pk):
+    """Sum over the conv launches of max(algorithmic FLOPs / tensor peak, algorithmic bytes / HBM peak), against the
+    sum of their measured times (CUDA events)."""
+    t_min = t_meas = 0.0
+    hbm_bound = []
+    for nm, t in zip(names, per_ms):
+        r = tmap.get(nm)
+        if r is None:
+            continue
+        tf = r["flops"] * B / (pk["tf_sustained"] * 1e12) * 1e3
+        th = r["bytes"] * B / (pk["hbm"] * 1e9) * 1e3
+        t_min += max(tf, th)
+        t_meas += t
+        if th > tf:
+            hbm_bound.append(nm)
+    return {"t_min_ms": round(t_min, 4), "t_measured_ms": round(t_meas, 4), "frac": round(t_min / t_meas, 4),
+            "hbm_bound_launches": hbm_bound, "hbm_peak_gbs": pk["hbm"], "tensor_peak_tflops": pk["tf_sustained"]}
+
+
 class ClockSampler:
     """nvidia-smi clocks / throttle reasons sampled DURING the timed region (B200_PROFILING.md recipe)."""
     Q = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,clocks_event_reasons.hw_slowdown,"
@@ -484,6 +503,9 @@ def main():
                     "algorithmic_bytes": round(sum(tmap[nm]["bytes"] for nm in names if nm in tmap and nm not in
                                                    ("conv_input", "conv_final")) * B),
                     "peak_source": f"{pk['source']} bf16 sustained", "share_of_step": round(tc_ms / sum(per), 3),
+                    # every launch against ITS OWN roofline: t_min = max(FLOPs / tensor peak, bytes / HBM peak) -- the
+                    # 32-channel layers have 95 FLOP/B and sit left of the ridge (215 FLOP/B): HBM bounds them
+                    "per_launch_bound": _per_launch_bound(names, per, tmap, B, pk),
                     "algorithmic_gflop_per_slice": round(flops_slice / 1e9, 3)}
 
     # ---- FGSM / training side measurements: every rank takes part (the training step all-reduces over NCCL) ----

@@ -81,7 +81,7 @@ struct HlP {
   int TWo, THo;            // valid output columns / rows per tile
   int R, THb, TN;          // halo box: columns, rows, images
   int rows_box;            // R * THb * TN  (<= 254)
-  int a_plane;             // bytes reserved per A plane per stage (multiple of 1024)
+  int a_plane;             // bytes reserved per A plane per stage (multiple of 1024; 512 in one CTA-pair plan, see hl_plan)
   int ksize, taps_w;       // K-side taps per dim; taps in the prepared weights
   int cblk_s[4];           // 32-channel K blocks taken from each source
   int pad;                 // data gradient: the box origin is shifted by -(k-1); TMA zero-fills outside the window
@@ -230,12 +230,21 @@ __global__ void __launch_bounds__(hl_threads(hl_two_sets(KWC, G, DGRAD)), 1) con
   static_assert(HEAD == 0 || (NT == 32 && RESIDENT && !DGRAD && G == 1 && !KWC && !CTA2 && HEAD <= 5),
                 "fused head: last 32-channel conv, tap-shift kernel");
   static_assert(!KWC || (NT == 32 && KS == 3 && G == 1), "kw-concatenation: 32-column tiles of a 3x3 conv");
-  static_assert(!CTA2 || (NT == 128 && !RESIDENT && G == 1 && !KWC), "CTA pairs: 128-column tiles, streamed weights");
+  static_assert(!CTA2 || (((NT == 128 && !RESIDENT) || (NT == 64 && RESIDENT)) && G == 1 && !KWC),
+                "CTA pairs: 128-column tiles with streamed weights, 64-column tiles with resident half-slots");
   constexpr int NB = KWC ? KS * NT : NT;                  // rows (GEMM N) of one weight plane of a slot
   constexpr int SLOTS_PER_CB = KWC ? KS : KS * KS;        // weight slots per 32-channel block: filter rows / taps
-  constexpr int B_PLANE = (CTA2 ? NB / 2 : NB) * HL_KC * 2;   // CTA pair: this CTA's half of the plane
-  constexpr int B_SLOT = 3 * B_PLANE;
   constexpr bool CONCAT = !KWC && NT <= 64;               // hi x [W_hi ; W_lo] as one UMMA of N = 2*NT
+  // CTA pair + CONCAT (NT = 64): a cta_group::2 UMMA takes the first half of its N columns from the leader's shared
+  // memory and the second half from the peer's, at the SAME offsets.  Slot layout per CTA (rank r), 2*NT rows of 64 B:
+  //   X [NT rows]   : r = 0 W_hi[0:NT], r = 1 W_lo[0:NT]        -> hi x [W_hi ; W_lo], N = 2*NT
+  //   Y [NT/2 rows] : W_hi[r*NT/2 : (r+1)*NT/2]                  -> lo x W_hi,         N = NT
+  //   Z [NT/2 rows] : W^2 [r*NT/2 : (r+1)*NT/2]                  -> var x W^2,         N = NT
+  // Same instruction order per accumulator column as the single-CTA CONCAT kernel: bit-identical results.
+  constexpr bool PAIR_CONCAT = CTA2 && CONCAT;
+  constexpr int B_PLANE = (CTA2 ? NB / 2 : NB) * HL_KC * 2;   // CTA pair: this CTA's half of the plane
+  constexpr int B_SLOT = PAIR_CONCAT ? 2 * NT * HL_KC * 2 : 3 * B_PLANE;
+  constexpr int B_OFF_Y = NT * HL_KC * 2, B_OFF_Z = B_OFF_Y + (NT / 2) * HL_KC * 2;      // PAIR_CONCAT regions
   constexpr int ACC_STAGE = KWC ? 2 * NB : (CONCAT ? 3 * NT : 2 * NT);     // TMEM columns per accumulator stage
   constexpr int TMEM_COLS = 2 * ACC_STAGE <= 256 ? 256 : 512;              // 2 stages, rounded up to a power of two
   extern __shared__ uint8_t smem_raw[];
@@ -254,9 +263,8 @@ __global__ void __launch_bounds__(hl_threads(hl_two_sets(KWC, G, DGRAD)), 1) con
   auto q_full = [&](int s) { return bar_base + 8u * (2 * HL_MAX_ASTAGES + 2 * HL_MAX_BSLOTS + 4 + s); };
   auto q_empty = [&](int s) { return bar_base + 8u * (2 * HL_MAX_ASTAGES + 2 * HL_MAX_BSLOTS + 6 + s); };
   const uint32_t tmem_slot = bar_base + 8u * (2 * HL_MAX_ASTAGES + 2 * HL_MAX_BSLOTS + 8);
-  // CTA pair, leader only: "the peer's A stage / weight half-slot has landed" (sb <= HL_CTA2_MAX_BSLOTS there)
+  // CTA pair, leader only: "the peer's A stage has landed" (its weight half-slots signal the leader's b_full directly)
   auto pa_full = [&](int s) { return bar_base + 8u * (2 * HL_MAX_ASTAGES + 2 * HL_MAX_BSLOTS + 9 + s); };
-  auto pb_full = [&](int s) { return bar_base + 8u * (2 * HL_MAX_ASTAGES + 2 * HL_MAX_BSLOTS + 9 + HL_MAX_ASTAGES + s); };
   const uint32_t crank = CTA2 ? ptx::cluster_ctarank() : 0u;
   // CTA pairs poll (barriers there are completed from the other CTA; see mbar_wait_poll), everything else may park
   auto WAIT = [](uint32_t bar, uint32_t parity) {
@@ -292,7 +300,7 @@ __global__ void __launch_bounds__(hl_threads(hl_two_sets(KWC, G, DGRAD)), 1) con
       if (p.cblk_s[s])
         for (int pl = 0; pl < 3; ++pl) ptx::prefetch_tensormap(&maps.a[s][pl]);
     ptx::prefetch_tensormap(&maps.w);
-    if (KWC && !DGRAD && p.tma_store) ptx::prefetch_tensormap(&maps.d);
+    if ((KWC && !DGRAD && p.tma_store) || PAIR_CONCAT) ptx::prefetch_tensormap(&maps.d);
     for (int s = 0; s < p.sa; ++s) {
       ptx::mbar_init(a_full(s), 1);
       ptx::mbar_init(a_empty(s), 9);          // UMMA commit + the 8 reducer warps
@@ -303,7 +311,6 @@ __global__ void __launch_bounds__(hl_threads(hl_two_sets(KWC, G, DGRAD)), 1) con
     }
     if constexpr (CTA2) {
       for (int s = 0; s < p.sa; ++s) ptx::mbar_init(pa_full(s), 1);
-      for (int s = 0; s < p.sb; ++s) ptx::mbar_init(pb_full(s), 1);
     }
     for (int s = 0; s < 2; ++s) {
       ptx::mbar_init(acc_full(s), 1);
@@ -352,7 +359,14 @@ __global__ void __launch_bounds__(hl_threads(hl_two_sets(KWC, G, DGRAD)), 1) con
       auto load_b_slot = [&](uint32_t sb_addr, uint32_t bar, int cbt, int tap, int ncol0, int n0) {
         const int row = p.upconv ? ncol0 : n0;                      // up-conv: the (parity, channel) axis, one "tap"
         const int t0 = p.upconv ? 0 : (KWC ? tap * KS : tap);
-        if constexpr (CTA2) {
+        if constexpr (PAIR_CONCAT) {
+          // three requests (maps.w: NT rows of one plane, maps.d: NT/2 rows of one plane), all signalled on the LEADER's
+          // b_full; used with resident weights only, so the request count is a one-off
+          const uint32_t lb = ptx::map_to_rank(bar, 0);
+          ptx::tma_load_4d_pair(sb_addr, &maps.w, lb, cbt * HL_KC, row, t0, (int)crank);                        // X
+          ptx::tma_load_4d_pair(sb_addr + B_OFF_Y, &maps.d, lb, cbt * HL_KC, row + (int)crank * (NT / 2), t0, 0);   // Y
+          ptx::tma_load_4d_pair(sb_addr + B_OFF_Z, &maps.d, lb, cbt * HL_KC, row + (int)crank * (NT / 2), t0, 2);   // Z
+        } else if constexpr (CTA2) {
           // CTA pair: this CTA's 64 rows of the 128-row N tile, landing in its own shared memory but signalled on the
           // LEADER's b_full, which expects both halves
           ptx::tma_load_4d_pair(sb_addr, &maps.w, ptx::map_to_rank(bar, 0), cbt * HL_KC, row + (int)crank * (NT / 2), t0, 0);
@@ -364,15 +378,16 @@ __global__ void __launch_bounds__(hl_threads(hl_two_sets(KWC, G, DGRAD)), 1) con
       int ai = 0, bi = 0;     // running A-stage / B-slot fill counters
       TileIt it;
       it.init(blockIdx.x, gridDim.x, p);
-      if (RESIDENT && blockIdx.x < p.total_tiles) {
-        // resident weights: the whole layer's operands for this CTA's N tile, before the dependency wait
-        const int ncol0 = it.nt * NT;
+      if (RESIDENT && u0 < n_units) {
+        // resident weights: the whole layer's operands for this CTA's N tile, before the dependency wait (CTA pair:
+        // tiles_n == 1, each CTA keeps ITS half of every slot and both halves complete the leader's barrier)
+        const int ncol0 = CTA2 ? 0 : it.nt * NT;
         const int group = ncol0 / p.cout;
         const int n0 = ncol0 - group * p.cout;
         for (int cbt = 0; cbt < cblk; ++cbt)
           for (int tap = 0; tap < SLOTS_PER_CB; ++tap) {
             const int slot = cbt * SLOTS_PER_CB + tap;
-            ptx::mbar_arrive_expect_tx(b_full(slot), (uint32_t)B_SLOT);
+            if (!CTA2 || crank == 0) ptx::mbar_arrive_expect_tx(b_full(slot), (uint32_t)(CTA2 ? 2 * B_SLOT : B_SLOT));
             load_b_slot(b_base + slot * B_SLOT, b_full(slot), cbt, tap, ncol0, n0);
           }
       }
@@ -451,7 +466,7 @@ __global__ void __launch_bounds__(hl_threads(hl_two_sets(KWC, G, DGRAD)), 1) con
       // one elected lane issues the UMMAs and commits.  Taps and K steps are fully unrolled so every descriptor is
       // "per-stage base + immediate": the issuing thread must sustain one UMMA per ~45 cycles.
       constexpr uint32_t idesc_n = ptx::idesc_bf16_f32(CTA2 ? 2 * HL_BM : HL_BM, NB);
-      constexpr uint32_t idesc_2n = ptx::idesc_bf16_f32(HL_BM, CONCAT ? 2 * NT : NT);
+      constexpr uint32_t idesc_2n = ptx::idesc_bf16_f32(CTA2 ? 2 * HL_BM : HL_BM, CONCAT ? 2 * NT : NT);
       // descriptor = constant high word | (1 << 16 | address >> 4) in the low word (smem < 256 KB: 14 bits);
       // high word of smem_desc_kmajor<64>: SBO = 512 B >> 4 at bits [32,46), version 1 at bit 46, SW64 (4) at [61,64)
       constexpr uint32_t DESC_HI = 32u | (1u << 14) | (4u << 29);
@@ -519,7 +534,10 @@ __global__ void __launch_bounds__(hl_threads(hl_two_sets(KWC, G, DGRAD)), 1) con
                 for (int ks = 0; ks < HL_KC / 16; ++ks) {
                   const uint32_t k16 = ks * 2;                          // 16 bf16 = 32 B along K
                   const uint32_t acc = (cbt > 0 || tap > 0 || ks > 0) ? 1u : 0u;
-                  if constexpr (CONCAT) {
+                  if constexpr (PAIR_CONCAT) {
+                    ptx::umma2_bf16(acc_mu, desc(a0 + k16), desc(b0 + k16), idesc_2n, acc);                           // X
+                    ptx::umma2_bf16(acc_mu, desc(a0 + plane16 + k16), desc(b0 + (B_OFF_Y >> 4) + k16), idesc_n, 1u);  // Y
+                  } else if constexpr (CONCAT) {
                     ptx::umma_bf16(acc_mu, desc(a0 + k16), desc(b0 + k16), idesc_2n, acc);               // hi x [Whi;Wlo]
                     ptx::umma_bf16(acc_mu, desc(a0 + plane16 + k16), desc(b0 + k16), idesc_n, 1u);      // lo x Whi
                   } else if constexpr (CTA2) {
@@ -531,7 +549,9 @@ __global__ void __launch_bounds__(hl_threads(hl_two_sets(KWC, G, DGRAD)), 1) con
                     ptx::umma_bf16(acc_mu, desc(a0 + plane16 + k16), desc(b0 + k16), idesc_n, 1u);
                     ptx::umma_bf16(acc_mu, desc(a0 + k16), desc(b0 + BPLANE16 + k16), idesc_n, 1u);
                   }
-                  if constexpr (CTA2)
+                  if constexpr (PAIR_CONCAT)
+                    ptx::umma2_bf16(acc_var, desc(a0 + 2 * plane16 + k16), desc(b0 + (B_OFF_Z >> 4) + k16), idesc_n, acc);
+                  else if constexpr (CTA2)
                     ptx::umma2_bf16(acc_var, desc(a0 + 2 * plane16 + k16), desc(b0 + 2 * BPLANE16 + k16), idesc_n, acc);
                   else
                     ptx::umma_bf16(acc_var, desc(a0 + 2 * plane16 + k16), desc(b0 + 2 * BPLANE16 + k16), idesc_n, acc);
@@ -1251,10 +1271,10 @@ static int hl_make_dst_map(CUtensorMap* out, const sn_packed_view& v, int cout, 
 // Prepared weights [3 planes][taps][n][cin] as a 4-D tensor (cin, n, tap, plane); one box = the three planes of
 // `box_taps` consecutive taps x `box_n` rows x 32 channels.
 static int hl_make_weight_map(CUtensorMap* out, const void* w_packed, int taps, int cout, int cin, int box_n,
-                              int box_taps = 1) {
+                              int box_taps = 1, int box_planes = 3) {
   cuuint64_t dims[4] = {(cuuint64_t)cin, (cuuint64_t)cout, (cuuint64_t)taps, 3};
   cuuint64_t strides[3] = {(cuuint64_t)cin * 2, (cuuint64_t)cin * cout * 2, (cuuint64_t)taps * cin * cout * 2};
-  cuuint32_t box[4] = {HL_KC, (cuuint32_t)box_n, (cuuint32_t)box_taps, 3};
+  cuuint32_t box[4] = {HL_KC, (cuuint32_t)box_n, (cuuint32_t)box_taps, (cuuint32_t)box_planes};
   cuuint32_t estr[4] = {1, 1, 1, 1};
   CUresult r = hl_encode_tiled()(out, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 4, const_cast<void*>(w_packed), dims, strides,
                                  box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_64B,
@@ -1347,6 +1367,9 @@ static int hl_launch(const HlMaps& maps, const HlP& p, cudaStream_t st) {
       }
     }
   }
+  if constexpr (NT == 64) {
+    if (p.cta2) return hl_launch3<64, 3, true, false, 1, false, true>(maps, p, st);   // k = 3, resident half-slots (hl_plan)
+  }
   if constexpr (NT == 32) {
     if (p.head_labels) {               // fused conv_final + softmax (hl_head_fusable() has checked the variant)
       switch (p.head_labels) {
@@ -1387,6 +1410,9 @@ static int hl_launch_dgrad(const HlMaps& maps, const HlP& p, cudaStream_t st) {
         default: return hl_launch3<128, 3, false, true, 1, false, true>(maps, p, st);
       }
     }
+  }
+  if constexpr (NT == 64) {
+    if (p.cta2) return hl_launch3<64, 3, true, true, 1, false, true>(maps, p, st);
   }
   if constexpr (NT == 32) {
     if (p.kwc) {
@@ -1474,6 +1500,37 @@ static int hl_plan(HlP& p, const HaloTiling& t, int keff, int ncols, int nt, int
     const long long pairs = (long long)p.tiles_n * ((p.pix_tiles + 1) / 2);
     // (not for k = 1 / up-convs by default: one tap per channel block is too little UMMA work per handshake -- measured
     //  +15...20 % on the three 2x2 up-convs -- while the 3x3 layers gain 3...12 %, profiles/r02_cta2.md)
+    // 64-column tiles (k = 3, tiles_n == 1: conv2/3, up3_conv2, up4_conv1's data gradient ...): a pair keeps HALF of every
+    // weight slot per SM -- 8 KB instead of 12 (the X / Y / Z regions of the kernel) -- so layers whose weights do not fit
+    // one SM (conv3, up3_conv2: 18 slots) become resident: no weight stream at all and, unlike two tiles per weight slot
+    // (G = 2), every tile keeps its own double-buffered accumulator stage.  conv3 at batch 64: 0.216 -> 0.161 ms.
+    // Streamed half-slots (up3_conv1: 36 slots) measured SLOWER than G = 2 (0.353 vs 0.294 ms) and are not built.
+    // SN_CTA2_64: 0 never, 1 (default) layers whose weights do not fit one SM, 2 every eligible layer.
+    {
+      static const int mode64_env = [] {
+        const char* e = getenv("SN_CTA2_64");
+        return e == nullptr ? 1 : atoi(e);
+      }();
+      const int slot_pair = 2 * nt * HL_KC * 2;
+      // Activation planes may start on multiples of 512 B here (the period of the SWIZZLE_64B pattern: address bits
+      // [4,6) ^= bits [7,9), so absolute and tile-relative swizzles agree) instead of 1 KB: that is what lets up3_conv2
+      // (18 slots of 8 KB + two stages of 3 x 194 rows) fit.  (512 B everywhere was measured: conv1 +9 %, others +-3 %.)
+      const int a_plane512 = ((rows_need * 64 + 511) / 512) * 512;
+      int a_stage_p = a_stage;
+      if (resident_slots * slot_pair + 2 * a_stage_p > avail) a_stage_p = 3 * a_plane512;
+      if (mode != 0 && mode64_env != 0 && nt == 64 && keff == 3 && p.tiles_n == 1 && !kwc &&
+          (mode == 2 || ((!p.b_resident || mode64_env == 2) && 4 * pairs >= 3 * (num_sms() / 2))) &&
+          resident_slots <= HL_MAX_BSLOTS && resident_slots * slot_pair + 2 * a_stage_p <= avail) {
+        p.cta2 = 1;
+        p.b_resident = 1;
+        p.a_plane = a_stage_p / 3;
+        p.sb = resident_slots;
+        p.sa = (avail - resident_slots * slot_pair) / a_stage_p;
+        if (p.sa > HL_MAX_ASTAGES) p.sa = HL_MAX_ASTAGES;
+        p.total_groups = (int)pairs;
+        return SN_OK;
+      }
+    }
     if (mode != 0 && nt == 128 && !p.b_resident && !kwc &&
         (mode == 2 || (keff >= 2 && 4 * pairs >= 3 * (num_sms() / 2)))) {
       const int b_half = b_slot / 2;
@@ -1597,10 +1654,12 @@ int conv_moments_halo_dispatch(const sn_tc_conv_desc* d, cudaStream_t stream, co
   }
   for (int pl = 0; pl < 3; ++pl) maps.a[2][pl] = maps.a[3][pl] = maps.a[0][pl];     // unused
   // regular: [3*taps][cout][cin]; up-conv: [3][4*cout][cin] (same memory, parity and channel fused into one axis)
+  const bool pair64 = p.cta2 && nt == 64;       // X region: NT rows of ONE plane; maps.d: NT/2 rows of one plane (Y, Z)
   if ((rc = hl_make_weight_map(&maps.w, d->w_packed, upconv ? 1 : taps_w, upconv ? ncols : d->cout, cin,
-                               p.cta2 ? nt / 2 : nt, p.kwc ? 3 : 1)))
+                               pair64 ? nt : (p.cta2 ? nt / 2 : nt), p.kwc ? 3 : 1, pair64 ? 1 : 3)))
     return rc;
   maps.d = maps.w;
+  if (pair64 && (rc = hl_make_weight_map(&maps.d, d->w_packed, taps_w, d->cout, cin, nt / 2, 1, 1))) return rc;
   if (p.tma_store && (rc = hl_make_dst_map(&maps.d, d->dst, d->cout, out_h, out_w, d->batch, t.TWo))) return rc;
   switch (nt) {
     case 128: return hl_launch<128>(maps, p, stream);
@@ -1672,10 +1731,13 @@ int conv_moments_halo_dgrad_dispatch(const sn_tc_dgrad_desc* d, cudaStream_t str
         return rc;
   }
   // transposed weights [3][taps][N = cin][K = nsrc * cout]
-  if ((rc = hl_make_weight_map(&maps.w, d->wt_packed, keff * keff, ncols, nsrc * d->cout, p.cta2 ? nt / 2 : nt,
-                               p.kwc ? 3 : 1)))
+  const bool pair64 = p.cta2 && nt == 64;
+  if ((rc = hl_make_weight_map(&maps.w, d->wt_packed, keff * keff, ncols, nsrc * d->cout,
+                               pair64 ? nt : (p.cta2 ? nt / 2 : nt), p.kwc ? 3 : 1, pair64 ? 1 : 3)))
     return rc;
-  maps.d = maps.w;          // unused
+  maps.d = maps.w;          // unused, except by the 64-column CTA pairs
+  if (pair64 && (rc = hl_make_weight_map(&maps.d, d->wt_packed, keff * keff, ncols, nsrc * d->cout, nt / 2, 1, 1)))
+    return rc;
   switch (nt) {
     case 128: return hl_launch_dgrad<128>(maps, p, stream);
     case 64: return hl_launch_dgrad<64>(maps, p, stream);

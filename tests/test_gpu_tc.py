@@ -459,6 +459,11 @@ CTA2_CASES = [
     (2, 5, 5, 256, 0, 128, 2, True),        # up-conv: N = 4 x 128
     (2, 10, 10, 128, 128, 128, 3, False),   # two sources
     (1, 6, 6, 512, 0, 512, 3, False),       # one pixel tile, four N tiles: every pair is a tile and its unsaved copy
+    # 64-column tiles: resident half-slots in the X / Y / Z layout (hi x [W_hi ; W_lo] split across the pair)
+    (3, 20, 20, 64, 0, 64, 3, False),       # conv3-like, odd number of pixel tiles
+    (64, 24, 24, 64, 0, 64, 3, False),      # several tile pairs per cluster
+    (2, 12, 12, 32, 0, 64, 3, False),       # conv2-like: one channel block
+    (2, 10, 10, 32, 32, 64, 3, False),      # two sources
 ]
 
 

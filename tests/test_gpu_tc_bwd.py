@@ -541,7 +541,8 @@ def test_dgrad_writes_only_its_window_and_is_deterministic(S, case):
 
 
 @pytest.mark.parametrize("case", [(3, 20, 20, 128, 128, 3), (20, 24, 24, 128, 128, 3), (2, 9, 9, 256, 128, 3),
-                                  (2, 5, 5, 128, 256, 2)])
+                                  (2, 5, 5, 128, 256, 2),
+                                  (3, 20, 20, 64, 64, 3), (20, 24, 24, 64, 64, 3), (2, 14, 14, 64, 32, 3)])   # 64-column pairs
 def test_dgrad_cta_pair_is_bit_identical(S, case):
     """Data gradient through the CTA-pair variant (N = cin = 128-column tiles): bit-identical to the single-CTA kernel."""
     F = S.fastops
