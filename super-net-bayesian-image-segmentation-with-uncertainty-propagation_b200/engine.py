@@ -224,9 +224,19 @@ class InferenceEngine:
             oh, ow = h - 2, w - 2
             self._alloc_outputs(B, oh, ow, C, dev)
             self.step_names.append(name + "+conv_final")
-            self.records.append(dict(kind="conv+head", name=name, src0=PackedView(mid), c0=c1n, h=h, w=w, k=3, cout=c2n))
-            steps.append(lambda src=PackedView(mid), hh=h, ww=w: F.conv_moments_tc_head(
-                src, B, hh, ww, wp, s, wf, wsf, self.p, self.v, *pre()))
+            dstv = None
+            if getattr(self, "keep_last", False):
+                # a gradient engine needs the 32-channel tensor (the head's backward recomputes conv_final from it):
+                # the fused launch stores it as well, and the records read as if the two layers had run separately
+                dstv = PackedView(new(oh, ow, c2n))
+                self.records.append(dict(kind="conv", name=name, src0=PackedView(mid), c0=c1n, src1=None, c1=0, h=h, w=w,
+                                         k=3, cout=c2n, dst=dstv, relu=True, upconv=False, rsum=None))
+                self.records.append(dict(kind="head", src=dstv, h=oh, w=ow, c=c2n))
+            else:
+                self.records.append(dict(kind="conv+head", name=name, src0=PackedView(mid), c0=c1n, h=h, w=w, k=3,
+                                         cout=c2n))
+            steps.append(lambda src=PackedView(mid), hh=h, ww=w, dstv=dstv: F.conv_moments_tc_head(
+                src, B, hh, ww, wp, s, wf, wsf, self.p, self.v, *pre(), dst=dstv))
             h, w = oh, ow
         else:
             self._alloc_outputs(B, h, w, C, dev)
@@ -325,7 +335,11 @@ class GradientEngine(InferenceEngine):
         self.want_rsum = train
         self.train = train
         self.exact_first_conv = True
-        super().__init__(model, batch, in_h, in_w, in_c, device, graph=False, keep_presoftmax=False, fuse_head=False)
+        self.keep_last = True
+        # FGSM / saliency chains end the forward in the fused head too (it also stores the last 32-channel tensor);
+        # training needs that layer's rank-1 statistic (rsum_out), which the fused launch does not emit
+        super().__init__(model, batch, in_h, in_w, in_c, device, graph=False, keep_presoftmax=False,
+                         fuse_head=False if train else None)
         self.use_graph_bwd = graph
         self._graph_bwd: Optional[torch.cuda.CUDAGraph] = None
         self._bwd_steps: List[Callable[[], None]] = []
