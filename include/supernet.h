@@ -190,9 +190,11 @@ enum { SN_TC_RELU = 1, SN_TC_UPCONV = 2, SN_TC_DST_F32 = 4, SN_TC_IM2COL = 8, SN
  *     tile, k = 3, width >= 32: the three taps of a filter row are N columns of one UMMA and are summed with a lane
  *     shift in the epilogue; packed rows leave through TMA stores).  Default: the library's choice (layers with >= 2
  *     input channel blocks).  Same results to rounding either way; an A/B and test switch like SN_TC_IM2COL.
- *   - SN_TC_CTA2 / SN_TC_NO_CTA2: force / forbid the CTA-pair variant (128 output columns per tile, streamed weights):
- *     clusters of two CTAs issue cta_group::2 UMMAs of M = 256 over two pixel tiles and each SM holds half of every
- *     weight slot.  Default: the library's choice (enough tile pairs to fill the SM pairs).  Bit-identical results.
+ *   - SN_TC_CTA2 / SN_TC_NO_CTA2: force / forbid the CTA-pair variant (128 output columns per tile with streamed weights;
+ *     64 output columns per tile, k = 3, with half of every weight slot RESIDENT per SM): clusters of two CTAs issue
+ *     cta_group::2 UMMAs of M = 256 over two pixel tiles and each SM holds half of every weight slot.  Default: the
+ *     library's choice (enough tile pairs to fill the SM pairs; 64 columns: layers whose weights do not fit one SM).
+ *     Bit-identical results.
  *     instead of the default persistent halo-tiled kernel; same results, kept for A/B measurements. */
 typedef struct sn_tc_conv_desc {
   sn_packed_view src[2];

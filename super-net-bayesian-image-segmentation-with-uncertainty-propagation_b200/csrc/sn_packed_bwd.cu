@@ -741,8 +741,8 @@ __global__ void __launch_bounds__(FW_THREADS) first_conv_wgrad_k3c32_kernel(int 
         const float* xp = xs + ((py + kh) * XW + px + kw) * CIN;
         if constexpr (CIN == 4) {
           const float4 xv = *reinterpret_cast<const float4*>(xp);
-          acc[0] = fmaf(xv.x, g, acc[0]); acc[1] = fmaf(xv.y, g, acc[1]);
-          acc[2] = fmaf(xv.z, g, acc[2]); acc[3] = fmaf(xv.w, g, acc[3]);
+          fma2(acc[0], acc[1], g, xv.x, xv.y);          // FFMA2: this loop is issue-bound (62 % issue-active in ncu)
+          fma2(acc[2], acc[3], g, xv.z, xv.w);
         } else {
 #pragma unroll
           for (int c = 0; c < CIN; ++c) acc[c] = fmaf(xp[c], g, acc[c]);
