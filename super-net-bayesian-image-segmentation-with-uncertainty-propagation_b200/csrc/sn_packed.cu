@@ -280,10 +280,11 @@ __global__ void __launch_bounds__(FC_THREADS) first_conv_k3c32_kernel(int B, int
 #pragma unroll
         for (int q = 0; q < FC_PPT; ++q) {
           const float xk = xv[q][k];
-          acc[q][0] = fmaf(xk, w0.x, acc[q][0]); acc[q][1] = fmaf(xk, w0.y, acc[q][1]);
-          acc[q][2] = fmaf(xk, w0.z, acc[q][2]); acc[q][3] = fmaf(xk, w0.w, acc[q][3]);
-          acc[q][4] = fmaf(xk, w1.x, acc[q][4]); acc[q][5] = fmaf(xk, w1.y, acc[q][5]);
-          acc[q][6] = fmaf(xk, w1.z, acc[q][6]); acc[q][7] = fmaf(xk, w1.w, acc[q][7]);
+          // FFMA2 (fma.rn.f32x2): the kernel is bound by the 1152 FMAs per pixel, two per issue slot halves them
+          fma2(acc[q][0], acc[q][1], xk, w0.x, w0.y);
+          fma2(acc[q][2], acc[q][3], xk, w0.z, w0.w);
+          fma2(acc[q][4], acc[q][5], xk, w1.x, w1.y);
+          fma2(acc[q][6], acc[q][7], xk, w1.z, w1.w);
         }
       }
 #pragma unroll
