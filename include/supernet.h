@@ -238,7 +238,9 @@ int sn_conv_moments_fwd_tc_head(const sn_tc_conv_desc* d, const sn_tc_head_desc*
  * k = 3, cout = 32, cin in {1, 4} runs on the tensor cores (bf16 hi/lo image and weights, ~1e-5 relative); with
  * SN_TC_EXACT the fp32 CUDA-core kernel is used instead: the gradient engine wants this layer's ReLU gates -- the
  * largest tensor of the network -- decided at fp32 accuracy, because every flipped gate is a 100 % error of that
- * element's gradient. */
+ * element's gradient.  SN_TC_ROWS selects the warp-specialised form of the tensor-core kernel (builder / UMMA / epilogue
+ * roles of one persistent CTA, TMA-store epilogue), SN_TC_IM2COL forces the default one-role-per-CTA form: bit-identical
+ * results and the same measured time; an A/B switch. */
 int sn_first_conv_fwd_packed(int32_t batch, int32_t in_h, int32_t in_w, int32_t cin, int32_t cout, int32_t ksize,
                              const float* x, const float* w_mu, const float* w_sigma, const sn_packed_view* dst,
                              int32_t flags, sn_stream_t st);

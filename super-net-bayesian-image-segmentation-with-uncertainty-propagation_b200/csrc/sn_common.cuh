@@ -15,6 +15,7 @@ int fail(int code, const char* fmt, ...);
 // Records cudaGetLastError() (if any) after a launch. Returns SN_OK / SN_ERR_LAUNCH.
 int check_launch(const char* what);
 int num_sms();
+void* tensor_map_encoder();      // cuTensorMapEncodeTiled through cudaGetDriverEntryPoint, or nullptr (sn_tc_halo.cu)
 
 static inline cudaStream_t as_stream(sn_stream_t s) { return reinterpret_cast<cudaStream_t>(s); }
 static inline bool aligned16(const void* p) { return (reinterpret_cast<uintptr_t>(p) & 15u) == 0; }

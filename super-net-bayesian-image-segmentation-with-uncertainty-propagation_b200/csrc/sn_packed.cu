@@ -5,6 +5,8 @@
 #include "sn_common.cuh"
 #include "sn_sm100.cuh"
 
+#include <cuda.h>
+
 #include <stdlib.h>
 #include <mutex>
 
@@ -534,6 +536,302 @@ __global__ void __launch_bounds__(FT_THREADS) first_conv_tc_kernel(int B, int H,
 }
 
 // ---------------------------------------------------------------------------------------------------------
+// The same first convolution, warp-specialised (round 2, last session).  The kernel above runs one role per CTA --
+// build, UMMA, epilogue, with three block-wide barriers per tile -- and relies on 5 CTAs per SM to overlap them:
+// measured 42 % issue-active and 3.3 TB/s of output against the 6.45 TB/s copy peak (profiles/r02_conv_input_by_line.md).
+// Here the three phases are ROLES of one persistent CTA per SM connected by mbarriers:
+//   warp 0        UMMA issuer: waits for a built A stage and a free TMEM accumulator stage, issues the tile's UMMAs
+//   warps 1-8     two epilogue groups (thread = TMEM lane = pixel), group e on the tiles of accumulator stage e: tcgen05.ld,
+//                 + the rank-1 variance s_n * sum x^2 (r comes from the builder through shared memory), ReLU gate, bf16
+//                 hi/lo/var split, stores (one group measured as THE serial stage: ~1 500 cycles of dependent work per tile)
+//   warps 9-20    three builder groups of four warps (thread = pixel), group g on the CTA's tiles g, g+3, ...: nine 16-byte
+//                 loads, hi/lo split, the im2col row written in the SWIZZLE_128B K-major layout of one of four A stages
+// so the global-load latency of tile t+1/t+2, the UMMAs of tile t and the stores of tile t-1 overlap inside one CTA.
+// Same operands, same UMMA order, same epilogue arithmetic as first_conv_tc_kernel: bit-identical output.
+// Measured (B200, batch 64, L2 flushed): 0.141-0.147 ms against 0.141 ms for the kernel above -- with one epilogue group
+// 0.191 ms (the epilogue, ~1 500 cycles of dependent work per tile, was the serial stage), with two or three groups
+// 0.153 ms in the bench; direct 256-bit stores instead of the TMA store 0.159-0.172 ms; a linear staging image + plain bulk
+// copy (4-way bank conflicts) 0.229 ms.  Not the default: see sn_first_conv_fwd_packed.
+constexpr int FWS_GROUPS = 3, FWS_EGROUPS = 2;                  // builder groups, epilogue groups (one per TMEM stage)
+constexpr int FWS_W_BUILD = 1 + 4 * FWS_EGROUPS;                // first builder warp
+constexpr int FW_WARPS = FWS_W_BUILD + 4 * FWS_GROUPS, FW_THREADS_WS = FW_WARPS * 32;
+constexpr int FWS_STAGES = 4, FWS_RSLOTS = FWS_STAGES + 4;      // r slots: a builder may run STAGES tiles ahead of the UMMAs,
+                                                                // the epilogue reads r up to EGROUPS tiles (TMEM stages) later
+constexpr int FWS_TILE_OUT = 128 * 3 * 32 * 2;                  // one tile's packed output: 128 pixels x 192 B, contiguous
+constexpr int FWS_OFF_OUT = FWS_STAGES * 32768 + 8192 + 5120;    // staging buffers, 1 KB aligned (SWIZZLE_64B pattern: 512 B)
+constexpr int FWS_SMEM = 1024 + FWS_OFF_OUT + FWS_EGROUPS * FWS_TILE_OUT;
+constexpr int FWS_TMEM_COLS = FWS_EGROUPS * 64 <= 128 ? 128 : 256;
+
+template <int CIN>
+__global__ void __launch_bounds__(FW_THREADS_WS, 1) first_conv_ws_kernel(const __grid_constant__ CUtensorMap dmap, int B,
+                                                                        int H, int W, const float* __restrict__ x,
+                                                                        const float* __restrict__ w,
+                                                                        const float* __restrict__ ws, sn_packed_view dst,
+                                                                        int relu, int v8, int bulk) {
+  // bulk: the destination is the whole buffer, so a tile's 128 pixels x 3 planes x 64 B are ONE box of the tensor
+  // (channel, plane, pixel): the epilogue stages them in shared memory in the SWIZZLE_64B layout (the 192-byte pixel stride
+  // is then bank-conflict free) and ONE TMA tensor store moves the 24 KB; the map clips the last, partial tile.  Why: a
+  // lane-per-pixel 256-bit store puts one 32-byte sector of 32 different lines into every LSU wavefront (768 wavefronts
+  // per tile), and both forms of this kernel topped out at ~3.3 TB/s of output whatever overlapped with the stores; a
+  // linear staging image (4-way bank conflicts on the 192-byte stride) was measured slower still (0.229 ms).
+  constexpr int K = 9 * CIN, COUT = 32;
+  constexpr int KSTEPS = (K + 15) / 16;
+  constexpr int CHUNKS = KSTEPS * 2;
+  extern __shared__ uint8_t fws_raw[];
+  const uint32_t base = (ptx::smem_u32(fws_raw) + 1023u) & ~1023u;
+  uint8_t* gen = fws_raw + (base - ptx::smem_u32(fws_raw));
+  constexpr int OFF_B = FWS_STAGES * 32768, OFF_R = OFF_B + 8192, OFF_BAR = OFF_R + FWS_RSLOTS * 128 * 4;
+  constexpr int OFF_OUT = FWS_OFF_OUT;                          // one staging buffer of a tile's output per epilogue group
+  static_assert(OFF_BAR + 256 <= OFF_OUT, "barrier block overlaps the staging buffers");
+  uint8_t* b_w = gen + OFF_B;
+  float* r_buf = reinterpret_cast<float*>(gen + OFF_R);
+  const uint32_t bar = base + OFF_BAR;
+  auto a_full = [&](int s) { return bar + 8u * s; };
+  auto a_empty = [&](int s) { return bar + 8u * (FWS_STAGES + s); };
+  auto acc_full = [&](int s) { return bar + 8u * (2 * FWS_STAGES + s); };
+  auto acc_empty = [&](int s) { return bar + 8u * (2 * FWS_STAGES + FWS_EGROUPS + s); };
+  const uint32_t tmem_slot = bar + 8u * (2 * FWS_STAGES + 2 * FWS_EGROUPS);
+  volatile uint32_t* tmem_slot_gen =
+      reinterpret_cast<volatile uint32_t*>(gen + OFF_BAR + 8 * (2 * FWS_STAGES + 2 * FWS_EGROUPS));
+  __shared__ float ss[COUT];
+  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+
+  // ---- B operand, once per CTA: element (n, k) = W[k][n], hi in rows 0-31, lo in rows 32-63 (as in the kernel above)
+  for (int i = tid; i < 64 * 8; i += FW_THREADS_WS) {
+    const int row = i >> 3, c = i & 7;
+    const int n = row & 31;
+    uint32_t v[4];
+#pragma unroll
+    for (int e = 0; e < 4; ++e) {
+      float f[2];
+#pragma unroll
+      for (int h = 0; h < 2; ++h) {
+        const int k = c * 8 + e * 2 + h;
+        float wv = k < K ? w[k * COUT + n] : 0.f;
+        const float hi = __bfloat162float(__float2bfloat16_rn(wv));
+        f[h] = row < 32 ? hi : wv - hi;
+      }
+      v[e] = pk2(f[0], f[1]);
+    }
+    *reinterpret_cast<uint4*>(b_w + (row >> 3) * 1024 + (row & 7) * 128 + ((c ^ (row & 7)) << 4)) =
+        make_uint4(v[0], v[1], v[2], v[3]);
+  }
+  if (tid < COUT) ss[tid] = softplus_f(ws[tid]);
+  // the A stages' unused K columns (chunks >= CHUNKS are never read; chunks < CHUNKS are always written) need no clearing
+  if (tid == 0) {
+    for (int s = 0; s < FWS_STAGES; ++s) {
+      ptx::mbar_init(a_full(s), 128);       // every builder thread of the tile's group arrives (after its own proxy fence)
+      ptx::mbar_init(a_empty(s), 1);        // UMMA commit
+    }
+    for (int s = 0; s < FWS_EGROUPS; ++s) {
+      ptx::mbar_init(acc_full(s), 1);       // UMMA commit
+      ptx::mbar_init(acc_empty(s), 4);      // the four warps of the stage's epilogue group
+    }
+    ptx::fence_barrier_init();
+  }
+  if (warp == 0) {
+    ptx::tmem_alloc(tmem_slot, FWS_TMEM_COLS);      // one accumulator stage of 64 columns per epilogue group
+    ptx::tmem_relinquish();
+  }
+  ptx::fence_proxy_async();
+  ptx::tc_fence_before();
+  __syncthreads();
+  ptx::tc_fence_after();
+  const uint32_t tmem = *tmem_slot_gen;
+
+  const int Ho = H - 2, Wo = W - 2;
+  const uint32_t total = (uint32_t)B * Ho * Wo;                 // < 2^31 (checked by the host)
+  const uint32_t n_tiles = (total + 127u) / 128u;
+  const int my_tiles = n_tiles > blockIdx.x ? (int)((n_tiles - 1 - blockIdx.x) / gridDim.x) + 1 : 0;
+
+  if (warp == 0) {
+    // ===================== UMMA issuer =====================
+    if (lane == 0) {
+      constexpr uint32_t idesc64 = ptx::idesc_bf16_f32(128, 64), idesc32 = ptx::idesc_bf16_f32(128, 32);
+      for (int t = 0; t < my_tiles; ++t) {
+        const int s = t % FWS_STAGES, as = t % FWS_EGROUPS;
+        ptx::mbar_wait(acc_empty(as), (((uint32_t)(t / FWS_EGROUPS)) & 1u) ^ 1u);
+        ptx::mbar_wait(a_full(s), ((uint32_t)(t / FWS_STAGES)) & 1u);
+        ptx::tc_fence_after();
+        const uint32_t a_hi = base + s * 32768, a_lo = a_hi + 16384, acc = tmem + as * 64;
+#pragma unroll
+        for (int ks = 0; ks < KSTEPS; ++ks) {
+          const uint64_t da_hi = ptx::smem_desc_kmajor<128>(a_hi + ks * 32);
+          const uint64_t da_lo = ptx::smem_desc_kmajor<128>(a_lo + ks * 32);
+          const uint64_t db = ptx::smem_desc_kmajor<128>(base + OFF_B + ks * 32);
+          ptx::umma_bf16(acc, da_hi, db, idesc64, ks > 0 ? 1u : 0u);      // hi x [W_hi ; W_lo] -> columns [0, 64)
+          ptx::umma_bf16(acc, da_lo, db, idesc32, 1u);                     // lo x W_hi          -> columns [0, 32)
+        }
+        ptx::umma_commit(a_empty(s));
+        ptx::umma_commit(acc_full(as));
+      }
+    }
+  } else if (warp < FWS_W_BUILD) {
+    // ===================== epilogue: thread = pixel row = TMEM lane; group eg drains accumulator stage eg =====================
+    const int q = warp & 3;                                      // the TMEM lane quarter this warp may read
+    const int eg = (warp - 1) >> 2;
+    const bool elected = ((warp - 1) & 3) == 0 && lane == 0;
+    const int row = q * 32 + lane;
+    __nv_bfloat16* out = reinterpret_cast<__nv_bfloat16*>(dst.base);
+    for (int t = eg; t < my_tiles; t += FWS_EGROUPS) {
+      const int as = eg;
+      const uint32_t i = ((uint32_t)blockIdx.x + (uint32_t)t * gridDim.x) * 128u + (uint32_t)row;
+      const bool live = i < total;
+      uint32_t xo = 0, yo = 0, b = 0;
+      if (live) {
+        xo = i % (uint32_t)Wo;
+        const uint32_t tt = i / (uint32_t)Wo;
+        yo = tt % (uint32_t)Ho;
+        b = tt / (uint32_t)Ho;
+      }
+      uint8_t* o = bulk ? nullptr
+                        : reinterpret_cast<uint8_t*>(
+                              out + ((((size_t)b * dst.h + yo + dst.y0) * dst.w + xo + dst.x0) * 3) * dst.c + dst.c0);
+      const int plane_b = bulk ? COUT * 2 : dst.c * 2;
+      ptx::mbar_wait(acc_full(as), ((uint32_t)(t / FWS_EGROUPS)) & 1u);
+      ptx::tc_fence_after();
+      const float r = r_buf[(t % FWS_RSLOTS) * 128 + row];
+      const uint32_t lane_base = tmem + ((uint32_t)(q * 32) << 16) + as * 64;
+      uint32_t a0[2][16], a1[2][16];
+      ptx::tmem_ld16(lane_base, a0[0]);
+      ptx::tmem_ld16(lane_base + 32, a1[0]);
+      ptx::tmem_ld16(lane_base + 16, a0[1]);
+      ptx::tmem_ld16(lane_base + 48, a1[1]);
+      ptx::tmem_ld_wait();
+      ptx::tc_fence_before();
+      __syncwarp();
+      if (lane == 0) ptx::mbar_arrive(acc_empty(as));            // the accumulator stage is in registers
+      if (bulk) {
+        // the group's previous store must have finished reading its staging buffer
+        if (elected) ptx::bulk_wait_read0();
+        ptx::named_barrier(1 + eg, 128);
+      }
+#pragma unroll
+      for (int c = 0; c < 2; ++c) {
+        const int c0 = c * 16;
+        float mu[16], var[16];
+#pragma unroll
+        for (int j = 0; j < 16; ++j) {
+          float m = __uint_as_float(a0[c][j]) + __uint_as_float(a1[c][j]);
+          float v = ss[c0 + j] * r;
+          if (relu) {
+            v = m > 0.f ? v : 0.f;
+            m = fmaxf(m, 0.f);
+          }
+          mu[j] = m;
+          var[j] = v;
+        }
+        if (live || bulk) {
+          uint32_t hi[8], lo[8], vr[8];
+#pragma unroll
+          for (int j = 0; j < 8; ++j) {
+            hi[j] = pk2(mu[2 * j], mu[2 * j + 1]);
+            lo[j] = pk2(mu[2 * j] - blo(hi[j]), mu[2 * j + 1] - bhi(hi[j]));
+            vr[j] = pk2(var[2 * j], var[2 * j + 1]);
+          }
+          if (bulk) {
+            // SWIZZLE_64B: 16-byte chunk bits [4,6) ^= address bits [7,9) (the staging buffers are 1 KB aligned)
+            const uint32_t stg = base + OFF_OUT + eg * FWS_TILE_OUT;
+            auto put = [&](int pl, const uint32_t (&w8)[8]) {
+              const uint32_t L = (uint32_t)row * 192u + (uint32_t)pl * 64u + (uint32_t)c0 * 2u;
+              const uint32_t x4 = ((L >> 7) & 3u) << 4;
+              ptx::st_shared_v4(stg + (L ^ x4), w8[0], w8[1], w8[2], w8[3]);
+              ptx::st_shared_v4(stg + ((L + 16u) ^ x4), w8[4], w8[5], w8[6], w8[7]);
+            };
+            put(0, hi);
+            put(1, lo);
+            put(2, vr);
+          } else if (v8) {
+            ptx::st_global_v8(o + c0 * 2, hi);
+            ptx::st_global_v8(o + plane_b + c0 * 2, lo);
+            ptx::st_global_v8(o + 2 * plane_b + c0 * 2, vr);
+          } else {
+            uint4* ph = reinterpret_cast<uint4*>(o + c0 * 2);
+            uint4* pl = reinterpret_cast<uint4*>(o + plane_b + c0 * 2);
+            uint4* pv = reinterpret_cast<uint4*>(o + 2 * plane_b + c0 * 2);
+            ph[0] = make_uint4(hi[0], hi[1], hi[2], hi[3]); ph[1] = make_uint4(hi[4], hi[5], hi[6], hi[7]);
+            pl[0] = make_uint4(lo[0], lo[1], lo[2], lo[3]); pl[1] = make_uint4(lo[4], lo[5], lo[6], lo[7]);
+            pv[0] = make_uint4(vr[0], vr[1], vr[2], vr[3]); pv[1] = make_uint4(vr[4], vr[5], vr[6], vr[7]);
+          }
+        }
+      }
+      if (bulk) {
+        ptx::fence_proxy_async();                                // generic-proxy writes of the staging buffer -> the bulk copy
+        ptx::named_barrier(1 + eg, 128);
+        if (elected) {
+          const uint32_t tile0 = ((uint32_t)blockIdx.x + (uint32_t)t * gridDim.x) * 128u;
+          asm volatile("cp.async.bulk.tensor.3d.global.shared::cta.bulk_group [%0, {%2, %3, %4}], [%1];" ::"l"(
+                           reinterpret_cast<uint64_t>(&dmap)),
+                       "r"(base + OFF_OUT + eg * FWS_TILE_OUT), "r"(0), "r"(0), "r"((int)tile0)
+                       : "memory");
+          ptx::bulk_commit_group();
+        }
+      }
+    }
+    if (bulk && elected) ptx::bulk_wait_read0();                 // the staging buffers must outlive the copies' reads
+  } else {
+    // ===================== builders: group g takes the CTA's tiles t = g, g + GROUPS, ... ; thread = pixel row =====================
+    const int g = (warp - FWS_W_BUILD) >> 2;
+    const int row = ((warp - FWS_W_BUILD) & 3) * 32 + lane;
+    for (int t = g; t < my_tiles; t += FWS_GROUPS) {
+      const int s = t % FWS_STAGES;
+      const uint32_t i = ((uint32_t)blockIdx.x + (uint32_t)t * gridDim.x) * 128u + (uint32_t)row;
+      const bool live = i < total;
+      uint32_t xo = 0, yo = 0, b = 0;
+      if (live) {
+        xo = i % (uint32_t)Wo;
+        const uint32_t tt = i / (uint32_t)Wo;
+        yo = tt % (uint32_t)Ho;
+        b = tt / (uint32_t)Ho;
+      }
+      float xv[KSTEPS * 16];
+#pragma unroll
+      for (int k = K; k < KSTEPS * 16; ++k) xv[k] = 0.f;
+#pragma unroll
+      for (int kh = 0; kh < 3; ++kh)
+#pragma unroll
+        for (int kw = 0; kw < 3; ++kw) {
+          const float* px = x + (((size_t)b * H + yo + kh) * W + xo + kw) * CIN;
+          if constexpr (CIN == 4) {
+            const float4 v = live ? __ldg(reinterpret_cast<const float4*>(px)) : make_float4(0.f, 0.f, 0.f, 0.f);
+            xv[(kh * 3 + kw) * 4 + 0] = v.x; xv[(kh * 3 + kw) * 4 + 1] = v.y;
+            xv[(kh * 3 + kw) * 4 + 2] = v.z; xv[(kh * 3 + kw) * 4 + 3] = v.w;
+          } else {
+#pragma unroll
+            for (int c = 0; c < CIN; ++c) xv[(kh * 3 + kw) * CIN + c] = live ? __ldg(px + c) : 0.f;
+          }
+        }
+      float r = 0.f;
+#pragma unroll
+      for (int k = 0; k < K; ++k) r = fmaf(xv[k], xv[k], r);
+      // the stage must have been drained by the UMMAs of the tile that used it FWS_STAGES tiles ago
+      ptx::mbar_wait(a_empty(s), (((uint32_t)(t / FWS_STAGES)) & 1u) ^ 1u);
+      uint8_t* rh = gen + s * 32768 + (row >> 3) * 1024 + (row & 7) * 128;
+      uint8_t* rl = rh + 16384;
+#pragma unroll
+      for (int c = 0; c < CHUNKS; ++c) {
+        uint32_t h[4], l[4];
+#pragma unroll
+        for (int e = 0; e < 4; ++e) {
+          const float f0 = xv[c * 8 + 2 * e], f1 = xv[c * 8 + 2 * e + 1];
+          h[e] = pk2(f0, f1);
+          l[e] = pk2(f0 - blo(h[e]), f1 - bhi(h[e]));
+        }
+        const int pc = (c ^ (row & 7)) << 4;
+        *reinterpret_cast<uint4*>(rh + pc) = make_uint4(h[0], h[1], h[2], h[3]);
+        *reinterpret_cast<uint4*>(rl + pc) = make_uint4(l[0], l[1], l[2], l[3]);
+      }
+      r_buf[(t % FWS_RSLOTS) * 128 + row] = r;
+      ptx::fence_proxy_async();                                  // this thread's generic-proxy writes -> the UMMA's async proxy
+      ptx::mbar_arrive(a_full(s));
+    }
+  }
+  ptx::tc_fence_before();
+  __syncthreads();
+  if (warp == 0) ptx::tmem_dealloc(tmem, FWS_TMEM_COLS);
+}
+
+// ---------------------------------------------------------------------------------------------------------
 // arg-max pooling on packed windows (Brats.py:171-174,206-216); thread = (output pixel, 8 channels)
 // ---------------------------------------------------------------------------------------------------------
 __global__ void maxpool_packed_kernel(sn_packed_view src, int B, int H, int W, int c, sn_packed_view dst) {
@@ -873,6 +1171,7 @@ int sn_first_conv_fwd_packed(int32_t batch, int32_t in_h, int32_t in_w, int32_t 
     const size_t cap = (size_t)num_sms() * FT_CTAS_PER_SM;
     const int grid = (int)(tiles < cap ? tiles : cap);
     int contiguous = dst->y0 == 0 && dst->x0 == 0 && dst->c0 == 0 && dst->h == Ho && dst->w == Wo && dst->c == cout;
+    const bool whole_buffer = contiguous != 0;
     // 2: every (pixel, plane, 16-channel chunk) segment of the destination is 32-byte aligned -> direct 256-bit stores
     static const bool first_v8 = [] {
       const char* e = getenv("SN_FIRST_V8");
@@ -880,6 +1179,52 @@ int sn_first_conv_fwd_packed(int32_t batch, int32_t in_h, int32_t in_w, int32_t 
     }();
     if (first_v8 && (reinterpret_cast<uintptr_t>(dst->base) & 31u) == 0 && dst->c % 16 == 0 && dst->c0 % 16 == 0)
       contiguous = 2;
+    // The warp-specialised form measures the SAME 0.141 ms as the one-role-per-CTA kernel at batch 64 (L2 flushed, A/B in
+    // one process, profiles/r02_session3.md): neither the overlap of the phases nor the store path is what bounds this
+    // layer, ~790 warp instructions per pixel row at ~43 % issue utilisation are.  It is therefore NOT the default;
+    // SN_TC_ROWS in `flags` or SN_FIRST_WS=1 selects it (parity-tested bit-identical), SN_TC_IM2COL forces the kernel above.
+    static const bool first_ws = [] {
+      const char* e = getenv("SN_FIRST_WS");
+      return e != nullptr && e[0] == '1';
+    }();
+    if ((first_ws || (flags & SN_TC_ROWS)) && !(flags & SN_TC_IM2COL) && pixels < (1ull << 31) - 128) {
+      static std::once_flag fws_once;
+      std::call_once(fws_once, [] {
+        cudaFuncSetAttribute(first_conv_ws_kernel<4>, cudaFuncAttributeMaxDynamicSharedMemorySize, FWS_SMEM);
+        cudaFuncSetAttribute(first_conv_ws_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, FWS_SMEM);
+      });
+      const size_t cap_ws = (size_t)num_sms();
+      const int grid_ws = (int)(tiles < cap_ws ? tiles : cap_ws);
+      const int v8 = contiguous == 2 ? 1 : 0;
+      static const bool first_bulk = [] {
+        const char* e = getenv("SN_FIRST_BULK");
+        return e == nullptr || e[0] != '0';
+      }();
+      int bulk = first_bulk && whole_buffer && aligned16(dst->base) ? 1 : 0;
+      CUtensorMap dmap{};
+      if (bulk) {
+        // the whole destination as (channel, plane, pixel): one box = a tile's 128 pixels x 3 planes x 32 channels
+        typedef CUresult (*EncFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*,
+                                  const cuuint64_t*, const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave,
+                                  CUtensorMapSwizzle, CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+        EncFn enc = reinterpret_cast<EncFn>(tensor_map_encoder());
+        cuuint64_t dims[3] = {32, 3, (cuuint64_t)pixels};
+        cuuint64_t strides[2] = {64, 192};
+        cuuint32_t box[3] = {32, 3, 128};
+        cuuint32_t estr[3] = {1, 1, 1};
+        if (enc == nullptr ||
+            enc(&dmap, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 3, dst->base, dims, strides, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
+                CU_TENSOR_MAP_SWIZZLE_64B, CU_TENSOR_MAP_L2_PROMOTION_L2_128B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE) != CUDA_SUCCESS)
+          bulk = 0;                          // no driver entry point: direct stores
+      }
+      if (cin == 4)
+        first_conv_ws_kernel<4><<<grid_ws, FW_THREADS_WS, FWS_SMEM, as_stream(st)>>>(dmap, batch, in_h, in_w, x, w_mu,
+                                                                                    w_sigma, *dst, relu, v8, bulk);
+      else
+        first_conv_ws_kernel<1><<<grid_ws, FW_THREADS_WS, FWS_SMEM, as_stream(st)>>>(dmap, batch, in_h, in_w, x, w_mu,
+                                                                                    w_sigma, *dst, relu, v8, bulk);
+      return check_launch("first_conv_ws");
+    }
     if (cin == 4)
       first_conv_tc_kernel<4><<<grid, FT_THREADS, FT_SMEM, as_stream(st)>>>(batch, in_h, in_w, x, w_mu, w_sigma, *dst,
                                                                             relu, contiguous);

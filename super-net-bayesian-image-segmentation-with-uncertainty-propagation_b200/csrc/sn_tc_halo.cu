@@ -1159,6 +1159,10 @@ static HlEncodeTiledFn hl_encode_tiled() {
   return fn;
 }
 
+// cuTensorMapEncodeTiled for the other translation units (sn_packed.cu: the first convolution's TMA store); nullptr when
+// the driver entry point is unavailable
+void* tensor_map_encoder() { return reinterpret_cast<void*>(hl_encode_tiled()); }
+
 struct HaloTiling {
   int R, THo, THb, TN, TWo, tiles_x, tiles_y, tiles_b;
   double eff;

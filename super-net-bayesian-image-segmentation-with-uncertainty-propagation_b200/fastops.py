@@ -150,12 +150,16 @@ def conv_moments_tc_head(src: PackedView, batch: int, in_h: int, in_w: int, w_pa
 
 
 def first_conv_packed(x: Tensor, w_mu: Tensor, w_sigma: Tensor, dst: PackedView, relu: bool = True,
-                      exact: bool = False) -> None:
-    """exact=True: the fp32 CUDA-core kernel instead of the tensor-core one (see SN_TC_EXACT in supernet.h)."""
+                      exact: bool = False, gen1: bool = False, ws: bool = False) -> None:
+    """exact=True: the fp32 CUDA-core kernel instead of the tensor-core one (see SN_TC_EXACT in supernet.h);
+    ws=True: the warp-specialised tensor-core kernel (SN_TC_ROWS; builder / UMMA / epilogue roles of one persistent CTA,
+    TMA-store epilogue), gen1=True: force the default one-role-per-CTA kernel (SN_TC_IM2COL).  Bit-identical results,
+    same measured time; both are kept for A/B measurements."""
     B, H, W, cin = x.shape
     k, _, _, cout = w_mu.shape
     v = dst.c_view()
-    flags = (SN_TC_RELU if relu else 0) | (SN_TC_EXACT if exact else 0)
+    flags = ((SN_TC_RELU if relu else 0) | (SN_TC_EXACT if exact else 0) | (SN_TC_IM2COL if gen1 else 0) |
+             (SN_TC_ROWS if ws else 0))
     check(_lib.load().sn_first_conv_fwd_packed(B, H, W, cin, cout, k, ptr(x), ptr(w_mu), ptr(w_sigma), C.byref(v),
                                                flags, stream_ptr()), "first_conv_fwd_packed")
 

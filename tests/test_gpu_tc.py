@@ -588,3 +588,34 @@ def test_conv_tc_head_rejects_what_it_cannot_fuse(S):
     assert not eng.head_fused and eng.step_names[-1] == "conv_final"
     with pytest.raises(RuntimeError, match="cannot end in the fused head"):
         InferenceEngine(model, 1, 64, 64, 1, "cuda", graph=False, fuse_head=True)
+
+
+@pytest.mark.parametrize("shape", [(2, 12, 14, 4), (3, 70, 90, 4), (2, 64, 64, 1), (2, 204, 204, 4), (1, 3, 3, 4)])
+@pytest.mark.parametrize("relu", [True, False])
+def test_first_conv_warp_specialised_is_bit_identical_to_gen1(S, shape, relu):
+    """The warp-specialised first convolution (builder / UMMA / epilogue roles of one persistent CTA) feeds the tensor cores
+    the same operands in the same order as the one-role-per-CTA kernel: same bits, inside a canary-filled window too."""
+    F = S.fastops
+    B, H, W, cin = shape
+    g = torch.Generator().manual_seed(B * 1000 + H + cin)
+    x = dev(torch.rand(B, H, W, cin, generator=g))
+    w = dev(torch.randn(3, 3, cin, 32, generator=g) * 0.1)
+    ws = dev(torch.empty(32).uniform_(-6, -2, generator=g))
+    Ho, Wo = H - 2, W - 2
+    ref = F.packed_empty(B, Ho, Wo, 32, "cuda")
+    F.first_conv_packed(x, w, ws, F.PackedView(ref), relu=relu, gen1=True)
+    out = torch.full_like(ref, -7.0)
+    for _ in range(2):
+        F.first_conv_packed(x, w, ws, F.PackedView(out), relu=relu, ws=True)       # whole buffer: TMA-store epilogue
+    big = torch.full((B, Ho + 3, Wo + 2, 3, 64), -7.0, device="cuda", dtype=torch.bfloat16)
+    F.first_conv_packed(x, w, ws, F.PackedView(big, 1, 2, 32), relu=relu, ws=True)   # a window: 256-bit stores
+    torch.cuda.synchronize()
+    assert torch.equal(out.view(torch.int16), ref.view(torch.int16))
+    assert torch.equal(big[:, 1:1 + Ho, 2:2 + Wo, :, 32:].view(torch.int16), ref.view(torch.int16))
+    big[:, 1:1 + Ho, 2:2 + Wo, :, 32:] = -7.0
+    assert bool((big == -7.0).all()), "a write landed outside the destination window"
+    m, v = F.unpack_moments(ref)
+    m_o, v_o = O.conv_input_conv_form(x.cpu().double(), w.cpu().double(), ws.cpu().double())
+    if relu:
+        m_o, v_o = O.relu(m_o, v_o)
+    assert rel(m, m_o) < 2e-5 and rel(v, v_o) < VAR_TOL
