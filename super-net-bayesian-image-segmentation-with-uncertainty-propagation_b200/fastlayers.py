@@ -14,12 +14,14 @@ like in engine.InferenceEngine, but decided at run time from how the handle is c
   myupsampling + 2x2 conv        -> four parity GEMMs scattered to (2y+a, 2x+b)              (Brats.py:178-203,414-415)
   myConc                         -> the consuming conv reads two source windows             (Brats.py:247-261)
   1x1 conv to n_labels + mysoftmax -> one kernel                                             (Brats.py:454-455)
+  3x3 conv 32 -> 32 + myReLU + that head -> ONE kernel (sn_conv_moments_fwd_tc_head)          (Brats.py:451-455)
 Anything outside those patterns still works through general packed kernels (sn_relu_packed, window copies).
 Inference only: the handles carry no autograd history (gradients: mode='fp32', or engine.GradientEngine).
 """
 from __future__ import annotations
 
 import ctypes as C
+import os
 from typing import Callable, Optional, Tuple
 
 import torch
@@ -55,6 +57,7 @@ class PackedMoments:
         self._op = op
         self._relu = relu
         self._relu_fusable = relu_fusable
+        self._conv_info = None          # pending single-source conv: (layer, source handle, h, w) -- what the fused head needs
 
     # ---- materialisation -------------------------------------------------------------------------------------
     def materialize(self, dst: Optional[PackedView] = None) -> PackedView:
@@ -145,6 +148,17 @@ class PendingHead:
         p = torch.empty((B, h * w, Cn), device=self.device, dtype=torch.float32)
         v = torch.empty_like(p)
         pre = (torch.empty_like(p), torch.empty_like(p)) if want_presoftmax else (None, None)
+        info = self.src._conv_info if isinstance(self.src, PackedMoments) else None
+        if (info is not None and self.src._view is None and self.src._relu and os.environ.get("SN_FUSE_HEAD", "1") != "0"
+                and F.tc_head_fusable(info[1].shape[3], 0, cin, info[0].kernel_size, True, Cn)):
+            # the producer is a still-pending 3x3 conv 32 -> 32 with its ReLU: run it WITH the head in its epilogue (the
+            # engines' last launch); the 32-channel tensor is not written -- the handle stays pending and can still
+            # materialise itself if somebody else asks for it.  Bit-identical to the two-kernel path.
+            layer, src, hin, win = info
+            wp, s = _prepared(layer, False)
+            sv = src.materialize()
+            F.conv_moments_tc_head(sv, B, hin, win, wp, s, wm.detach(), ws.detach(), p, v, pre[0], pre[1])
+            return p, v, pre
         F.final_conv_softmax_packed(self.src.materialize(), B, h, w, cin, wm.detach(), ws.detach(), p, v, pre[0], pre[1])
         return p, v, pre
 
@@ -230,6 +244,8 @@ def conv_intermediate(layer, mu, sigma) -> Tuple[object, object]:
                           src1=views[1][0] if len(views) > 1 else None, c1=views[1][1] if len(views) > 1 else 0)
 
     hdl = PackedMoments(out_shape, mu.device, op=op, relu=bool(layer.fuse_relu), relu_fusable=not layer.fuse_relu)
+    if len(srcs) == 1 and not upconv:
+        hdl._conv_info = (layer, srcs[0][0], h, w)
     return hdl, hdl
 
 
@@ -240,6 +256,7 @@ def relu(mu, sigma):
         raise RuntimeError("FAST mode: myReLU directly after myupsampling / myConc / the n_labels head is not supported")
     if mu._view is None and mu._relu_fusable and not mu._relu:
         out = PackedMoments(mu.shape, mu.device, op=mu._op, relu=True)          # epilogue flag of the pending conv
+        out._conv_info = mu._conv_info
         return out, out
     if mu._relu:                                                                # already gated: idempotent
         return mu, mu

@@ -151,8 +151,16 @@ def test_layerwise_fast_forward_equals_the_engine(S, variant, C, in_ch, B, alpha
     x = O.make_input(variant, B, alpha=alpha).cuda()
     with torch.no_grad():
         p, v, mf, sf = model(x, return_presoftmax=True)
-    p2, v2, mf2, sf2 = model.forward_layerwise_fast(x, return_presoftmax=True)
+    calls = []
+    orig = S.fastops.conv_moments_tc_head
+    S.fastops.conv_moments_tc_head = lambda *a, **k: (calls.append(1), orig(*a, **k))[1]
+    try:
+        p2, v2, mf2, sf2 = model.forward_layerwise_fast(x, return_presoftmax=True)
+    finally:
+        S.fastops.conv_moments_tc_head = orig
     assert torch.equal(p, p2) and torch.equal(v, v2) and torch.equal(mf, mf2) and torch.equal(sf, sf2)
+    # ... including the last launch: the pending 3x3 conv + ReLU + conv_final + softmax as ONE kernel
+    assert len(calls) >= 1
 
 
 def test_fast_handles_general_paths(S):
